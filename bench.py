@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""Benchmark of the CI wavefunction-overlap hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference ...                       # reference algorithm on host cores
+
+One "step" = one pass of the whole hot path over the workload: S_AO = Cinv Cinv^T,
+S_MO = C_bra S_AO C_ket^T, every (bra SD, ket SD) determinant and the CI-weighted
+reduction into the n_bra x n_ket matrix (+ the all-reduce for N > 1).
+Metric: determinant-pair overlaps per second, N_pairs = (K_bra+1)(K_ket+1).
+
+Workloads (BASELINE.json configs; seeds of SURVEY.md 8d):
+  c4 (default)  n_occ=100, n_mo=500, 50x50 states, full CIS space (K=40 000/side, 1.6e9 pairs)
+  c3            n_occ=34,  n_mo=180, 20x20 states, full space (K=4964), sigma=-1 (main.overlaps)
+  c2            n_occ=5,   n_mo=24,  10x10 states, full space (K=95)
+  c5            n_occ=64,  n_mo=320, 8x8 states,  K_b=K_k=1000 random excitations (1e6 pairs)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "c4": dict(seed=2, n_occ=100, n_mo=500, n_bra=50, n_ket=50, sigma=1.0, K=None,
+               desc="n_occ=100 n_mo=500 50x50 states, full CIS space"),
+    "c3": dict(seed=1, n_occ=34, n_mo=180, n_bra=20, n_ket=20, sigma=-1.0, K=None,
+               desc="n_occ=34 n_mo=180 20x20 states singlet->triplet, full CIS space"),
+    "c2": dict(seed=0, n_occ=5, n_mo=24, n_bra=10, n_ket=10, sigma=1.0, K=None,
+               desc="n_occ=5 n_mo=24 10x10 states, full CIS space"),
+    "c5": dict(seed=3, n_occ=64, n_mo=320, n_bra=8, n_ket=8, sigma=1.0, K=1000,
+               desc="n_occ=64 n_mo=320 8x8 states, 1000x1000 random excitations"),
+}
+
+
+def f_det(n):
+    """Algorithmic flops of one partially pivoted LU determinant."""
+    return n * (n - 1) // 2 + n * (n - 1) * (2 * n - 1) // 3 + (n - 1)
+
+
+def make_inputs(w, top_k=None, n_states=None):
+    from pywfo_b200 import helpers
+    nb = n_states or w["n_bra"]
+    nk = n_states or w["n_ket"]
+    if top_k is None and w["K"] is not None:
+        return helpers.synthetic_case(w["seed"], w["n_mo"], w["n_occ"], nb, nk, shared_k=w["K"])
+    return helpers.synthetic_case(w["seed"], w["n_mo"], w["n_occ"], nb, nk, top_k=top_k)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU during the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join(2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------- CPU baseline
+def cpu_baseline_run(w, budget_s=20.0):
+    """Reference algorithm (oracle port of pywfo.main.overlaps_cache / overlaps: memoised
+    np.linalg.det per unique pair + the Python double loop) on a bounded, truncated instance
+    of the workload.  Returns (pairs_per_s, seconds, sample description, unique pairs)."""
+    from oracle import pywfo_oracle as orc
+    n = w["n_occ"]
+    full_k = n * (w["n_mo"] - n)
+    # per unique determinant ~ (7 + n^2/115) us, per loop term ~0.5 us: size the sample
+    t_det = (7.0 + n * n / 115.0) * 1e-6
+    ns = 3 if w["n_bra"] >= 3 else w["n_bra"]
+    k = 100
+    while k > 8 and (ns * k) ** 2 * t_det + ns * ns * 4 * k * k * 0.6e-6 > budget_s:
+        k //= 2
+    k = min(k, full_k)
+    bra_mos, ket_mos, bci, kci = make_inputs(w, top_k=k, n_states=ns)
+    t0 = time.perf_counter()
+    if w["sigma"] > 0:
+        _, n_unique = orc.ref_overlaps_cache(bra_mos, ket_mos, bci, kci, n, 1e-12)
+    else:
+        orc.ref_overlaps_minus(bra_mos, ket_mos, bci, kci, n, 1e-12)
+        kb = int((np.abs(bci) > 1e-12).any(axis=0).sum())
+        kk = int((np.abs(kci) > 1e-12).any(axis=0).sum())
+        n_unique = (kb + 1) * (kk + 1)
+    dt = time.perf_counter() - t0
+    sample = (f"oracle port of pywfo.main.{'overlaps_cache' if w['sigma'] > 0 else 'overlaps'} on "
+              f"{ns}x{ns} states, top-{k} excitations/state of the same MOs: {n_unique} unique "
+              f"determinants + Python reduction loop, {dt:.1f} s")
+    return n_unique / dt, dt, sample, n_unique
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    vals = []
+    sample = ""
+    for i in range(args.warmup + args.steps):
+        v, dt, sample, n_unique = cpu_baseline_run(w, budget_s=args.cpu_budget)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([dt for _, dt in vals])) * 1e3
+    cores = blas_threads()
+    line = {
+        "impl": "reference", "metric": "determinant-pair overlaps/sec", "value": value, "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {w['desc']} (bounded sample per step)"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "host_cores": os.cpu_count(),
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args, w):
+    import torch
+    import torch.distributed as dist
+    from pywfo_b200 import _lib, excitations as ex, main as wmain
+    from pywfo_b200 import dist as wdist
+
+    rank, world = wdist.init_from_env()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ctx = _lib.context(local)
+    n, n_mo = w["n_occ"], w["n_mo"]
+    sigma = w["sigma"]
+    tier = args.tier
+
+    # ---- synthetic inputs (host), tables (host), upload
+    bra_mos, ket_mos, bci, kci = make_inputs(w)
+    thr = 0.0 if w["K"] is None else 1e-12
+    sem = "cache" if sigma > 0 else "minus"
+    bt = ex.build_tables(bci, thr, sem)
+    kt = ex.build_tables(kci, thr, sem, order="locality")
+    Kb, Kk = bt.K, kt.K
+    n_pairs = (Kb + 1) * (Kk + 1)
+    lo, hi = ex.shard_bounds(Kb, world, rank)
+    c_inv = np.linalg.inv(ket_mos)
+    f64 = dict(dtype=torch.float64, device=dev)
+    d_bra, d_ket, d_inv = (torch.tensor(x, **f64) for x in (bra_mos, ket_mos, c_inv))
+    d_sao, d_smo = torch.empty((n_mo, n_mo), **f64), torch.empty((n_mo, n_mo), **f64)
+    d_be = torch.tensor(bt.exc, dtype=torch.int32, device=dev)
+    d_ke = torch.tensor(kt.exc, dtype=torch.int32, device=dev)
+    d_cb, d_ck = torch.tensor(bt.coeff, **f64), torch.tensor(kt.coeff, **f64)
+    d_out = torch.empty((bt.coeff.shape[0], kt.coeff.shape[0]), **f64)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx.set_timing(True)
+
+    def step():
+        ctx.sao_dev(d_inv, d_sao, stream)
+        ctx.smo_dev(d_bra, d_sao, d_ket, d_smo, stream)
+        ctx.state_overlaps_dev(d_smo, n, d_be, d_cb, d_ke, d_ck, d_out, sigma=sigma, tier=tier,
+                               k_begin=lo, k_end=hi, stream=stream)
+        if world > 1:
+            dist.all_reduce(d_out, op=dist.ReduceOp.SUM)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    result_first = d_out.cpu().numpy().copy()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ctx.launch_count()
+    step_ms, kern_ms = [], []
+    barrier()
+    for _ in range(args.steps):
+        flush.fill_(1)                      # L2 flush between timed iterations (outside the timed region)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        barrier()
+        step_ms.append(e0.elapsed_time(e1))
+        kern_ms.append(ctx.last_kernel_ms())
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop()
+    used_tier = ctx.last_tier()
+    t_local = torch.tensor([float(np.sum(step_ms))], **f64)
+    if world > 1:
+        dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
+    total_ms = float(t_local.item())
+    ms_per_step = total_ms / args.steps
+    value = n_pairs * args.steps / (total_ms * 1e-3)
+
+    # ---- parity beside the timing (every rank holds the full matrix after the all-reduce)
+    parity = None
+    if rank == 0 and args.check:
+        from oracle import pywfo_oracle as orc   # checker only
+        S = orc.mo_overlap(bra_mos, ket_mos, orc.get_S_AO(bra_mos, ket_mos, "ket"))
+        if w["K"] is None:
+            if sigma > 0:
+                want = orc.state_overlaps_factored(S, n, orc.signed_ci(bci, n), orc.signed_ci(kci, n), sigma)
+            else:   # "minus" semantics: coefficient factor ((-1)^(occ-f+1))^occ on top of the appended sign
+                q = (((-1.0) ** (n - np.arange(n) + 1)) ** n)[None, :, None]
+                want = orc.state_overlaps_factored(S, n, orc.signed_ci(bci * q, n), orc.signed_ci(kci * q, n), sigma)
+        else:
+            want = orc.state_overlaps_closed_form(S, n, [tuple(e) for e in bt.exc], bt.coeff,
+                                                  [tuple(e) for e in kt.exc], kt.coeff, sigma)
+        scale = np.abs(want).max()
+        err = float(np.abs(result_first - want).max() / scale)
+        big = np.abs(want) > 1e-10 * scale
+        parity = {"max_rel_err": err, "signs_equal": bool(np.array_equal(np.sign(result_first[big]), np.sign(want[big]))),
+                  "checker": "oracle closed form (numpy/LAPACK), same inputs"}
+
+    # ---- e2e: the public Python entry point on HOST arrays (inv, thresholding, H2D, kernels, D2H)
+    fn = wmain.overlaps_cache if sigma > 0 else wmain.overlaps
+    e2e_times = []
+    for i in range(1 + args.e2e_steps):
+        barrier()
+        t0 = time.perf_counter()
+        res = fn(bra_mos, ket_mos, bci, kci, n, ci_thresh=thr, ao_ovlps="ket", tier=tier)
+        barrier()
+        if i > 0:
+            e2e_times.append(time.perf_counter() - t0)
+    t_e2e = torch.tensor([float(np.mean(e2e_times))], **f64)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_s = float(t_e2e.item())
+    h2d = 3 * n_mo * n_mo * 8 + bt.exc.nbytes + kt.exc.nbytes + bt.coeff.nbytes + kt.coeff.nbytes
+    d2h = int(res.nbytes)
+    e2e_err = float(np.abs(res - result_first).max() / max(np.abs(result_first).max(), 1e-300))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (device time from CUDA events inside the library,
+    #      recorded on the launching stream around that kernel only)
+    peaks = {"dfma": ctx.fp64_peak(0, 8192), "dmma884": ctx.fp64_peak(1, 8192)}
+    peak = max(peaks.values())
+    pairs_shard = (hi - lo) * Kk
+    k_ms = float(np.mean(kern_ms))
+    if used_tier == 1:
+        flops_pair = 2 * w["n_ket"] + 3
+        kname = "t1_fused_kernel (rank-1 update pair determinants + DMMA CI contraction)"
+    else:
+        flops_pair = f_det(n) + 2 * w["n_ket"]
+        kname = "t0_fused_kernel (pivoted LU per pair + CI contraction)"
+    achieved = pairs_shard * flops_pair / (k_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": "measured in this run: max of register-resident DFMA loop and DMMA.8x8x4 loop "
+                               "(MEASURED_PEAKS.json has no FP64 entry)",
+                "fp64_peaks_tflops": peaks, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
+                "algorithmic_flops_per_pair": flops_pair,
+                "hbm_algorithmic_bytes": int(h2d + d2h), "hbm_peak_gbs": hbm_peak()}
+
+    # ---- the brute-force determinant kernel (T0) on a bounded sample of the same workload
+    kernels = {}
+    if args.t0_sample > 0:
+        ks = min(Kb, max(1, args.t0_sample // 64))
+        kl = min(Kk, 64)
+        d_ke_s, d_ck_s = d_ke[:kl].contiguous(), d_ck[:, :kl].contiguous()
+        for _ in range(2):
+            ctx.state_overlaps_dev(d_smo, n, d_be, d_cb, d_ke_s, d_ck_s, d_out, sigma=sigma, tier="lu",
+                                   k_begin=0, k_end=ks, stream=stream)
+        torch.cuda.synchronize()
+        t0_ms = []
+        for _ in range(3):
+            ctx.state_overlaps_dev(d_smo, n, d_be, d_cb, d_ke_s, d_ck_s, d_out, sigma=sigma, tier="lu",
+                                   k_begin=0, k_end=ks, stream=stream)
+            torch.cuda.synchronize()
+            t0_ms.append(ctx.last_kernel_ms())
+        t0m = float(np.mean(t0_ms))
+        fl = ks * kl * (f_det(n) + 2 * w["n_ket"])
+        kernels["t0_lu_per_pair"] = {
+            "pairs": ks * kl, "kernel_ms": t0m, "pairs_per_s": ks * kl / (t0m * 1e-3),
+            "achieved_tflops": fl / (t0m * 1e-3) / 1e12, "frac_of_fp64_peak": fl / (t0m * 1e-3) / 1e12 / peak,
+            "flops_per_pair": f_det(n) + 2 * w["n_ket"],
+            "note": "brute-force tier on a sample of the same workload; full workload at this rate: "
+                    f"{n_pairs / (ks * kl / (t0m * 1e-3)):.1f} s"}
+
+    cpu = None
+    if world == 1 and args.cpu_budget > 0:
+        v, dt, sample, _ = cpu_baseline_run(w, budget_s=args.cpu_budget)
+        cpu = {"value": v, "unit": "pairs/s", "cores": blas_threads(), "kind": "port", "sample": sample}
+
+    line = {
+        "metric": "determinant-pair overlaps/sec", "value": value, "unit": "pairs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {w['desc']}", "n_occ": n, "n_mo": n_mo, "n_bra": w["n_bra"],
+                   "n_ket": w["n_ket"], "K_bra": Kb, "K_ket": Kk, "pairs": n_pairs, "sigma": sigma,
+                   "tier": {0: "lu", 1: "update"}.get(used_tier, str(used_tier)), "parallelism": f"bra-shard x{world}",
+                   "l2": "flushed (256 MB write) between timed steps; inputs 38 MB < L2"},
+        "wall_ms_per_matrix": ms_per_step,
+        "clocks": clocks,
+        "e2e": {"value": n_pairs / e2e_s, "unit": "pairs/s", "ms_per_call": e2e_s * 1e3,
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
+                "call": f"pywfo_b200.main.{'overlaps_cache' if sigma > 0 else 'overlaps'}(host numpy arrays)",
+                "max_rel_diff_vs_device_leg": e2e_err},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "parity": parity,
+        "kernels": kernels,
+        "host_cores": os.cpu_count(),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def hbm_peak():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        return 6650.0   # B200_PROFILING.md fallback
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--tier", default="auto", choices=["auto", "lu", "update"])
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--t0-sample", type=int, default=16384, help="pairs in the brute-force sample leg (0 = skip)")
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU baseline work (0 = skip)")
+    ap.add_argument("--no-check", dest="check", action="store_false")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, w)
+    return run_ours(args, w)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

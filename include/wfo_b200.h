@@ -1,0 +1,134 @@
+/*
+ * wfo_b200.h -- C ABI of the B200-native CI wavefunction-overlap hot path.
+ *
+ * pywfo (the reference) has no FFI: its boundary is the Python signature
+ *   overlaps | overlaps_naive | overlaps_most_naive | overlaps_cache
+ *       (bra_mos, ket_mos, bra_ci, ket_ci, occ, ci_thresh, ao_ovlps)   pywfo/main.py:81,314,422,520
+ *   moovlp | moovlp_expl | moovlp_dots (mos1, mos2, S_AO)              pywfo/main.py:27,46,72
+ *   dets.wfoverlap(bra_mos, ket_mos, bra_ci, ket_ci, ci_thresh, S_AO)   pywfo/dets.py:201
+ * pywfo_b200/main.py and pywfo_b200/dets.py keep those signatures and bind the
+ * functions below through ctypes (INTEGRATION.md shows the stub a pywfo
+ * maintainer would add).  Each entry point names the reference lines it replaces.
+ *
+ * Conventions
+ *   - all matrices row-major float64, index tables int32
+ *   - an excitation is the pair (from, to): from in [0, n_occ), to in [0, n_virt)
+ *     relative to n_occ; its MO index list is [0..n_occ-1] minus from, then
+ *     n_occ+to APPENDED (pywfo/main.py:565-576).  (-1,-1) is the ground state.
+ *   - *_dev functions take DEVICE pointers and a cudaStream_t (as void*), run
+ *     asynchronously on that stream and never copy to/from the host
+ *   - *_host functions take HOST pointers, do the H2D/D2H copies themselves
+ *     and return after the result is in host memory
+ *   - return value: 0 on success, non-zero on error; wfo_last_error() then
+ *     holds a message (thread-local).  There is no CPU fallback: without a
+ *     CUDA device every compute entry point fails.
+ */
+#ifndef WFO_B200_H
+#define WFO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WFO_OK 0
+#define WFO_ERR_CUDA 1
+#define WFO_ERR_ARG 2
+#define WFO_ERR_SINGULAR 3 /* base block S_MO[:occ,:occ] singular: tier 1/2 not applicable */
+
+/* algorithm tiers (identical results to ~1e-13) */
+#define WFO_TIER_LU 0      /* T0: one partially pivoted LU per determinant pair          */
+#define WFO_TIER_UPDATE 1  /* T1: one base LU + rank-1 row/column update per pair        */
+#define WFO_TIER_CLOSED 2  /* T2: closed-form contraction, pair determinants not formed  */
+#define WFO_TIER_AUTO (-1) /* T1, falling back to T0 when the base block is singular      */
+
+typedef struct wfo_ctx wfo_ctx;
+
+/* ---- housekeeping -------------------------------------------------------- */
+int wfo_version(void);
+const char *wfo_last_error(void);
+int wfo_device_count(void);
+/* One context per (process, device): scratch memory, SM count, a private stream
+ * for the *_host entry points. */
+int wfo_create(int device, wfo_ctx **out);
+int wfo_destroy(wfo_ctx *ctx);
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+long long wfo_launch_count(const wfo_ctx *ctx);
+
+/* ---- stage 1: MO overlap  S_MO = C_bra S_AO C_ket^T ------------------------
+ * replaces pywfo/main.py:532 (and moovlp main.py:27-43, moovlp_expl :46-68,
+ * moovlp_dots :71-78, dets.py:264).  bra_mos (p x u), s_ao (u x v), ket_mos
+ * (q x v) -> s_mo (p x q).  FP64 tensor-core (DMMA) GEMM chain; `work` is a
+ * device scratch of p*v doubles (may be NULL: taken from the context). */
+int wfo_smo_dev(wfo_ctx *ctx, const double *bra_mos, const double *s_ao, const double *ket_mos,
+                int p, int u, int v, int q, double *s_mo, double *work, void *stream);
+int wfo_smo_host(wfo_ctx *ctx, const double *bra_mos, const double *s_ao, const double *ket_mos,
+                 int p, int u, int v, int q, double *s_mo);
+/* S_AO = Cinv Cinv^T, replaces the product in pywfo/main.py:304 (the inverse
+ * itself stays numpy/LAPACK on the host, as in the reference). */
+int wfo_sao_dev(wfo_ctx *ctx, const double *c_inv, int n, double *s_ao, void *stream);
+/* generic C = alpha*op(A) op(B) + beta*C (row-major; ta/tb: 0 = N, 1 = T) */
+int wfo_gemm_dev(wfo_ctx *ctx, int ta, int tb, int m, int n, int k, double alpha, const double *A,
+                 int lda, const double *B, int ldb, double beta, double *C, int ldc, void *stream);
+
+/* ---- stage 2: determinant table for explicit index lists --------------------
+ * replaces pywfo/main.py:579-585 (sd_ovlp) and pywfo/dets.py:191-198
+ * (precompute): D[k][l] = det(S_MO[rows[k]][:, cols[l]]), rows (kb x n),
+ * cols (kk x n), partially pivoted LU per pair.  Test/bench entry: the product
+ * path never materialises D (see wfo_state_overlaps_*). */
+int wfo_det_table_dev(wfo_ctx *ctx, const double *s_mo, int n_mo, int ld_smo, int n,
+                      const int32_t *rows, int kb, const int32_t *cols, int kk, double *D,
+                      void *stream);
+int wfo_det_table_host(wfo_ctx *ctx, const double *s_mo, int n_mo, int n, const int32_t *rows,
+                       int kb, const int32_t *cols, int kk, double *D);
+/* excitation tables -> appended-order index lists (pywfo/main.py:565-576) */
+int wfo_exc_lists_dev(wfo_ctx *ctx, const int32_t *exc, int k, int n_occ, int32_t *lists,
+                      void *stream);
+
+/* ---- stages 2+3 fused: state-overlap matrix --------------------------------
+ * replaces the loops pywfo/main.py:587-626 (sigma=+1) and main.py:170-197
+ * (sigma=-1) and the contraction pywfo/dets.py:279-283:
+ *   out[i][j] = sum_{k in [k_begin,k_end)} sum_l Cb[i][k] Ck[j][l]
+ *               ( D(0,0) D(k,l) + sigma D(k,0) D(0,l) )
+ * bra_exc (kb x 2), ket_exc (kk x 2) int32 excitation tables, Cb (n_bra x kb),
+ * Ck (n_ket x kk) coefficient matrices (thresholding, 1/sqrt2 and the sign
+ * conventions of each reference entry point are folded in by the caller, see
+ * pywfo_b200/excitations.py).  [k_begin,k_end) is this rank's shard of the bra
+ * excitations; partial results of all shards add up to the full matrix (one
+ * all-reduce).  Per-pair determinants never leave registers/shared memory.
+ * `out` (n_bra x n_ket) is overwritten.  tier: WFO_TIER_*. */
+int wfo_state_overlaps_dev(wfo_ctx *ctx, const double *s_mo, int n_mo, int n_occ,
+                           const int32_t *bra_exc, int kb, const double *Cb, int n_bra,
+                           const int32_t *ket_exc, int kk, const double *Ck, int n_ket,
+                           double sigma, int tier, int k_begin, int k_end, double *out,
+                           void *stream);
+int wfo_state_overlaps_host(wfo_ctx *ctx, const double *s_mo, int n_mo, int n_occ,
+                            const int32_t *bra_exc, int kb, const double *Cb, int n_bra,
+                            const int32_t *ket_exc, int kk, const double *Ck, int n_ket,
+                            double sigma, int tier, int k_begin, int k_end, double *out);
+/* The whole path from host buffers in one call (what pywfo_b200.main.overlaps_*
+ * uses): S_AO = c_inv c_inv^T, S_MO = bra S_AO ket^T, then the fused stages. */
+int wfo_overlaps_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos,
+                      const double *c_inv, int n_mo, int n_occ, const int32_t *bra_exc, int kb,
+                      const double *Cb, int n_bra, const int32_t *ket_exc, int kk,
+                      const double *Ck, int n_ket, double sigma, int tier, int k_begin,
+                      int k_end, double *out);
+/* tier actually used by the last wfo_state_overlaps_* call of this context */
+int wfo_last_tier(const wfo_ctx *ctx);
+/* device time (ms, CUDA events on the launching stream) of the dominant
+ * determinant kernel of the last wfo_state_overlaps_* call made with timing on */
+int wfo_set_timing(wfo_ctx *ctx, int on);
+double wfo_last_kernel_ms(const wfo_ctx *ctx);
+
+/* ---- measurement helpers (bench.py roofline denominators) ------------------
+ * MEASURED_PEAKS.json has no FP64 entry, so the harness measures it in-run:
+ * kind 0 = register-resident DFMA loop, kind 1 = DMMA m8n8k4 loop,
+ * kind 2 = DMMA m16n8k8 loop.  Returns TFLOP/s. */
+int wfo_fp64_peak(wfo_ctx *ctx, int kind, int iters, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WFO_B200_H */

@@ -1,0 +1,233 @@
+"""ctypes binding of libwfo_b200.so (include/wfo_b200.h).
+
+There is no CPU fallback: if the library is missing or no B200 is visible the
+compute entry points raise.  The library is built in-tree by
+``pywfo_b200/build.py`` (``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libwfo_b200.so")
+
+TIER_AUTO, TIER_LU, TIER_UPDATE, TIER_CLOSED = -1, 0, 1, 2
+TIERS = {"auto": TIER_AUTO, "lu": TIER_LU, "update": TIER_UPDATE, "closed": TIER_CLOSED,
+         None: TIER_AUTO, -1: TIER_AUTO, 0: TIER_LU, 1: TIER_UPDATE, 2: TIER_CLOSED}
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int32)
+c_vp = C.c_void_p
+
+# name -> (restype, argtypes); every symbol include/wfo_b200.h declares
+SIGNATURES = {
+    "wfo_version": (C.c_int, []),
+    "wfo_last_error": (C.c_char_p, []),
+    "wfo_device_count": (C.c_int, []),
+    "wfo_create": (C.c_int, [C.c_int, C.POINTER(c_vp)]),
+    "wfo_destroy": (C.c_int, [c_vp]),
+    "wfo_launch_count": (C.c_longlong, [c_vp]),
+    "wfo_smo_dev": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
+    "wfo_smo_host": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_vp]),
+    "wfo_sao_dev": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, c_vp]),
+    "wfo_gemm_dev": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, c_vp, C.c_int,
+                               c_vp, C.c_int, C.c_double, c_vp, C.c_int, c_vp]),
+    "wfo_det_table_dev": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, c_vp, C.c_int, c_vp, c_vp]),
+    "wfo_det_table_host": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, c_vp, C.c_int, c_vp, C.c_int, c_vp]),
+    "wfo_exc_lists_dev": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp]),
+    "wfo_state_overlaps_dev": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, c_vp, C.c_int, c_vp, C.c_int, c_vp, C.c_int,
+                                         c_vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
+    "wfo_state_overlaps_host": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, c_vp, C.c_int, c_vp, C.c_int, c_vp, C.c_int,
+                                          c_vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, c_vp]),
+    "wfo_overlaps_host": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, C.c_int, c_vp, C.c_int, c_vp,
+                                    C.c_int, c_vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, c_vp]),
+    "wfo_last_tier": (C.c_int, [c_vp]),
+    "wfo_set_timing": (C.c_int, [c_vp, C.c_int]),
+    "wfo_last_kernel_ms": (C.c_double, [c_vp]),
+    "wfo_fp64_peak": (C.c_int, [c_vp, C.c_int, C.c_int, c_dp]),
+}
+
+
+class WfoError(RuntimeError):
+    pass
+
+
+_lib = None
+_lock = threading.Lock()
+_contexts: dict[int, "Context"] = {}
+
+
+def load():
+    """dlopen the in-tree library and attach the prototypes.  Raises if absent."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise WfoError(
+                    f"{LIB_PATH} is missing: build it with `python -m pywfo_b200.build` "
+                    "(there is no CPU fallback)")
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = load().wfo_last_error().decode("utf-8", "replace")
+        raise WfoError(f"wfo_b200 error {rc}: {msg}")
+
+
+def _hptr(a: np.ndarray):
+    return a.ctypes.data_as(c_vp)
+
+
+def as_f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def as_i32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Context:
+    """One per (process, device); owns the device scratch arena."""
+
+    def __init__(self, device: int = 0):
+        lib = load()
+        if lib.wfo_device_count() <= 0:
+            raise WfoError("no CUDA device visible: pywfo_b200 has no CPU fallback")
+        h = c_vp()
+        check(lib.wfo_create(device, C.byref(h)))
+        self.lib, self.handle, self.device = lib, h, device
+
+    def close(self):
+        if self.handle:
+            self.lib.wfo_destroy(self.handle)
+            self.handle = None
+
+    # ---- host-pointer entry points -------------------------------------------
+    def smo_host(self, bra_mos, s_ao, ket_mos):
+        bra, s, ket = as_f64(bra_mos), as_f64(s_ao), as_f64(ket_mos)
+        p, u = bra.shape
+        q, v = ket.shape
+        if s.shape != (u, v):
+            raise ValueError(f"S_AO has shape {s.shape}, expected {(u, v)}")
+        out = np.empty((p, q))
+        check(self.lib.wfo_smo_host(self.handle, _hptr(bra), _hptr(s), _hptr(ket), p, u, v, q, _hptr(out)))
+        return out
+
+    def det_table_host(self, s_mo, rows, cols):
+        s = as_f64(s_mo)
+        r, c = as_i32(rows), as_i32(cols)
+        n = r.shape[1]
+        if c.shape[1] != n or s.shape[0] != s.shape[1]:
+            raise ValueError("rows/cols must be (K, n) lists and S_MO square")
+        out = np.empty((r.shape[0], c.shape[0]))
+        check(self.lib.wfo_det_table_host(self.handle, _hptr(s), s.shape[0], n, _hptr(r), r.shape[0],
+                                          _hptr(c), c.shape[0], _hptr(out)))
+        return out
+
+    def state_overlaps_host(self, s_mo, n_occ, bra_exc, Cb, ket_exc, Ck, sigma=1.0, tier="auto",
+                            k_begin=0, k_end=None):
+        s = as_f64(s_mo)
+        be, ke = as_i32(bra_exc).reshape(-1, 2), as_i32(ket_exc).reshape(-1, 2)
+        cb, ck = as_f64(Cb), as_f64(Ck)
+        kb, kk = be.shape[0], ke.shape[0]
+        if cb.shape[1] != kb or ck.shape[1] != kk:
+            raise ValueError("coefficient matrices do not match the excitation tables")
+        k_end = kb if k_end is None else k_end
+        out = np.empty((cb.shape[0], ck.shape[0]))
+        check(self.lib.wfo_state_overlaps_host(self.handle, _hptr(s), s.shape[0], int(n_occ), _hptr(be), kb,
+                                               _hptr(cb), cb.shape[0], _hptr(ke), kk, _hptr(ck), ck.shape[0],
+                                               float(sigma), TIERS[tier], int(k_begin), int(k_end), _hptr(out)))
+        return out
+
+    def overlaps_host(self, bra_mos, ket_mos, c_inv, n_occ, bra_exc, Cb, ket_exc, Ck, sigma=1.0, tier="auto",
+                      k_begin=0, k_end=None, out=None):
+        bra, ket, inv = as_f64(bra_mos), as_f64(ket_mos), as_f64(c_inv)
+        n_mo = bra.shape[0]
+        if bra.shape != (n_mo, n_mo) or ket.shape != (n_mo, n_mo) or inv.shape != (n_mo, n_mo):
+            raise ValueError("MO matrices must be square and of equal shape")
+        be, ke = as_i32(bra_exc).reshape(-1, 2), as_i32(ket_exc).reshape(-1, 2)
+        cb, ck = as_f64(Cb), as_f64(Ck)
+        kb, kk = be.shape[0], ke.shape[0]
+        if cb.shape[1] != kb or ck.shape[1] != kk:
+            raise ValueError("coefficient matrices do not match the excitation tables")
+        k_end = kb if k_end is None else k_end
+        if out is None:
+            out = np.empty((cb.shape[0], ck.shape[0]))
+        check(self.lib.wfo_overlaps_host(self.handle, _hptr(bra), _hptr(ket), _hptr(inv), n_mo, int(n_occ),
+                                         _hptr(be), kb, _hptr(cb), cb.shape[0], _hptr(ke), kk, _hptr(ck),
+                                         ck.shape[0], float(sigma), TIERS[tier], int(k_begin), int(k_end),
+                                         _hptr(out)))
+        return out
+
+    # ---- device-pointer entry points (torch tensors used only as memory) ------
+    def smo_dev(self, bra, s_ao, ket, out, stream=0):
+        p, u = bra.shape
+        q, v = ket.shape
+        check(self.lib.wfo_smo_dev(self.handle, bra.data_ptr(), s_ao.data_ptr(), ket.data_ptr(), p, u, v, q,
+                                   out.data_ptr(), None, stream))
+
+    def sao_dev(self, c_inv, out, stream=0):
+        check(self.lib.wfo_sao_dev(self.handle, c_inv.data_ptr(), c_inv.shape[0], out.data_ptr(), stream))
+
+    def gemm_dev(self, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, Cm, ldc, stream=0):
+        check(self.lib.wfo_gemm_dev(self.handle, int(ta), int(tb), m, n, k, float(alpha), A.data_ptr(), lda,
+                                    B.data_ptr(), ldb, float(beta), Cm.data_ptr(), ldc, stream))
+
+    def det_table_dev(self, s_mo, n, rows, cols, out, stream=0):
+        check(self.lib.wfo_det_table_dev(self.handle, s_mo.data_ptr(), s_mo.shape[0], s_mo.stride(0), n,
+                                         rows.data_ptr(), rows.shape[0], cols.data_ptr(), cols.shape[0],
+                                         out.data_ptr(), stream))
+
+    def exc_lists_dev(self, exc, n_occ, lists, stream=0):
+        check(self.lib.wfo_exc_lists_dev(self.handle, exc.data_ptr(), exc.shape[0], n_occ, lists.data_ptr(), stream))
+
+    def state_overlaps_dev(self, s_mo, n_occ, bra_exc, Cb, ket_exc, Ck, out, sigma=1.0, tier="auto",
+                           k_begin=0, k_end=None, stream=0):
+        kb, kk = bra_exc.shape[0], ket_exc.shape[0]
+        k_end = kb if k_end is None else k_end
+        check(self.lib.wfo_state_overlaps_dev(self.handle, s_mo.data_ptr(), s_mo.shape[0], int(n_occ),
+                                              bra_exc.data_ptr(), kb, Cb.data_ptr(), Cb.shape[0],
+                                              ket_exc.data_ptr(), kk, Ck.data_ptr(), Ck.shape[0], float(sigma),
+                                              TIERS[tier], int(k_begin), int(k_end), out.data_ptr(), stream))
+
+    # ---- bookkeeping -----------------------------------------------------------
+    def launch_count(self) -> int:
+        return int(self.lib.wfo_launch_count(self.handle))
+
+    def last_tier(self) -> int:
+        return int(self.lib.wfo_last_tier(self.handle))
+
+    def set_timing(self, on: bool):
+        check(self.lib.wfo_set_timing(self.handle, int(on)))
+
+    def last_kernel_ms(self) -> float:
+        return float(self.lib.wfo_last_kernel_ms(self.handle))
+
+    def fp64_peak(self, kind: int, iters: int = 4096) -> float:
+        t = C.c_double()
+        check(self.lib.wfo_fp64_peak(self.handle, kind, iters, C.byref(t)))
+        return t.value
+
+
+def context(device: int | None = None) -> Context:
+    """Process-wide context cache.  ``device=None`` -> LOCAL_RANK (torchrun) or 0."""
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    with _lock:
+        ctx = _contexts.get(device)
+    if ctx is None:
+        ctx = Context(device)
+        with _lock:
+            _contexts[device] = ctx
+    return ctx

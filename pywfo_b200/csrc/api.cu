@@ -1,0 +1,621 @@
+// extern "C" entry points of libwfo_b200.so (see include/wfo_b200.h).
+#include <math.h>
+#include <new>
+
+#include "common.cuh"
+#include "det_lu_v1.cuh"
+#include "gemm_f64.cuh"
+#include "lu_base.cuh"
+#include "misc_kernels.cuh"
+#include "pair_update.cuh"
+
+namespace wfo {
+thread_local char g_err[512] = "";
+
+struct Arena {
+    char *base;
+    size_t cap, off;
+    template <typename T>
+    T *take(size_t count) {
+        size_t bytes = align_up(count * sizeof(T), 256);
+        T *p = reinterpret_cast<T *>(base + off);
+        off += bytes;
+        return p;
+    }
+};
+struct Sizer {   // same interface, only adds up
+    size_t off = 0;
+    template <typename T>
+    T *take(size_t count) {
+        off += align_up(count * sizeof(T), 256);
+        return nullptr;
+    }
+};
+
+static int ensure_scratch(wfo_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->scratch_bytes) return WFO_OK;
+    WFO_CUDA(cudaDeviceSynchronize());   // earlier async work may still read the old arena
+    if (ctx->scratch) WFO_CUDA(cudaFree(ctx->scratch));
+    ctx->scratch = nullptr;
+    ctx->scratch_bytes = 0;
+    size_t want = bytes + bytes / 4 + (1 << 20);
+    WFO_CUDA(cudaMalloc(&ctx->scratch, want));
+    ctx->scratch_bytes = want;
+    return WFO_OK;
+}
+
+#define WFO_LAUNCH_CHECK(ctx)                 \
+    do {                                      \
+        (ctx)->launches++;                    \
+        WFO_CUDA(cudaGetLastError());         \
+    } while (0)
+
+static int gemm(wfo_ctx *ctx, bool ta, bool tb, int m, int n, int k, double alpha, const double *A, int lda,
+                const double *B, int ldb, double beta, double *C, int ldc, int kslab, long long slab_stride,
+                cudaStream_t st) {
+    if (m <= 0 || n <= 0) return WFO_OK;
+    if (kslab <= 0) kslab = k > 0 ? k : 1;
+    int nz = k > 0 ? cdiv(k, kslab) : 1;
+    dim3 grid(cdiv(n, GN), cdiv(m, GM), nz), block(128);
+    if (!ta && !tb) gemm_f64_kernel<false, false><<<grid, block, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kslab, slab_stride);
+    else if (!ta && tb) gemm_f64_kernel<false, true><<<grid, block, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kslab, slab_stride);
+    else if (ta && !tb) gemm_f64_kernel<true, false><<<grid, block, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kslab, slab_stride);
+    else gemm_f64_kernel<true, true><<<grid, block, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kslab, slab_stride);
+    WFO_LAUNCH_CHECK(ctx);
+    return WFO_OK;
+}
+
+static size_t t0_smem_bytes(int n) { return (size_t)n * (n | 1) * sizeof(double) + 2 * (size_t)n * sizeof(int); }
+static int t0_threads(int n) { return n > 64 ? 256 : 128; }
+
+static int det_table(wfo_ctx *ctx, const double *S, int ld_s, int n, const int32_t *rows, int kb,
+                     const int32_t *cols, int kk, double *D, cudaStream_t st) {
+    long long npairs = (long long)kb * kk;
+    if (npairs <= 0) return WFO_OK;
+    size_t smem = t0_smem_bytes(n);
+    if (n < 1 || n > 128 || smem > ctx->smem_optin)
+        return set_err(WFO_ERR_ARG, "det_table: n_occ=%lld outside the supported range 1..128%s", "", n);
+    WFO_CUDA(cudaFuncSetAttribute(det_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int threads = t0_threads(n), per_sm = 1;
+    WFO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, det_table_kernel, threads, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)ctx->sm_count * per_sm;
+    if (grid > npairs) grid = npairs;
+    det_table_kernel<<<(unsigned)grid, threads, smem, st>>>(S, ld_s, n, rows, kb, cols, kk, D);
+    WFO_LAUNCH_CHECK(ctx);
+    return WFO_OK;
+}
+
+template <int NT>
+static void launch_t1(dim3 grid, cudaStream_t st, const double *Ai, const double *W, const BraMeta *bra,
+                      const double *bscale, int ksh, const KetMeta *ket, const double *ckts, int kk,
+                      int lps, double *gpart) {
+    t1_fused_kernel<NT><<<grid, T1_WARPS * 32, 0, st>>>(Ai, W, bra, bscale, ksh, ket, ckts, kk, lps, gpart);
+}
+
+struct Plan {   // everything wfo_state_overlaps needs from the arena
+    // common
+    double *ckt, *gpart, *G, *P, *w, *dk0, *d0l, *d00, *out_dev;
+    // T0
+    int32_t *bra_lists, *ket_lists, *gs_list;
+    // T1
+    double *Abuf, *Ai, *X, *Y, *Wb, *bscale, *ksgn;
+    BraMeta *bmeta;
+    KetMeta *kmeta;
+    BaseInfo *info;
+};
+
+template <typename AR>
+static void carve(AR &ar, Plan &p, int n, int v, int ksh, int kk, int n_bra, int ldg, int n_parts, int n_slabs,
+                  bool t0, bool t1) {
+    p.ckt = ar.template take<double>((size_t)kk * ldg);
+    p.gpart = ar.template take<double>((size_t)n_parts * ksh * ldg);
+    p.G = ar.template take<double>((size_t)ksh * ldg);
+    p.P = ar.template take<double>((size_t)n_slabs * n_bra * ldg);
+    p.w = ar.template take<double>(ldg);
+    p.dk0 = ar.template take<double>(ksh > 0 ? ksh : 1);
+    p.d0l = ar.template take<double>(kk > 0 ? kk : 1);
+    p.d00 = ar.template take<double>(1);
+    if (t0) {
+        p.bra_lists = ar.template take<int32_t>((size_t)(ksh > 0 ? ksh : 1) * n);
+        p.ket_lists = ar.template take<int32_t>((size_t)(kk > 0 ? kk : 1) * n);
+        p.gs_list = ar.template take<int32_t>(n);
+    }
+    if (t1) {
+        p.Ai = ar.template take<double>((size_t)n * n);
+        p.X = ar.template take<double>((size_t)(v > 0 ? v : 1) * n);
+        p.Y = ar.template take<double>((size_t)n * (v > 0 ? v : 1));
+        p.Wb = ar.template take<double>((size_t)(v + 1) * (v + 1));
+        p.bscale = ar.template take<double>(ksh > 0 ? ksh : 1);
+        p.ksgn = ar.template take<double>(kk > 0 ? kk : 1);
+        p.bmeta = ar.template take<BraMeta>(ksh > 0 ? ksh : 1);
+        p.kmeta = ar.template take<KetMeta>(kk > 0 ? kk : 1);
+        p.info = ar.template take<BaseInfo>(1);
+    }
+}
+
+static int pick_ldg(int n_ket) {
+    int nt = cdiv(n_ket + 1, 8);
+    if ((nt & 1) == 0) nt++;   // odd tile count: conflict-free B-fragment loads (stride = 8 mod 16)
+    return nt * 8;
+}
+
+
+struct Part {   // how the pair space of one call is cut up
+    int ldg, ktiles, t1_splits, lps, t0_chunks, chunk_len, n_parts, kslab, n_slabs;
+    bool may_t0, want_t1;
+};
+
+static size_t base_smem_bytes(int n) { return (size_t)n * (n | 1) * 8 + (size_t)n * 8 + (size_t)n * 4; }
+
+// which tiers can / should run for this call
+static int resolve_tier(const wfo_ctx *ctx, int n, int tier, bool *want_t1, bool *may_t0) {
+    if (tier != WFO_TIER_AUTO && tier != WFO_TIER_LU && tier != WFO_TIER_UPDATE)
+        return set_err(WFO_ERR_ARG, "state_overlaps: tier %lld not available%s", "", tier);
+    *want_t1 = (tier == WFO_TIER_AUTO || tier == WFO_TIER_UPDATE);
+    *may_t0 = (tier == WFO_TIER_AUTO || tier == WFO_TIER_LU);
+    const bool t0_fits = n <= 128 && t0_smem_bytes(n) <= ctx->smem_optin;
+    const bool t1_fits = base_smem_bytes(n) <= ctx->smem_optin;
+    if (tier == WFO_TIER_LU && !t0_fits)
+        return set_err(WFO_ERR_ARG, "state_overlaps: tier LU supports n_occ <= 128, got %lld%s", "", n);
+    if (tier == WFO_TIER_UPDATE && !t1_fits)
+        return set_err(WFO_ERR_ARG, "state_overlaps: tier UPDATE supports n_occ <= 160, got %lld%s", "", n);
+    if (tier == WFO_TIER_AUTO) {
+        if (!t1_fits) *want_t1 = false;
+        if (!t0_fits) *may_t0 = false;
+        if (!*want_t1 && !*may_t0)
+            return set_err(WFO_ERR_ARG, "state_overlaps: n_occ=%lld too large for every tier%s", "", n);
+    }
+    return WFO_OK;
+}
+
+static Part make_part(const wfo_ctx *ctx, int ksh, int kk, int n_ket, bool may_t0, bool want_t1) {
+    Part q;
+    q.may_t0 = may_t0;
+    q.want_t1 = want_t1;
+    q.ldg = pick_ldg(n_ket);
+    const int target_ctas = ctx->sm_count * 16;
+    // T1: grid (k tiles of 128, l splits)
+    q.ktiles = cdiv(ksh, T1_KTILE);
+    int splits = cdiv(target_ctas, q.ktiles);
+    int max_splits = cdiv(kk, 4 * T1_LT);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    q.lps = (int)align_up((size_t)cdiv(kk, splits), T1_LT);
+    q.t1_splits = cdiv(kk, q.lps);
+    // T0: items (k, chunk of l)
+    int chunks = cdiv(target_ctas, ksh);
+    if (chunks > kk) chunks = kk;
+    if (chunks < 1) chunks = 1;
+    q.chunk_len = cdiv(kk, chunks);
+    q.t0_chunks = cdiv(kk, q.chunk_len);
+    q.n_parts = 1;
+    if (want_t1 && q.t1_splits > q.n_parts) q.n_parts = q.t1_splits;
+    if (may_t0 && q.t0_chunks > q.n_parts) q.n_parts = q.t0_chunks;
+    q.kslab = 1024;
+    q.n_slabs = cdiv(ksh, q.kslab);
+    return q;
+}
+
+__global__ void iota_kernel(int32_t *p, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+
+}  // namespace wfo
+
+using namespace wfo;
+
+extern "C" {
+
+int wfo_version(void) { return 100; }
+const char *wfo_last_error(void) { return g_err; }
+
+int wfo_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int wfo_create(int device, wfo_ctx **out) {
+    if (!out) return set_err(WFO_ERR_ARG, "wfo_create: out is NULL%s");
+    *out = nullptr;
+    int ndev = 0;
+    WFO_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return set_err(WFO_ERR_ARG, "wfo_create: no CUDA device %lld%s", "", device);
+    WFO_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    WFO_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return set_err(WFO_ERR_ARG, "wfo_create: device is sm_%lld%lld, this library is sm_100a only", "", prop.major, prop.minor);
+    wfo_ctx *c = new (std::nothrow) wfo_ctx();
+    if (!c) return set_err(WFO_ERR_ARG, "wfo_create: out of host memory%s");
+    memset(c, 0, sizeof(*c));
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    c->last_tier = -1;
+    WFO_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    WFO_CUDA(cudaEventCreate(&c->ev0));
+    WFO_CUDA(cudaEventCreate(&c->ev1));
+    *out = c;
+    return WFO_OK;
+}
+
+int wfo_destroy(wfo_ctx *ctx) {
+    if (!ctx) return WFO_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return WFO_OK;
+}
+
+long long wfo_launch_count(const wfo_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int wfo_last_tier(const wfo_ctx *ctx) { return ctx ? ctx->last_tier : -1; }
+int wfo_set_timing(wfo_ctx *ctx, int on) {
+    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL%s");
+    ctx->timing = on;
+    return WFO_OK;
+}
+double wfo_last_kernel_ms(const wfo_ctx *ctx) {
+    if (!ctx || !ctx->timing) return -1.0;
+    float ms = -1.f;
+    if (cudaEventSynchronize(ctx->ev1) != cudaSuccess) return -1.0;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) != cudaSuccess) return -1.0;
+    return ms;
+}
+
+/* ---------------------------------------------------------------- stage 1 */
+int wfo_gemm_dev(wfo_ctx *ctx, int ta, int tb, int m, int n, int k, double alpha, const double *A, int lda,
+                 const double *B, int ldb, double beta, double *C, int ldc, void *stream) {
+    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL%s");
+    WFO_CUDA(cudaSetDevice(ctx->device));
+    return gemm(ctx, ta != 0, tb != 0, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, 0, 0, (cudaStream_t)stream);
+}
+
+int wfo_sao_dev(wfo_ctx *ctx, const double *c_inv, int n, double *s_ao, void *stream) {
+    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL%s");
+    WFO_CUDA(cudaSetDevice(ctx->device));
+    // S_AO = Cinv Cinv^T  (pywfo/main.py:304)
+    return gemm(ctx, false, true, n, n, n, 1.0, c_inv, n, c_inv, n, 0.0, s_ao, n, 0, 0, (cudaStream_t)stream);
+}
+
+int wfo_smo_dev(wfo_ctx *ctx, const double *bra_mos, const double *s_ao, const double *ket_mos, int p, int u,
+                int v, int q, double *s_mo, double *work, void *stream) {
+    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL%s");
+    WFO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!work) {
+        WFO_TRY(ensure_scratch(ctx, (size_t)p * v * sizeof(double) + 256));
+        work = reinterpret_cast<double *>(ctx->scratch);
+    }
+    // (bra S_AO) then (.) ket^T, the order of pywfo/main.py:532
+    WFO_TRY(gemm(ctx, false, false, p, v, u, 1.0, bra_mos, u, s_ao, v, 0.0, work, v, 0, 0, st));
+    WFO_TRY(gemm(ctx, false, true, p, q, v, 1.0, work, v, ket_mos, v, 0.0, s_mo, q, 0, 0, st));
+    return WFO_OK;
+}
+
+int wfo_smo_host(wfo_ctx *ctx, const double *bra_mos, const double *s_ao, const double *ket_mos, int p, int u,
+                 int v, int q, double *s_mo) {
+    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL%s");
+    WFO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    size_t nb = (size_t)p * u, ns = (size_t)u * v, nk = (size_t)q * v, nw = (size_t)p * v, no = (size_t)p * q;
+    Sizer sz;
+    sz.take<double>(nb); sz.take<double>(ns); sz.take<double>(nk); sz.take<double>(nw); sz.take<double>(no);
+    WFO_TRY(ensure_scratch(ctx, sz.off));
+    Arena ar{ctx->scratch, ctx->scratch_bytes, 0};
+    double *db = ar.take<double>(nb), *ds = ar.take<double>(ns), *dk = ar.take<double>(nk),
+           *dw = ar.take<double>(nw), *dout = ar.take<double>(no);
+    WFO_CUDA(cudaMemcpyAsync(db, bra_mos, nb * 8, cudaMemcpyHostToDevice, st));
+    WFO_CUDA(cudaMemcpyAsync(ds, s_ao, ns * 8, cudaMemcpyHostToDevice, st));
+    WFO_CUDA(cudaMemcpyAsync(dk, ket_mos, nk * 8, cudaMemcpyHostToDevice, st));
+    WFO_TRY(wfo_smo_dev(ctx, db, ds, dk, p, u, v, q, dout, dw, st));
+    WFO_CUDA(cudaMemcpyAsync(s_mo, dout, no * 8, cudaMemcpyDeviceToHost, st));
+    WFO_CUDA(cudaStreamSynchronize(st));
+    return WFO_OK;
+}
+
+/* ---------------------------------------------------------------- stage 2 */
+int wfo_exc_lists_dev(wfo_ctx *ctx, const int32_t *exc, int k, int n_occ, int32_t *lists, void *stream) {
+    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL%s");
+    if (k <= 0) return WFO_OK;
+    WFO_CUDA(cudaSetDevice(ctx->device));
+    long long tot = (long long)k * n_occ;
+    exc_lists_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(exc, k, n_occ, lists);
+    WFO_LAUNCH_CHECK(ctx);
+    return WFO_OK;
+}
+
+int wfo_det_table_dev(wfo_ctx *ctx, const double *s_mo, int n_mo, int ld_smo, int n, const int32_t *rows,
+                      int kb, const int32_t *cols, int kk, double *D, void *stream) {
+    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL%s");
+    if (n > n_mo) return set_err(WFO_ERR_ARG, "det_table: n=%lld > n_mo=%lld%s", "", n, n_mo);
+    WFO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev0, st));
+    WFO_TRY(det_table(ctx, s_mo, ld_smo, n, rows, kb, cols, kk, D, st));
+    if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev1, st));
+    return WFO_OK;
+}
+
+int wfo_det_table_host(wfo_ctx *ctx, const double *s_mo, int n_mo, int n, const int32_t *rows, int kb,
+                       const int32_t *cols, int kk, double *D) {
+    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL%s");
+    if (kb <= 0 || kk <= 0) return WFO_OK;
+    WFO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    size_t ns = (size_t)n_mo * n_mo, nr = (size_t)kb * n, nc = (size_t)kk * n, nd = (size_t)kb * kk;
+    Sizer sz;
+    sz.take<double>(ns); sz.take<int32_t>(nr); sz.take<int32_t>(nc); sz.take<double>(nd);
+    WFO_TRY(ensure_scratch(ctx, sz.off));
+    Arena ar{ctx->scratch, ctx->scratch_bytes, 0};
+    double *ds = ar.take<double>(ns);
+    int32_t *dr = ar.take<int32_t>(nr), *dc = ar.take<int32_t>(nc);
+    double *dd = ar.take<double>(nd);
+    WFO_CUDA(cudaMemcpyAsync(ds, s_mo, ns * 8, cudaMemcpyHostToDevice, st));
+    WFO_CUDA(cudaMemcpyAsync(dr, rows, nr * 4, cudaMemcpyHostToDevice, st));
+    WFO_CUDA(cudaMemcpyAsync(dc, cols, nc * 4, cudaMemcpyHostToDevice, st));
+    WFO_TRY(wfo_det_table_dev(ctx, ds, n_mo, n_mo, n, dr, kb, dc, kk, dd, st));
+    WFO_CUDA(cudaMemcpyAsync(D, dd, nd * 8, cudaMemcpyDeviceToHost, st));
+    WFO_CUDA(cudaStreamSynchronize(st));
+    return WFO_OK;
+}
+
+/* ----------------------------------------------------------- stages 2 + 3 */
+// `arena_off`: bytes at the start of the context arena owned by the caller (host wrappers)
+static int state_overlaps_impl(wfo_ctx *ctx, size_t arena_off, const double *s_mo, int n_mo, int n,
+                               const int32_t *bra_exc, int kb, const double *Cb, int n_bra,
+                               const int32_t *ket_exc, int kk, const double *Ck, int n_ket, double sigma,
+                               int tier, int k_begin, int k_end, double *out, cudaStream_t st) {
+    if (n < 1 || n > n_mo) return set_err(WFO_ERR_ARG, "state_overlaps: n_occ=%lld must be in 1..n_mo=%lld%s", "", n, n_mo);
+    if (n_bra < 1 || n_ket < 1) return set_err(WFO_ERR_ARG, "state_overlaps: need at least one bra and one ket state%s");
+    if (n_ket > 62) return set_err(WFO_ERR_ARG, "state_overlaps: n_ket=%lld > 62 not supported yet%s", "", n_ket);
+    if (k_begin < 0 || k_end > kb || k_begin > k_end)
+        return set_err(WFO_ERR_ARG, "state_overlaps: bad shard [%lld,%lld)%s", "", k_begin, k_end);
+    bool want_t1 = false, may_t0 = false;
+    WFO_TRY(resolve_tier(ctx, n, tier, &want_t1, &may_t0));
+    const int v = n_mo - n;
+    const int ksh = k_end - k_begin;
+    if (ksh == 0 || kk == 0) {   // empty shard / no ket determinants: the partial sum is zero
+        WFO_CUDA(cudaMemsetAsync(out, 0, (size_t)n_bra * n_ket * sizeof(double), st));
+        ctx->last_tier = want_t1 ? WFO_TIER_UPDATE : WFO_TIER_LU;
+        return WFO_OK;
+    }
+    const Part q = make_part(ctx, ksh, kk, n_ket, may_t0, want_t1);
+    const int ldg = q.ldg, ktiles = q.ktiles, t1_splits = q.t1_splits, lps = q.lps, t0_chunks = q.t0_chunks,
+              chunk_len = q.chunk_len, kslab = q.kslab, n_slabs = q.n_slabs;
+
+    Plan p;
+    memset(&p, 0, sizeof(p));
+    Sizer sz;
+    sz.off = arena_off;
+    carve(sz, p, n, v, ksh, kk, n_bra, ldg, q.n_parts, n_slabs, may_t0, want_t1);
+    WFO_TRY(ensure_scratch(ctx, sz.off));
+    Arena ar{ctx->scratch, ctx->scratch_bytes, arena_off};
+    carve(ar, p, n, v, ksh, kk, n_bra, ldg, q.n_parts, n_slabs, may_t0, want_t1);
+
+    const int32_t *bra_sh = bra_exc + 2 * (size_t)k_begin;
+    const double *d00_ptr = nullptr;
+    int used = -1, parts_used = 0;
+
+    if (want_t1) {
+        // ---- one base factorisation, then the three block products
+        size_t smem = base_smem_bytes(n);
+        WFO_CUDA(cudaFuncSetAttribute(base_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        base_inverse_kernel<<<1, LUB_THREADS, smem, st>>>(s_mo, n_mo, n, p.Ai, p.info);
+        WFO_LAUNCH_CHECK(ctx);
+        // the conditioning of the base block decides whether the rank-update tier is usable:
+        // one 32-byte read-back (the only host synchronisation of the call)
+        BaseInfo hinfo;
+        WFO_CUDA(cudaMemcpyAsync(&hinfo, p.info, sizeof(hinfo), cudaMemcpyDeviceToHost, st));
+        WFO_CUDA(cudaStreamSynchronize(st));
+        const bool ok = !hinfo.singular && hinfo.min_piv > 1e-6 * hinfo.max_piv;
+        if (ok) {
+            const double *Bblk = s_mo + n;                    // occ  x virt
+            const double *Cblk = s_mo + (size_t)n * n_mo;     // virt x occ
+            if (v > 0) {
+                WFO_TRY(gemm(ctx, false, false, v, n, n, 1.0, Cblk, n_mo, p.Ai, n, 0.0, p.X, n, 0, 0, st));
+                WFO_TRY(gemm(ctx, false, false, n, v, n, 1.0, p.Ai, n, Bblk, n_mo, 0.0, p.Y, v, 0, 0, st));
+            }
+            long long wtot = (long long)(v + 1) * (v + 1);
+            w_init_kernel<<<(unsigned)((wtot + 255) / 256), 256, 0, st>>>(s_mo, n_mo, n, v, p.Wb);
+            WFO_LAUNCH_CHECK(ctx);
+            if (v > 0) WFO_TRY(gemm(ctx, false, false, v, v, n, -1.0, Cblk, n_mo, p.Y, v, 1.0, p.Wb, v + 1, 0, 0, st));
+            t1_prep_bra_kernel<<<cdiv(ksh, 256), 256, 0, st>>>(bra_sh, ksh, n, v, p.X, p.info, p.bmeta, p.bscale, p.dk0);
+            WFO_LAUNCH_CHECK(ctx);
+            t1_prep_ket_kernel<<<cdiv(kk, 256), 256, 0, st>>>(ket_exc, kk, n, v, p.Y, p.info, p.kmeta, p.ksgn, p.d0l);
+            WFO_LAUNCH_CHECK(ctx);
+            long long ctot = (long long)kk * ldg;
+            ckt_kernel<<<(unsigned)((ctot + 255) / 256), 256, 0, st>>>(Ck, kk, n_ket, p.ksgn, ldg, p.ckt);
+            WFO_LAUNCH_CHECK(ctx);
+            dim3 grid(ktiles, t1_splits);
+            if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev0, st));
+            switch (ldg / 8) {
+                case 1: launch_t1<1>(grid, st, p.Ai, p.Wb, p.bmeta, p.bscale, ksh, p.kmeta, p.ckt, kk, lps, p.gpart); break;
+                case 3: launch_t1<3>(grid, st, p.Ai, p.Wb, p.bmeta, p.bscale, ksh, p.kmeta, p.ckt, kk, lps, p.gpart); break;
+                case 5: launch_t1<5>(grid, st, p.Ai, p.Wb, p.bmeta, p.bscale, ksh, p.kmeta, p.ckt, kk, lps, p.gpart); break;
+                case 7: launch_t1<7>(grid, st, p.Ai, p.Wb, p.bmeta, p.bscale, ksh, p.kmeta, p.ckt, kk, lps, p.gpart); break;
+                default: return set_err(WFO_ERR_ARG, "state_overlaps: unsupported ldg %lld%s", "", ldg);
+            }
+            WFO_LAUNCH_CHECK(ctx);
+            if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev1, st));
+            d00_ptr = &p.info->det;
+            used = WFO_TIER_UPDATE;
+            parts_used = t1_splits;
+        } else if (!may_t0) {
+            return set_err(WFO_ERR_SINGULAR,
+                           "state_overlaps: base block S_MO[:occ,:occ] is (numerically) singular, "
+                           "tier UPDATE not applicable%s");
+        }
+    }
+    if (used < 0) {
+        if (!may_t0)
+            return set_err(WFO_ERR_SINGULAR, "state_overlaps: base block singular and n_occ too large for tier LU%s");
+        // ---- brute force: ground-state row/column/corner first, then the fused pair kernel
+        iota_kernel<<<cdiv(n, 128), 128, 0, st>>>(p.gs_list, n);
+        WFO_LAUNCH_CHECK(ctx);
+        WFO_TRY(wfo_exc_lists_dev(ctx, bra_sh, ksh, n, p.bra_lists, st));
+        WFO_TRY(wfo_exc_lists_dev(ctx, ket_exc, kk, n, p.ket_lists, st));
+        WFO_TRY(det_table(ctx, s_mo, n_mo, n, p.bra_lists, ksh, p.gs_list, 1, p.dk0, st));
+        WFO_TRY(det_table(ctx, s_mo, n_mo, n, p.gs_list, 1, p.ket_lists, kk, p.d0l, st));
+        WFO_TRY(det_table(ctx, s_mo, n_mo, n, p.gs_list, 1, p.gs_list, 1, p.d00, st));
+        long long ctot = (long long)kk * ldg;
+        ckt_kernel<<<(unsigned)((ctot + 255) / 256), 256, 0, st>>>(Ck, kk, n_ket, nullptr, ldg, p.ckt);
+        WFO_LAUNCH_CHECK(ctx);
+        size_t smem = t0_smem_bytes(n);
+        WFO_CUDA(cudaFuncSetAttribute(t0_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int threads = t0_threads(n), per_sm = 1;
+        WFO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, t0_fused_kernel, threads, smem));
+        if (per_sm < 1) per_sm = 1;
+        long long items = (long long)ksh * t0_chunks;
+        long long grid = (long long)ctx->sm_count * per_sm;
+        if (grid > items) grid = items;
+        if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev0, st));
+        t0_fused_kernel<<<(unsigned)grid, threads, smem, st>>>(s_mo, n_mo, n, p.bra_lists, ksh, p.ket_lists, kk,
+                                                              p.ckt, ldg, chunk_len, t0_chunks, p.gpart);
+        WFO_LAUNCH_CHECK(ctx);
+        if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev1, st));
+        d00_ptr = p.d00;
+        used = WFO_TIER_LU;
+        parts_used = t0_chunks;
+    }
+
+    // ---- CI contraction: G = sum of partials (+ dk0 column), P = Cb[:, shard] G, finalize
+    long long gtot = (long long)ksh * ldg;
+    sum_parts_kernel<<<(unsigned)((gtot + 255) / 256), 256, 0, st>>>(p.gpart, parts_used, ksh, ldg, n_ket, p.dk0, p.G);
+    WFO_LAUNCH_CHECK(ctx);
+    WFO_TRY(gemm(ctx, false, false, n_bra, ldg, ksh, 1.0, Cb + k_begin, kb, p.G, ldg, 0.0, p.P, ldg, kslab,
+                 (long long)n_bra * ldg, st));
+    ket_gs_dot_kernel<<<n_ket, 256, 0, st>>>(Ck, kk, p.d0l, p.w);
+    WFO_LAUNCH_CHECK(ctx);
+    finalize_kernel<<<cdiv(n_bra * n_ket, 128), 128, 0, st>>>(p.P, n_slabs, n_bra, ldg, n_ket, p.w, d00_ptr, sigma, out);
+    WFO_LAUNCH_CHECK(ctx);
+    ctx->last_tier = used;
+    return WFO_OK;
+}
+
+int wfo_state_overlaps_dev(wfo_ctx *ctx, const double *s_mo, int n_mo, int n_occ, const int32_t *bra_exc, int kb,
+                           const double *Cb, int n_bra, const int32_t *ket_exc, int kk, const double *Ck,
+                           int n_ket, double sigma, int tier, int k_begin, int k_end, double *out, void *stream) {
+    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL%s");
+    WFO_CUDA(cudaSetDevice(ctx->device));
+    return state_overlaps_impl(ctx, 0, s_mo, n_mo, n_occ, bra_exc, kb, Cb, n_bra, ket_exc, kk, Ck, n_ket, sigma,
+                               tier, k_begin, k_end, out, (cudaStream_t)stream);
+}
+
+// shared by the two host front ends: uploads tables, runs, downloads
+static int host_front(wfo_ctx *ctx, const double *s_mo_host, const double *bra_mos, const double *ket_mos,
+                      const double *c_inv, int n_mo, int n, const int32_t *bra_exc, int kb, const double *Cb,
+                      int n_bra, const int32_t *ket_exc, int kk, const double *Ck, int n_ket, double sigma,
+                      int tier, int k_begin, int k_end, double *out) {
+    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL%s");
+    if (kb < 0 || kk < 0 || n_bra < 1 || n_ket < 1 || n_mo < 1)
+        return set_err(WFO_ERR_ARG, "state_overlaps: negative or empty sizes%s");
+    WFO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    size_t nsq = (size_t)n_mo * n_mo;
+    Sizer sz;
+    sz.take<double>(nsq);                                     // S_MO
+    if (!s_mo_host) { sz.take<double>(nsq); sz.take<double>(nsq); sz.take<double>(nsq); sz.take<double>(nsq); sz.take<double>(nsq); }
+    sz.take<int32_t>(2 * (size_t)(kb + 1)); sz.take<int32_t>(2 * (size_t)(kk + 1));
+    sz.take<double>((size_t)n_bra * (kb + 1)); sz.take<double>((size_t)n_ket * (kk + 1));
+    sz.take<double>((size_t)n_bra * n_ket);
+    size_t front = sz.off;
+    {   // size the arena once for the front buffers plus the implementation's plan
+        size_t total = front;
+        const int v = n_mo - n, ksh = k_end - k_begin;
+        bool want_t1 = false, may_t0 = false;
+        if (n >= 1 && n <= n_mo && ksh > 0 && kk > 0 && k_begin >= 0 && k_end <= kb &&
+            resolve_tier(ctx, n, tier, &want_t1, &may_t0) == WFO_OK) {
+            Part q = make_part(ctx, ksh, kk, n_ket, may_t0, want_t1);
+            Plan p;
+            Sizer s2;
+            s2.off = front;
+            carve(s2, p, n, v, ksh, kk, n_bra, q.ldg, q.n_parts, q.n_slabs, may_t0, want_t1);
+            total = s2.off;
+        }
+        WFO_TRY(ensure_scratch(ctx, total));
+    }
+    Arena ar{ctx->scratch, ctx->scratch_bytes, 0};
+    double *d_smo = ar.take<double>(nsq);
+    if (!s_mo_host) {
+        double *d_bra = ar.take<double>(nsq), *d_ket = ar.take<double>(nsq), *d_inv = ar.take<double>(nsq),
+               *d_sao = ar.take<double>(nsq), *d_work = ar.take<double>(nsq);
+        WFO_CUDA(cudaMemcpyAsync(d_bra, bra_mos, nsq * 8, cudaMemcpyHostToDevice, st));
+        WFO_CUDA(cudaMemcpyAsync(d_ket, ket_mos, nsq * 8, cudaMemcpyHostToDevice, st));
+        WFO_CUDA(cudaMemcpyAsync(d_inv, c_inv, nsq * 8, cudaMemcpyHostToDevice, st));
+        WFO_TRY(wfo_sao_dev(ctx, d_inv, n_mo, d_sao, st));
+        WFO_TRY(wfo_smo_dev(ctx, d_bra, d_sao, d_ket, n_mo, n_mo, n_mo, n_mo, d_smo, d_work, st));
+    } else {
+        WFO_CUDA(cudaMemcpyAsync(d_smo, s_mo_host, nsq * 8, cudaMemcpyHostToDevice, st));
+    }
+    int32_t *d_be = ar.take<int32_t>(2 * (size_t)(kb + 1)), *d_ke = ar.take<int32_t>(2 * (size_t)(kk + 1));
+    double *d_cb = ar.take<double>((size_t)n_bra * (kb + 1)), *d_ck = ar.take<double>((size_t)n_ket * (kk + 1));
+    double *d_out = ar.take<double>((size_t)n_bra * n_ket);
+    if (kb > 0) {
+        WFO_CUDA(cudaMemcpyAsync(d_be, bra_exc, 2 * (size_t)kb * 4, cudaMemcpyHostToDevice, st));
+        WFO_CUDA(cudaMemcpyAsync(d_cb, Cb, (size_t)n_bra * kb * 8, cudaMemcpyHostToDevice, st));
+    }
+    if (kk > 0) {
+        WFO_CUDA(cudaMemcpyAsync(d_ke, ket_exc, 2 * (size_t)kk * 4, cudaMemcpyHostToDevice, st));
+        WFO_CUDA(cudaMemcpyAsync(d_ck, Ck, (size_t)n_ket * kk * 8, cudaMemcpyHostToDevice, st));
+    }
+    char *before = ctx->scratch;
+    WFO_TRY(state_overlaps_impl(ctx, ar.off, d_smo, n_mo, n, d_be, kb, d_cb, n_bra, d_ke, kk, d_ck, n_ket, sigma,
+                                tier, k_begin, k_end, d_out, st));
+    if (ctx->scratch != before) return set_err(WFO_ERR_CUDA, "internal: arena moved during a host call%s");
+    WFO_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n_bra * n_ket * 8, cudaMemcpyDeviceToHost, st));
+    WFO_CUDA(cudaStreamSynchronize(st));
+    return WFO_OK;
+}
+
+int wfo_state_overlaps_host(wfo_ctx *ctx, const double *s_mo, int n_mo, int n_occ, const int32_t *bra_exc, int kb,
+                            const double *Cb, int n_bra, const int32_t *ket_exc, int kk, const double *Ck,
+                            int n_ket, double sigma, int tier, int k_begin, int k_end, double *out) {
+    if (!s_mo) return set_err(WFO_ERR_ARG, "state_overlaps_host: s_mo is NULL%s");
+    return host_front(ctx, s_mo, nullptr, nullptr, nullptr, n_mo, n_occ, bra_exc, kb, Cb, n_bra, ket_exc, kk, Ck,
+                      n_ket, sigma, tier, k_begin, k_end, out);
+}
+
+int wfo_overlaps_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos, const double *c_inv, int n_mo,
+                      int n_occ, const int32_t *bra_exc, int kb, const double *Cb, int n_bra,
+                      const int32_t *ket_exc, int kk, const double *Ck, int n_ket, double sigma, int tier,
+                      int k_begin, int k_end, double *out) {
+    if (!bra_mos || !ket_mos || !c_inv) return set_err(WFO_ERR_ARG, "overlaps_host: NULL MO pointer%s");
+    return host_front(ctx, nullptr, bra_mos, ket_mos, c_inv, n_mo, n_occ, bra_exc, kb, Cb, n_bra, ket_exc, kk, Ck,
+                      n_ket, sigma, tier, k_begin, k_end, out);
+}
+
+/* ------------------------------------------------------------ measurement */
+int wfo_fp64_peak(wfo_ctx *ctx, int kind, int iters, double *tflops) {
+    if (!ctx || !tflops) return set_err(WFO_ERR_ARG, "fp64_peak: NULL argument%s");
+    WFO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    WFO_TRY(ensure_scratch(ctx, 256));
+    double *out = reinterpret_cast<double *>(ctx->scratch);
+    const int blocks = ctx->sm_count * 8, threads = 256;
+    double flops_per_thread_iter = kind == 0 ? 16 * 2.0 : (kind == 1 ? 8 * 512.0 / 32 : 4 * 2048.0 / 32);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        WFO_CUDA(cudaEventRecord(ctx->ev0, st));
+        if (kind == 0) dfma_peak_kernel<<<blocks, threads, 0, st>>>(iters, out);
+        else if (kind == 1) dmma884_peak_kernel<<<blocks, threads, 0, st>>>(iters, out);
+        else if (kind == 2) dmma1688_peak_kernel<<<blocks, threads, 0, st>>>(iters, out);
+        else return set_err(WFO_ERR_ARG, "fp64_peak: kind must be 0, 1 or 2%s");
+        WFO_LAUNCH_CHECK(ctx);
+        WFO_CUDA(cudaEventRecord(ctx->ev1, st));
+        WFO_CUDA(cudaEventSynchronize(ctx->ev1));
+        float ms = 0.f;
+        WFO_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    *tflops = flops_per_thread_iter * iters * (double)blocks * threads / (best * 1e-3) / 1e12;
+    return WFO_OK;
+}
+
+}  // extern "C"

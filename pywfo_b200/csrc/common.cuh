@@ -1,0 +1,71 @@
+// Shared helpers of the wfo_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/wfo_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "wfo_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace wfo {
+
+extern thread_local char g_err[512];
+
+inline int set_err(int code, const char *fmt, const char *a = "", long long b = 0, long long c = 0) {
+    snprintf(g_err, sizeof(g_err), fmt, a, b, c);
+    return code;
+}
+
+#define WFO_CUDA(call)                                                                   \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess) {                                                         \
+            snprintf(wfo::g_err, sizeof(wfo::g_err), "%s:%d %s: %s", __FILE__, __LINE__, \
+                     #call, cudaGetErrorString(e_));                                     \
+            return WFO_ERR_CUDA;                                                         \
+        }                                                                                \
+    } while (0)
+
+#define WFO_TRY(call)            \
+    do {                         \
+        int r_ = (call);         \
+        if (r_ != WFO_OK) return r_; \
+    } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// FP64 tensor-core MMA, D(8x8) += A(8x4) * B(4x8).  SASS: DMMA.8x8x4.
+// Fragment ownership (lane = 4*g + t):  a = A[g][t],  b = B[t][g],
+// c0/c1 = C[g][2t], C[g][2t+1].
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ unsigned hi_abs(double x) {
+    return (unsigned)__double2hiint(x) & 0x7fffffffu;
+}
+
+}  // namespace wfo
+
+struct wfo_ctx {
+    int device;
+    int sm_count;
+    size_t smem_optin;
+    cudaStream_t stream;   // private stream of the *_host entry points
+    char *scratch;         // device arena, grown on demand
+    size_t scratch_bytes;
+    char *hscratch;        // pinned host staging for the *_host entry points
+    size_t hscratch_bytes;
+    long long launches;
+    int last_tier;
+    int timing;
+    float last_ms;
+    cudaEvent_t ev0, ev1;
+};

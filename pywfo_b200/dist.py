@@ -1,0 +1,71 @@
+"""Multi-GPU plumbing: shard the bra excitations, one all-reduce of the result.
+
+One process per GPU (torchrun); ``torch.distributed`` is used for nothing but
+the rendezvous and the single ``all_reduce(sum)`` of the ``n_bra x n_ket``
+partial matrices (NCCL over NVLink on the GPU box, gloo in the CPU tests).
+The pair space needs no other exchange.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from .excitations import shard_bounds
+
+
+def world():
+    """(rank, world_size) of the initialised default process group, else (0, 1)."""
+    try:
+        import torch.distributed as dist
+    except Exception:  # torch missing: single process
+        return 0, 1
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def init_from_env(backend: str | None = None):
+    """Initialise the default group from torchrun's environment (no-op for 1 rank)."""
+    import torch
+    import torch.distributed as dist
+
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    if ws <= 1 or dist.is_initialized():
+        return world()
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29511")
+    if backend == "nccl":
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    dist.init_process_group(backend=backend, rank=int(os.environ["RANK"]), world_size=ws)
+    return world()
+
+
+def sharded_state_overlaps(partial_fn, K_bra: int, n_bra: int, n_ket: int, device=None):
+    """Run ``partial_fn(k_begin, k_end) -> (n_bra, n_ket)`` on this rank's slice of the
+    bra excitations and sum the partial matrices over all ranks.
+
+    ``partial_fn`` returns a numpy array (host path) or a torch tensor (device
+    path); the all-reduce runs on whatever device the group's backend needs.
+    The product passes a closure over the CUDA entry point; the CPU tests pass
+    the oracle so that the sharding logic is exercised without a GPU.
+    """
+    import torch
+    import torch.distributed as dist
+
+    rank, ws = world()
+    lo, hi = shard_bounds(K_bra, ws, rank)
+    part = partial_fn(lo, hi)
+    if ws == 1:
+        return part
+    was_numpy = isinstance(part, np.ndarray)
+    t = torch.from_numpy(np.ascontiguousarray(part)) if was_numpy else part
+    if dist.get_backend() == "nccl" and not t.is_cuda:
+        t = t.cuda(device if device is not None else torch.cuda.current_device())
+    assert tuple(t.shape) == (n_bra, n_ket)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    if was_numpy:
+        return t.cpu().numpy()
+    return t

@@ -1,0 +1,127 @@
+"""Drop-in for the hot path of ``pywfo/main.py``: same names, same arguments.
+
+    overlaps | overlaps_naive | overlaps_most_naive | overlaps_cache
+        (bra_mos, ket_mos, bra_ci, ket_ci, occ, ci_thresh=1e-4, ao_ovlps="ket")
+    moovlp | moovlp_expl | moovlp_dots (mos1, mos2, S_AO)
+    get_S_AO(bra_mos, ket_mos, ao_ovlps)
+
+The host does what the reference's host code does around the arithmetic --
+``np.linalg.inv`` of the MO matrix for ``ao_ovlps in {"bra","ket"}``
+(pywfo/main.py:303) and the thresholding of the CI vectors (main.py:539-540,
+112, 122-123; see excitations.py) -- and hands everything else to the CUDA
+library through ``include/wfo_b200.h``: S_AO = Cinv Cinv^T, S_MO, every
+determinant pair and the CI-weighted reduction.  Extra keyword arguments
+(``tier``, ``device``) are a superset of the reference signature.
+
+When ``torch.distributed`` is initialised with more than one rank, each rank
+computes the partial matrix of its shard of the bra excitations and the
+partials are summed with one all-reduce (dist.py).
+"""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+
+from . import _lib, dist
+from .excitations import build_tables, check_minus_inputs
+
+logger = logging.getLogger("pywfo_b200")
+logger.addHandler(logging.NullHandler())
+
+
+def log(message, level="info"):
+    """pywfo/main.py:23: kept so that callers' ``log`` imports keep working; quiet."""
+    getattr(logger, level)(message)
+
+
+def get_S_AO(bra_mos, ket_mos, ao_ovlps):
+    """pywfo/main.py:301-311.  The inverse is numpy/LAPACK on the host exactly as
+    upstream; the product ``inv inv^T`` runs on the GPU (wfo_sao_dev via smo)."""
+    if isinstance(ao_ovlps, str):
+        inv = np.linalg.inv({"bra": bra_mos, "ket": ket_mos}[ao_ovlps])
+        # inv @ I @ inv^T through the DMMA GEMM chain
+        return _lib.context().smo_host(inv, np.eye(inv.shape[1]), inv)
+    if isinstance(ao_ovlps, np.ndarray):  # upstream's isinstance(.., np.array) raises TypeError
+        return ao_ovlps
+    raise Exception("Invalid AO overlaps!")
+
+
+def moovlp(mos1, mos2, S_AO):
+    """<phi_p|phi_q> = sum_uv C_pu C'_qv S_uv (pywfo/main.py:27-43) on the GPU."""
+    return _lib.context().smo_host(mos1, S_AO, mos2)
+
+
+def moovlp_expl(mos1, mos2, S_AO):
+    """pywfo/main.py:46-68: same contraction (upstream: explicit Python loops)."""
+    return moovlp(mos1, mos2, S_AO)
+
+
+def moovlp_dots(mos1, mos2, S_AO):
+    """pywfo/main.py:71-78: same contraction (upstream: numba-jitted dots)."""
+    return moovlp(mos1, mos2, S_AO)
+
+
+def _state_overlaps(semantics, sigma, bra_mos, ket_mos, bra_ci, ket_ci, occ, ci_thresh, ao_ovlps,
+                    tier="auto", device=None):
+    bra_mos = np.asarray(bra_mos, dtype=np.float64)
+    ket_mos = np.asarray(ket_mos, dtype=np.float64)
+    bra_ci = np.asarray(bra_ci, dtype=np.float64)
+    ket_ci = np.asarray(ket_ci, dtype=np.float64)
+    occ = int(occ)
+    if bra_ci.ndim != 3 or ket_ci.ndim != 3:
+        raise ValueError("CI coefficients must have shape (n_states, occ, virt)")
+    if bra_ci.shape[1] != occ or ket_ci.shape[1] != occ:
+        raise ValueError("CI coefficients do not match occ")
+    ctx = _lib.context(device)
+    bra_t = build_tables(bra_ci, ci_thresh, semantics)
+    ket_t = build_tables(ket_ci, ci_thresh, semantics, order="locality")
+    n_bra, n_ket = bra_ci.shape[0], ket_ci.shape[0]
+    if bra_t.K == 0 or ket_t.K == 0:
+        return np.zeros((n_bra, n_ket))
+
+    if isinstance(ao_ovlps, str):
+        c_inv = np.linalg.inv({"bra": bra_mos, "ket": ket_mos}[ao_ovlps])   # main.py:303
+
+        def partial(lo, hi):
+            return ctx.overlaps_host(bra_mos, ket_mos, c_inv, occ, bra_t.exc, bra_t.coeff, ket_t.exc,
+                                     ket_t.coeff, sigma=sigma, tier=tier, k_begin=lo, k_end=hi)
+    elif isinstance(ao_ovlps, np.ndarray):
+        s_mo = ctx.smo_host(bra_mos, ao_ovlps, ket_mos)
+
+        def partial(lo, hi):
+            return ctx.state_overlaps_host(s_mo, occ, bra_t.exc, bra_t.coeff, ket_t.exc, ket_t.coeff,
+                                           sigma=sigma, tier=tier, k_begin=lo, k_end=hi)
+    else:
+        raise Exception("Invalid AO overlaps!")
+    return dist.sharded_state_overlaps(partial, bra_t.K, n_bra, n_ket, device=ctx.device)
+
+
+def overlaps_cache(bra_mos, ket_mos, bra_ci, ket_ci, occ, ci_thresh=1e-4, ao_ovlps="ket", **kw):
+    """Singlet->singlet state overlaps, pywfo/main.py:520-627."""
+    return _state_overlaps("cache", 1.0, bra_mos, ket_mos, bra_ci, ket_ci, occ, ci_thresh, ao_ovlps, **kw)
+
+
+def overlaps_naive(bra_mos, ket_mos, bra_ci, ket_ci, occ, ci_thresh=1e-4, ao_ovlps="ket", **kw):
+    """pywfo/main.py:314-419 (the live definition): same numbers as ``overlaps_cache``."""
+    return _state_overlaps("cache", 1.0, bra_mos, ket_mos, bra_ci, ket_ci, occ, ci_thresh, ao_ovlps, **kw)
+
+
+def overlaps_most_naive(bra_mos, ket_mos, bra_ci, ket_ci, occ, ci_thresh=1e-4, ao_ovlps="ket", **kw):
+    """pywfo/main.py:422-517: same numbers as ``overlaps_cache``."""
+    return _state_overlaps("cache", 1.0, bra_mos, ket_mos, bra_ci, ket_ci, occ, ci_thresh, ao_ovlps, **kw)
+
+
+def overlaps(bra_mos, ket_mos, bra_ci, ket_ci, occ, ci_thresh=1e-4, ao_ovlps="ket", **kw):
+    """The "minus" (Ms=0 triplet) formula, pywfo/main.py:81-199, with upstream's
+    assertions (main.py:90-91), strict threshold and sign^occ behaviour."""
+    bra_mos = np.asarray(bra_mos)
+    ket_mos = np.asarray(ket_mos)
+    bra_ci = np.asarray(bra_ci)
+    ket_ci = np.asarray(ket_ci)
+    assert bra_mos.shape == ket_mos.shape
+    assert bra_ci.shape == ket_ci.shape
+    if not isinstance(ao_ovlps, (str, np.ndarray)):
+        raise Exception("Invalid AO overlaps!")
+    check_minus_inputs(bra_ci, ket_ci, ci_thresh)
+    return _state_overlaps("minus", -1.0, bra_mos, ket_mos, bra_ci, ket_ci, occ, ci_thresh, ao_ovlps, **kw)

@@ -1,0 +1,328 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the golden
+vectors.  Needs a B200: run with ``-m gpu``.
+
+Tolerance: north_star asks for <= 1e-10 relative error in FP64 and the sign of
+every state overlap; elements below 1e-10 * max|S| are compared absolutely.
+"""
+import numpy as np
+import pytest
+
+from oracle import pywfo_oracle as orc
+from conftest import RANDOM_CASES, load_golden
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+
+
+def assert_parity(got, want, rtol=RTOL):
+    got = np.asarray(got)
+    want = np.asarray(want)
+    assert got.shape == want.shape
+    scale = np.abs(want).max() if want.size else 0.0
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=rtol * scale + 1e-300)
+    big = np.abs(want) > rtol * scale
+    assert np.array_equal(np.sign(got[big]), np.sign(want[big]))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from pywfo_b200 import _lib
+    return _lib.context(0)
+
+
+def _smo(g, ao="ket"):
+    return orc.mo_overlap(g["bra_mos"], g["ket_mos"], orc.get_S_AO(g["bra_mos"], g["ket_mos"], ao))
+
+
+# ---------------------------------------------------------------- stage 1
+@pytest.mark.parametrize("name", ["simple", "more_virtual_mos", "r_odd", "r_n17", "r_n34", "h2o2"])
+def test_mo_overlap(ctx, name):
+    from pywfo_b200 import main
+    g = load_golden(name)
+    S_AO = orc.get_S_AO(g["bra_mos"], g["ket_mos"], "ket")
+    want = orc.mo_overlap(g["bra_mos"], g["ket_mos"], S_AO)
+    for fn in (main.moovlp, main.moovlp_expl, main.moovlp_dots):
+        np.testing.assert_allclose(fn(g["bra_mos"], g["ket_mos"], S_AO), want, rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(main.get_S_AO(g["bra_mos"], g["ket_mos"], "ket"), S_AO, rtol=1e-11, atol=1e-12)
+
+
+def test_mo_overlap_identity_big(ctx):
+    """pywfo/tests/test_pywfo.py:39-57 (test_big_mo_overlaps, n=1000 upstream; regenerated)."""
+    from pywfo_b200 import helpers, main
+    mos = helpers.get_dummy_mos(500, 20180325)
+    inv = np.linalg.inv(mos)
+    S_AO = inv.dot(inv.T)
+    np.testing.assert_allclose(main.moovlp(mos, mos, S_AO), np.eye(500), atol=1e-8)
+
+
+def test_mo_overlap_rectangular(ctx):
+    rng = np.random.default_rng(1)
+    a, s, b = rng.standard_normal((37, 70)), rng.standard_normal((70, 65)), rng.standard_normal((129, 65))
+    np.testing.assert_allclose(ctx.smo_host(a, s, b), a @ s @ b.T, rtol=1e-12, atol=1e-11)
+
+
+# ---------------------------------------------------------------- stage 2
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 9, 17, 32, 33, 34, 64, 65, 100, 128])
+def test_det_table_vs_lapack(ctx, n):
+    rng = np.random.default_rng(n)
+    n_mo = n + 7
+    q, _ = np.linalg.qr(rng.standard_normal((n_mo, n_mo)))
+    S = q + 0.05 * rng.standard_normal((n_mo, n_mo))
+    rows = np.array([rng.permutation(n_mo)[:n] for _ in range(5)], dtype=np.int32)
+    cols = np.array([rng.permutation(n_mo)[:n] for _ in range(4)], dtype=np.int32)
+    want = orc.det_from_lists(S, rows, cols)
+    got = ctx.det_table_host(S, rows, cols)
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-12 * np.abs(want).max())
+    assert np.array_equal(np.sign(got), np.sign(want))
+
+
+def test_det_table_singular_and_tiny(ctx):
+    S = np.arange(36, dtype=float).reshape(6, 6)            # rank 2: every 3x3 minor is singular
+    rows = np.array([[0, 1, 2], [1, 3, 5]], dtype=np.int32)
+    cols = np.array([[0, 2, 4]], dtype=np.int32)
+    got = ctx.det_table_host(S, rows, cols)
+    assert np.all(np.abs(got) < 1e-9)
+    Z = np.zeros((4, 4))
+    assert np.all(ctx.det_table_host(Z, rows[:, :2] % 4, cols[:, :2] % 4) == 0.0)
+
+
+def test_precompute_matches_reference_semantics(ctx):
+    """pywfo/dets.py:191-198 on explicit alpha/beta block lists."""
+    from pywfo_b200 import dets
+    g = load_golden("r_n9")
+    S = _smo(g)
+    occ = int(g["occ"])
+    blocks_b = [orc.exc_index_list(e, occ) for e in [orc.GS, (0, 0), (3, 2), (8, 10)]]
+    blocks_k = [orc.exc_index_list(e, occ) for e in [orc.GS, (1, 1), (8, 0)]]
+    want = orc.det_from_lists(S, blocks_b, blocks_k)
+    np.testing.assert_allclose(dets.precompute(blocks_b, blocks_k, S), want, rtol=1e-10, atol=1e-14)
+
+
+# ---------------------------------------------------------------- whole path, goldens
+@pytest.mark.parametrize("tier", ["auto", "lu", "update"])
+def test_golden_pins(ctx, tier):
+    from pywfo_b200 import main
+    g = load_golden("simple")
+    for fn in (main.overlaps_naive, main.overlaps_most_naive, main.overlaps_cache):
+        got = fn(g["bra_mos"], g["ket_mos"], g["bra_ci"], g["ket_ci"], occ=1, tier=tier)
+        assert got[0][0] == pytest.approx(0.97008177)            # pywfo/tests/test_pywfo.py:94
+        assert_parity(got, g["ref_overlaps_cache"])
+    g = load_golden("more_virtual_mos")
+    got = main.overlaps_most_naive(g["bra_mos"], g["ket_mos"], g["bra_ci"], g["ket_ci"], occ=2, tier=tier)
+    want = np.array((0.11025145, 0.97114924, 0.97595963, -0.09630209)).reshape(-1, 2)
+    np.testing.assert_allclose(got, want, atol=1e-7)             # pywfo/tests/test_pywfo.py:122-125
+    assert_parity(got, g["ref_overlaps_most_naive"])
+    assert_parity(main.overlaps(g["bra_mos"], g["ket_mos"], g["bra_ci"], g["ket_ci"], occ=2, tier=tier),
+                  g["ref_overlaps"])
+
+
+@pytest.mark.parametrize("tier", ["auto", "lu", "update"])
+def test_h2o2(ctx, tier):
+    """pywfo/tests/test_pywfo.py:128-156 and the 4x4 variants, reference self-output."""
+    from pywfo_b200 import dets, main
+    g = load_golden("h2o2")
+    bra, ket, bci, kci = g["bra_mos"], g["ket_mos"], g["bra_ci"], g["ket_ci"]
+    got = main.overlaps_cache(bra, ket, bci[:1], kci[:1], 9, ci_thresh=3e-2, ao_ovlps="ket", tier=tier)
+    assert_parity(got, g["ref_cache_state0_3e-2"])
+    assert_parity(main.overlaps_cache(bra, ket, bci, kci, 9, ci_thresh=1e-2, tier=tier), g["ref_cache_4x4_1e-2"])
+    assert_parity(main.overlaps_cache(bra, ket, bci, kci, 9, ci_thresh=1e-4, tier=tier), g["ref_cache_4x4_1e-4"])
+    assert_parity(main.overlaps(bra, ket, bci, kci, 9, ci_thresh=1e-2, tier=tier), g["ref_minus_4x4_1e-2"])
+    S_AO = orc.get_S_AO(bra, ket, "ket")
+    assert_parity(dets.wfoverlap(bra, ket, bci, kci, 1e-2, S_AO, debug=False, tier=tier), g["ref_wfoverlap_4x4_1e-2"])
+    assert_parity(dets.wfoverlap(bra, ket, bci[:1], kci[:1], 3e-2, S_AO, tier=tier), g["ref_wfoverlap_1x1_3e-2"])
+
+
+@pytest.mark.parametrize("name", RANDOM_CASES)
+@pytest.mark.parametrize("tier", ["lu", "update"])
+def test_random_goldens(ctx, name, tier):
+    from pywfo_b200 import dets, main
+    g = load_golden(name)
+    a = (g["bra_mos"], g["ket_mos"], g["bra_ci"], g["ket_ci"], int(g["occ"]))
+    thr = float(g["ci_thresh"])
+    assert_parity(main.overlaps_cache(*a, ci_thresh=thr, tier=tier), g["ref_overlaps_cache"])
+    assert_parity(main.overlaps_naive(*a, ci_thresh=thr, tier=tier), g["ref_overlaps_cache"])
+    assert_parity(main.overlaps_cache(*a, ci_thresh=thr, ao_ovlps="bra", tier=tier), g["ref_overlaps_cache_bra"])
+    nmin = min(a[2].shape[0], a[3].shape[0])
+    assert_parity(main.overlaps(a[0], a[1], a[2][:nmin], a[3][:nmin], a[4], ci_thresh=thr, tier=tier),
+                  g["ref_overlaps"])
+    S_AO = orc.get_S_AO(a[0], a[1], "bra")
+    assert_parity(dets.wfoverlap(a[0], a[1], a[2], a[3], thr, S_AO, tier=tier), g["ref_wfoverlap"])
+    # ndarray AO overlaps (documented upstream, main.py:305, but raising there): accepted here
+    assert_parity(main.overlaps_cache(*a, ci_thresh=thr, ao_ovlps=S_AO, tier=tier), g["ref_overlaps_cache_bra"])
+
+
+# ---------------------------------------------------------------- reference error behaviour
+def test_error_behaviour(ctx):
+    from pywfo_b200 import main
+    g = load_golden("r_even")
+    a = (g["bra_mos"], g["ket_mos"], g["bra_ci"], g["ket_ci"], int(g["occ"]))
+    with pytest.raises(AssertionError):                      # main.py:91
+        main.overlaps(*a)
+    with pytest.raises(Exception, match="Invalid AO overlaps"):   # main.py:308
+        main.overlaps_cache(*a, ao_ovlps=1.5)
+    bci = g["bra_ci"][:2].copy()
+    bci[1] = 0
+    with pytest.raises(ValueError):                          # main.py:186
+        main.overlaps(g["bra_mos"], g["ket_mos"], bci, g["ket_ci"][:2], a[4])
+    # thresholds that drop everything: zeros (the reference sums empty lists)
+    z = main.overlaps_cache(*a, ci_thresh=10.0)
+    assert z.shape == (3, 2) and not z.any()
+
+
+# ---------------------------------------------------------------- kernel-form calls, edge cases
+def _random_tables(rng, occ, virt, kb, kk, n_bra, n_ket, with_gs=False):
+    bra = np.stack([rng.integers(0, occ, kb), rng.integers(0, virt, kb)], 1).astype(np.int32)
+    ket = np.stack([rng.integers(0, occ, kk), rng.integers(0, virt, kk)], 1).astype(np.int32)
+    if with_gs:
+        bra[kb // 2] = (-1, -1)
+        ket[0] = (-1, -1)
+    return bra, rng.standard_normal((n_bra, kb)), ket, rng.standard_normal((n_ket, kk))
+
+
+@pytest.mark.parametrize("occ,n_mo,kb,kk", [(1, 4, 3, 3), (2, 3, 2, 2), (5, 24, 95, 95), (9, 38, 130, 70),
+                                           (34, 60, 40, 33), (64, 80, 20, 9), (100, 120, 12, 10), (128, 140, 6, 5)])
+@pytest.mark.parametrize("sigma", [1.0, -1.0])
+def test_kernel_form_tiers_agree_with_oracle(ctx, occ, n_mo, kb, kk, sigma):
+    rng = np.random.default_rng(occ * 7 + kb)
+    np.random.seed(occ)
+    _, bra_mos, ket_mos = orc.bra_ket_dummy_mos(n_mo, occ)
+    S = orc.mo_overlap(bra_mos, ket_mos, orc.get_S_AO(bra_mos, ket_mos, "ket"))
+    bra, Cb, ket, Ck = _random_tables(rng, occ, n_mo - occ, kb, kk, 3, 4, with_gs=True)
+    want = orc.state_overlaps_bruteforce(S, occ, [tuple(e) for e in bra], Cb, [tuple(e) for e in ket], Ck, sigma)
+    for tier, code in (("lu", 0), ("update", 1)):
+        got = ctx.state_overlaps_host(S, occ, bra, Cb, ket, Ck, sigma=sigma, tier=tier)
+        assert ctx.last_tier() == code
+        assert_parity(got, want, rtol=1e-9)
+
+
+def test_shards_add_up_on_gpu(ctx):
+    rng = np.random.default_rng(3)
+    occ, n_mo = 9, 38
+    np.random.seed(3)
+    _, bra_mos, ket_mos = orc.bra_ket_dummy_mos(n_mo, occ)
+    S = orc.mo_overlap(bra_mos, ket_mos, orc.get_S_AO(bra_mos, ket_mos, "ket"))
+    bra, Cb, ket, Ck = _random_tables(rng, occ, n_mo - occ, 150, 77, 4, 3)
+    for tier in ("lu", "update"):
+        full = ctx.state_overlaps_host(S, occ, bra, Cb, ket, Ck, tier=tier)
+        parts = sum(ctx.state_overlaps_host(S, occ, bra, Cb, ket, Ck, tier=tier, k_begin=lo, k_end=hi)
+                    for lo, hi in ((0, 19), (19, 19), (19, 100), (100, 150)))
+        np.testing.assert_allclose(parts, full, rtol=1e-12, atol=1e-14 * np.abs(full).max())
+
+
+def test_singular_base_block_falls_back_to_lu(ctx):
+    """S_oo singular: the rank-update tier is not applicable, AUTO must use the brute force LU."""
+    rng = np.random.default_rng(8)
+    occ, n_mo = 6, 15
+    q, _ = np.linalg.qr(rng.standard_normal((n_mo, n_mo)))
+    S = q.copy()
+    S[2, :occ] = 0.0                                   # a zero row inside the occupied block
+    bra, Cb, ket, Ck = _random_tables(rng, occ, n_mo - occ, 30, 25, 2, 3)
+    want = orc.state_overlaps_bruteforce(S, occ, [tuple(e) for e in bra], Cb, [tuple(e) for e in ket], Ck, 1.0)
+    got = ctx.state_overlaps_host(S, occ, bra, Cb, ket, Ck, tier="auto")
+    assert ctx.last_tier() == 0
+    assert_parity(got, want, rtol=1e-9)
+    from pywfo_b200._lib import WfoError
+    with pytest.raises(WfoError, match="singular"):
+        ctx.state_overlaps_host(S, occ, bra, Cb, ket, Ck, tier="update")
+
+
+def test_device_pointer_entry_points(ctx):
+    """The *_dev functions on torch-owned device memory (torch = memory + stream only)."""
+    import torch
+    g = load_golden("r_n17")
+    occ = int(g["occ"])
+    from pywfo_b200 import excitations as ex
+    bt = ex.build_tables(g["bra_ci"], 0.05)
+    kt = ex.build_tables(g["ket_ci"], 0.05, order="locality")
+    dev = torch.device("cuda:0")
+    f64 = dict(dtype=torch.float64, device=dev)
+    bra, ket = torch.tensor(g["bra_mos"], **f64), torch.tensor(g["ket_mos"], **f64)
+    inv = torch.tensor(np.linalg.inv(g["ket_mos"]), **f64)
+    n_mo = bra.shape[0]
+    s_ao, s_mo = torch.empty((n_mo, n_mo), **f64), torch.empty((n_mo, n_mo), **f64)
+    st = torch.cuda.current_stream().cuda_stream
+    ctx.sao_dev(inv, s_ao, st)
+    ctx.smo_dev(bra, s_ao, ket, s_mo, st)
+    be = torch.tensor(bt.exc, dtype=torch.int32, device=dev)
+    ke = torch.tensor(kt.exc, dtype=torch.int32, device=dev)
+    cb, ck = torch.tensor(bt.coeff, **f64), torch.tensor(kt.coeff, **f64)
+    out = torch.empty((cb.shape[0], ck.shape[0]), **f64)
+    for tier in ("update", "lu"):
+        ctx.state_overlaps_dev(s_mo, occ, be, cb, ke, ck, out, tier=tier, stream=st)
+        torch.cuda.synchronize()
+        want, _ = orc.ref_overlaps_cache(g["bra_mos"], g["ket_mos"], g["bra_ci"], g["ket_ci"], occ, 0.05)
+        assert_parity(out.cpu().numpy(), want)
+    lists = torch.empty((bt.K, occ), dtype=torch.int32, device=dev)
+    ctx.exc_lists_dev(be, occ, lists, st)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(lists.cpu().numpy(), ex.exc_index_lists(bt.exc, occ))
+    assert ctx.launch_count() > 0
+
+
+# ---------------------------------------------------------------- BASELINE.json configs
+def test_config_water_full_cis(ctx):
+    """configs[1]: n_occ=5, n_mo=24, 10x10 states, full CIS space (K=95); full reference restatement."""
+    from pywfo_b200 import helpers, main
+    bra_mos, ket_mos, bci, kci = helpers.synthetic_case(0, 24, 5, 10, 10)
+    want, n_unique = orc.ref_overlaps_cache(bra_mos, ket_mos, bci, kci, 5, 0.0)
+    assert n_unique == 96 * 96
+    for tier in ("lu", "update"):
+        assert_parity(main.overlaps_cache(bra_mos, ket_mos, bci, kci, 5, ci_thresh=0.0, tier=tier), want)
+
+
+def test_config_naphthalene_triplet_truncated(ctx):
+    """configs[2]: n_occ=34, n_mo=180, sigma=-1 (main.overlaps); truncated to what the CPU finishes."""
+    from pywfo_b200 import helpers, main
+    bra_mos, ket_mos, bci, kci = helpers.synthetic_case(1, 180, 34, 3, 3, top_k=40)
+    want = orc.ref_overlaps_minus(bra_mos, ket_mos, bci, kci, 34, 1e-12)
+    for tier in ("lu", "update"):
+        assert_parity(main.overlaps(bra_mos, ket_mos, bci, kci, 34, ci_thresh=1e-12, tier=tier), want)
+
+
+def test_config_large_full_space_properties(ctx):
+    """configs[3]: n_occ=100, n_mo=500, 50x50 states, full CIS space (K=40 000 per side, 1.6e9 pairs).
+    The reference cannot run this; checked against the factored closed form (O(n^2 v) per state) and
+    through linearity in the bra coefficients."""
+    from pywfo_b200 import helpers, main
+    occ, n_mo, ns = 100, 500, 50
+    bra_mos, ket_mos, bci, kci = helpers.synthetic_case(2, n_mo, occ, ns, ns)
+    got = main.overlaps_cache(bra_mos, ket_mos, bci, kci, occ, ci_thresh=0.0, tier="update")
+    S = orc.mo_overlap(bra_mos, ket_mos, orc.get_S_AO(bra_mos, ket_mos, "ket"))
+    want = orc.state_overlaps_factored(S, occ, orc.signed_ci(bci, occ), orc.signed_ci(kci, occ), 1.0)
+    assert_parity(got, want, rtol=1e-9)
+    # linearity: state 0 replaced by a combination of states 1 and 2
+    b2 = bci.copy()
+    b2[0] = 0.25 * bci[1] - 1.5 * bci[2]
+    got2 = main.overlaps_cache(bra_mos, ket_mos, b2, kci, occ, ci_thresh=0.0, tier="update")
+    np.testing.assert_allclose(got2[0], 0.25 * got[1] - 1.5 * got[2], rtol=1e-9, atol=1e-12 * np.abs(got).max())
+    np.testing.assert_allclose(got2[1:], got[1:], rtol=1e-13, atol=0)
+
+
+def test_config_large_lu_sample(ctx):
+    """configs[3] shape, brute-force tier on a sample of the pair space (the full 1.6e9 LUs take
+    minutes): LU tier == update tier == oracle on the same sample."""
+    from pywfo_b200 import helpers
+    occ, n_mo = 100, 500
+    bra_mos, ket_mos, bci, kci = helpers.synthetic_case(2, n_mo, occ, 4, 5, top_k=24)
+    from pywfo_b200 import main
+    got_lu = main.overlaps_cache(bra_mos, ket_mos, bci, kci, occ, ci_thresh=1e-12, tier="lu")
+    got_up = main.overlaps_cache(bra_mos, ket_mos, bci, kci, occ, ci_thresh=1e-12, tier="update")
+    want, _ = orc.ref_overlaps_cache(bra_mos, ket_mos, bci, kci, occ, 1e-12)
+    assert_parity(got_lu, want, rtol=1e-9)
+    assert_parity(got_up, want, rtol=1e-9)
+
+
+@pytest.mark.parametrize("k", [32, 100])
+def test_config_sweep_n64(ctx, k):
+    """configs[4]: n_occ=64, n_mo=320, 8x8 states, K_b=K_k=k random excitations shared by all states."""
+    from pywfo_b200 import helpers
+    occ, n_mo = 64, 320
+    np.random.seed(3)
+    _, bra_mos, ket_mos = helpers.get_bra_ket_dummy_mos(n_mo, occ)
+    S = orc.mo_overlap(bra_mos, ket_mos, orc.get_S_AO(bra_mos, ket_mos, "ket"))
+    rng = np.random.default_rng(3 + k)
+    bra, Cb, ket, Ck = _random_tables(rng, occ, n_mo - occ, k, k, 8, 8)
+    want = orc.state_overlaps_closed_form(S, occ, [tuple(e) for e in bra], Cb, [tuple(e) for e in ket], Ck, 1.0)
+    for tier in ("lu", "update"):
+        assert_parity(ctx.state_overlaps_host(S, occ, bra, Cb, ket, Ck, tier=tier), want, rtol=1e-9)
