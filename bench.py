@@ -205,11 +205,12 @@ def run_ours(args, w):
     lo, hi = ex.shard_bounds(Kb, world, rank)
     c_inv = np.linalg.inv(ket_mos)
     f64 = dict(dtype=torch.float64, device=dev)
-    d_bra, d_ket, d_inv = (torch.tensor(x, **f64) for x in (bra_mos, ket_mos, c_inv))
+    d_bra, d_ket, d_inv = (torch.tensor(np.ascontiguousarray(x), **f64).contiguous()
+                           for x in (bra_mos, ket_mos, c_inv))
     d_sao, d_smo = torch.empty((n_mo, n_mo), **f64), torch.empty((n_mo, n_mo), **f64)
     d_be = torch.tensor(bt.exc, dtype=torch.int32, device=dev)
     d_ke = torch.tensor(kt.exc, dtype=torch.int32, device=dev)
-    d_cb, d_ck = torch.tensor(bt.coeff, **f64), torch.tensor(kt.coeff, **f64)
+    d_cb, d_ck = torch.tensor(bt.coeff, **f64).contiguous(), torch.tensor(kt.coeff, **f64).contiguous()
     d_out = torch.empty((bt.coeff.shape[0], kt.coeff.shape[0]), **f64)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     stream = torch.cuda.current_stream().cuda_stream

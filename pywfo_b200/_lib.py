@@ -171,13 +171,23 @@ class Context:
         return out
 
     # ---- device-pointer entry points (torch tensors used only as memory) ------
+    @staticmethod
+    def _dev(*tensors):
+        """Device tensors must be dense row-major: the C ABI sees raw pointers."""
+        for t in tensors:
+            if not t.is_cuda or not t.is_contiguous():
+                raise ValueError("device entry points need contiguous CUDA tensors "
+                                 f"(got device={t.device}, strides={tuple(t.stride())})")
+
     def smo_dev(self, bra, s_ao, ket, out, stream=0):
+        self._dev(bra, s_ao, ket, out)
         p, u = bra.shape
         q, v = ket.shape
         check(self.lib.wfo_smo_dev(self.handle, bra.data_ptr(), s_ao.data_ptr(), ket.data_ptr(), p, u, v, q,
                                    out.data_ptr(), None, stream))
 
     def sao_dev(self, c_inv, out, stream=0):
+        self._dev(c_inv, out)
         check(self.lib.wfo_sao_dev(self.handle, c_inv.data_ptr(), c_inv.shape[0], out.data_ptr(), stream))
 
     def gemm_dev(self, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, Cm, ldc, stream=0):
@@ -185,15 +195,18 @@ class Context:
                                     B.data_ptr(), ldb, float(beta), Cm.data_ptr(), ldc, stream))
 
     def det_table_dev(self, s_mo, n, rows, cols, out, stream=0):
+        self._dev(rows, cols, out)
         check(self.lib.wfo_det_table_dev(self.handle, s_mo.data_ptr(), s_mo.shape[0], s_mo.stride(0), n,
                                          rows.data_ptr(), rows.shape[0], cols.data_ptr(), cols.shape[0],
                                          out.data_ptr(), stream))
 
     def exc_lists_dev(self, exc, n_occ, lists, stream=0):
+        self._dev(exc, lists)
         check(self.lib.wfo_exc_lists_dev(self.handle, exc.data_ptr(), exc.shape[0], n_occ, lists.data_ptr(), stream))
 
     def state_overlaps_dev(self, s_mo, n_occ, bra_exc, Cb, ket_exc, Ck, out, sigma=1.0, tier="auto",
                            k_begin=0, k_end=None, stream=0):
+        self._dev(s_mo, bra_exc, Cb, ket_exc, Ck, out)
         kb, kk = bra_exc.shape[0], ket_exc.shape[0]
         k_end = kb if k_end is None else k_end
         check(self.lib.wfo_state_overlaps_dev(self.handle, s_mo.data_ptr(), s_mo.shape[0], int(n_occ),

@@ -237,8 +237,13 @@ def test_device_pointer_entry_points(ctx):
     kt = ex.build_tables(g["ket_ci"], 0.05, order="locality")
     dev = torch.device("cuda:0")
     f64 = dict(dtype=torch.float64, device=dev)
-    bra, ket = torch.tensor(g["bra_mos"], **f64), torch.tensor(g["ket_mos"], **f64)
-    inv = torch.tensor(np.linalg.inv(g["ket_mos"]), **f64)
+    # the golden MOs are transposed views (F-ordered): the C ABI wants dense row-major
+    with pytest.raises(ValueError):
+        t = torch.zeros((4, 6), **f64).t()
+        ctx.sao_dev(t, torch.zeros((6, 6), **f64))
+    bra = torch.tensor(np.ascontiguousarray(g["bra_mos"]), **f64).contiguous()
+    ket = torch.tensor(np.ascontiguousarray(g["ket_mos"]), **f64).contiguous()
+    inv = torch.tensor(np.linalg.inv(g["ket_mos"]), **f64).contiguous()
     n_mo = bra.shape[0]
     s_ao, s_mo = torch.empty((n_mo, n_mo), **f64), torch.empty((n_mo, n_mo), **f64)
     st = torch.cuda.current_stream().cuda_stream
