@@ -293,7 +293,7 @@ def run_ours(args, w):
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_s = float(t_e2e.item())
-    h2d = 3 * n_mo * n_mo * 8 + bt.exc.nbytes + kt.exc.nbytes + bt.coeff.nbytes + kt.coeff.nbytes
+    h2d = 3 * n_mo * n_mo * 8 + bci.nbytes + kci.nbytes   # MOs + inverse + raw CI tensors
     d2h = int(res.nbytes)
     e2e_err = float(np.abs(res - result_first).max() / max(np.abs(result_first).max(), 1e-300))
 

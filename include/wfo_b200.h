@@ -37,6 +37,7 @@ extern "C" {
 #define WFO_ERR_CUDA 1
 #define WFO_ERR_ARG 2
 #define WFO_ERR_SINGULAR 3 /* base block S_MO[:occ,:occ] singular: tier 1/2 not applicable */
+#define WFO_ERR_EMPTY_STATE 4 /* pywfo.main.overlaps semantics: a state keeps no excitation (ValueError upstream) */
 
 /* algorithm tiers (identical results to ~1e-13) */
 #define WFO_TIER_LU 0      /* T0: one partially pivoted LU per determinant pair          */
@@ -115,6 +116,19 @@ int wfo_overlaps_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos
                       const double *Cb, int n_bra, const int32_t *ket_exc, int kk,
                       const double *Ck, int n_ket, double sigma, int tier, int k_begin,
                       int k_end, double *out);
+/* The whole path from the RAW CI tensors (what pywfo_b200.main.overlaps* uses): the
+ * selection of excitations -- pywfo/main.py:539-540 (|c| >= thr per state, semantics 0,
+ * sigma=+1: overlaps_cache / overlaps_naive / overlaps_most_naive) or main.py:112,122-123
+ * (|c| > thr, semantics 1, sigma=-1 and the sign^occ factor of main.py:154,176: overlaps)
+ * -- runs on the device too, so the host only supplies bra_ci (n_bra, n_occ, n_virt),
+ * ket_ci (n_ket, n_occ, n_virt) and the MO matrices.  The bra excitations are sharded
+ * over `world` ranks ([rank] gets a contiguous, balanced slice); `out` is this rank's
+ * partial matrix.  info (may be NULL) receives {K_bra, K_ket, empty_state, tier_used}.
+ * Returns WFO_ERR_EMPTY_STATE for semantics 1 when a state keeps no excitation. */
+int wfo_overlaps_ci_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos,
+                         const double *c_inv, int n_mo, int n_occ, const double *bra_ci, int n_bra,
+                         const double *ket_ci, int n_ket, double ci_thresh, int semantics, int tier,
+                         int rank, int world, double *out, int32_t *info);
 /* tier actually used by the last wfo_state_overlaps_* call of this context */
 int wfo_last_tier(const wfo_ctx *ctx);
 /* device time (ms, CUDA events on the launching stream) of the dominant

@@ -45,6 +45,8 @@ SIGNATURES = {
                                           c_vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, c_vp]),
     "wfo_overlaps_host": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, C.c_int, c_vp, C.c_int, c_vp,
                                     C.c_int, c_vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, c_vp]),
+    "wfo_overlaps_ci_host": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, C.c_int, c_vp, C.c_int,
+                                       C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
     "wfo_last_tier": (C.c_int, [c_vp]),
     "wfo_set_timing": (C.c_int, [c_vp, C.c_int]),
     "wfo_last_kernel_ms": (C.c_double, [c_vp]),
@@ -169,6 +171,28 @@ class Context:
                                          ck.shape[0], float(sigma), TIERS[tier], int(k_begin), int(k_end),
                                          _hptr(out)))
         return out
+
+    def overlaps_ci_host(self, bra_mos, ket_mos, c_inv, n_occ, bra_ci, ket_ci, ci_thresh, semantics=0,
+                         tier="auto", rank=0, world=1):
+        """Whole path from raw CI tensors; excitation selection on the device.
+        Returns (partial matrix, info = [K_bra, K_ket, empty_state, tier_used])."""
+        bra, ket, inv = as_f64(bra_mos), as_f64(ket_mos), as_f64(c_inv)
+        bci, kci = as_f64(bra_ci), as_f64(ket_ci)
+        n_mo = bra.shape[0]
+        if bra.shape != (n_mo, n_mo) or ket.shape != (n_mo, n_mo) or inv.shape != (n_mo, n_mo):
+            raise ValueError("MO matrices must be square and of equal shape")
+        if bci.ndim != 3 or kci.ndim != 3 or bci.shape[1:] != (n_occ, n_mo - n_occ) or kci.shape[1:] != bci.shape[1:]:
+            raise ValueError("CI coefficients must have shape (n_states, occ, n_mo - occ)")
+        out = np.empty((bci.shape[0], kci.shape[0]))
+        info = np.zeros(4, dtype=np.int32)
+        rc = self.lib.wfo_overlaps_ci_host(self.handle, _hptr(bra), _hptr(ket), _hptr(inv), n_mo, int(n_occ),
+                                           _hptr(bci), bci.shape[0], _hptr(kci), kci.shape[0], float(ci_thresh),
+                                           int(semantics), TIERS[tier], int(rank), int(world), _hptr(out),
+                                           _hptr(info))
+        if rc == 4:
+            raise ValueError("not enough values to unpack (expected 2, got 0)")   # pywfo/main.py:186
+        check(rc)
+        return out, info
 
     # ---- device-pointer entry points (torch tensors used only as memory) ------
     @staticmethod

@@ -1,13 +1,16 @@
 // extern "C" entry points of libwfo_b200.so (see include/wfo_b200.h).
 #include <math.h>
+#include <stdlib.h>
 #include <new>
 
 #include "common.cuh"
+#include "det_lu_blocked.cuh"
 #include "det_lu_v1.cuh"
 #include "gemm_f64.cuh"
 #include "lu_base.cuh"
 #include "misc_kernels.cuh"
 #include "pair_update.cuh"
+#include "tables.cuh"
 
 namespace wfo {
 thread_local char g_err[512] = "";
@@ -44,6 +47,20 @@ static int ensure_scratch(wfo_ctx *ctx, size_t bytes) {
     return WFO_OK;
 }
 
+// grow the arena but keep its first keep_bytes (device-to-device copy)
+static int ensure_scratch_keep(wfo_ctx *ctx, size_t bytes, size_t keep_bytes) {
+    if (bytes <= ctx->scratch_bytes) return WFO_OK;
+    WFO_CUDA(cudaDeviceSynchronize());
+    size_t want = bytes + bytes / 4 + (1 << 20);
+    char *fresh = nullptr;
+    WFO_CUDA(cudaMalloc(&fresh, want));
+    if (ctx->scratch && keep_bytes) WFO_CUDA(cudaMemcpy(fresh, ctx->scratch, keep_bytes, cudaMemcpyDeviceToDevice));
+    if (ctx->scratch) WFO_CUDA(cudaFree(ctx->scratch));
+    ctx->scratch = fresh;
+    ctx->scratch_bytes = want;
+    return WFO_OK;
+}
+
 #define WFO_LAUNCH_CHECK(ctx)                 \
     do {                                      \
         (ctx)->launches++;                    \
@@ -68,20 +85,53 @@ static int gemm(wfo_ctx *ctx, bool ta, bool tb, int m, int n, int k, double alph
 static size_t t0_smem_bytes(int n) { return (size_t)n * (n | 1) * sizeof(double) + 2 * (size_t)n * sizeof(int); }
 static int t0_threads(int n) { return n > 64 ? 256 : 128; }
 
+static bool use_v1() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("WFO_T0_V1"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
+// blocked-kernel configuration by matrix size: (warps, rows per lane of the panel warp)
+#define WFO_BLK_DISPATCH(n, CALL)                      \
+    do {                                               \
+        if ((n) <= 32) { CALL(2, 1); }                 \
+        else if ((n) <= 64) { CALL(4, 2); }            \
+        else if ((n) <= 96) { CALL(8, 3); }            \
+        else { CALL(8, 4); }                           \
+    } while (0)
+
+template <typename K>
+static int persistent_grid(wfo_ctx *ctx, K kernel, int threads, size_t smem, long long items, unsigned *grid) {
+    WFO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    WFO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long g = (long long)ctx->sm_count * per_sm;
+    if (g > items) g = items;
+    *grid = (unsigned)g;
+    return WFO_OK;
+}
+
 static int det_table(wfo_ctx *ctx, const double *S, int ld_s, int n, const int32_t *rows, int kb,
                      const int32_t *cols, int kk, double *D, cudaStream_t st) {
     long long npairs = (long long)kb * kk;
     if (npairs <= 0) return WFO_OK;
-    size_t smem = t0_smem_bytes(n);
-    if (n < 1 || n > 128 || smem > ctx->smem_optin)
+    if (n < 1 || n > 128)
         return set_err(WFO_ERR_ARG, "det_table: n_occ=%lld outside the supported range 1..128%s", "", n);
-    WFO_CUDA(cudaFuncSetAttribute(det_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int threads = t0_threads(n), per_sm = 1;
-    WFO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, det_table_kernel, threads, smem));
-    if (per_sm < 1) per_sm = 1;
-    long long grid = (long long)ctx->sm_count * per_sm;
-    if (grid > npairs) grid = npairs;
-    det_table_kernel<<<(unsigned)grid, threads, smem, st>>>(S, ld_s, n, rows, kb, cols, kk, D);
+    unsigned grid = 1;
+    if (use_v1()) {
+        size_t smem = t0_smem_bytes(n);
+        int threads = t0_threads(n);
+        WFO_TRY(persistent_grid(ctx, det_table_kernel, threads, smem, npairs, &grid));
+        det_table_kernel<<<grid, threads, smem, st>>>(S, ld_s, n, rows, kb, cols, kk, D);
+    } else {
+        size_t smem = blk_smem_bytes(n);
+#define CALL_DT(W, SL)                                                                                   \
+    WFO_TRY(persistent_grid(ctx, det_table_blk_kernel<W, SL>, W * 32, smem, npairs, &grid));             \
+    det_table_blk_kernel<W, SL><<<grid, W * 32, smem, st>>>(S, ld_s, n, rows, kb, cols, kk, D)
+        WFO_BLK_DISPATCH(n, CALL_DT);
+#undef CALL_DT
+    }
     WFO_LAUNCH_CHECK(ctx);
     return WFO_OK;
 }
@@ -467,17 +517,25 @@ static int state_overlaps_impl(wfo_ctx *ctx, size_t arena_off, const double *s_m
         long long ctot = (long long)kk * ldg;
         ckt_kernel<<<(unsigned)((ctot + 255) / 256), 256, 0, st>>>(Ck, kk, n_ket, nullptr, ldg, p.ckt);
         WFO_LAUNCH_CHECK(ctx);
-        size_t smem = t0_smem_bytes(n);
-        WFO_CUDA(cudaFuncSetAttribute(t0_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int threads = t0_threads(n), per_sm = 1;
-        WFO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, t0_fused_kernel, threads, smem));
-        if (per_sm < 1) per_sm = 1;
-        long long items = (long long)ksh * t0_chunks;
-        long long grid = (long long)ctx->sm_count * per_sm;
-        if (grid > items) grid = items;
-        if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev0, st));
-        t0_fused_kernel<<<(unsigned)grid, threads, smem, st>>>(s_mo, n_mo, n, p.bra_lists, ksh, p.ket_lists, kk,
-                                                              p.ckt, ldg, chunk_len, t0_chunks, p.gpart);
+        const long long items = (long long)ksh * t0_chunks;
+        unsigned grid = 1;
+        if (use_v1()) {
+            size_t smem = t0_smem_bytes(n);
+            int threads = t0_threads(n);
+            WFO_TRY(persistent_grid(ctx, t0_fused_kernel, threads, smem, items, &grid));
+            if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev0, st));
+            t0_fused_kernel<<<grid, threads, smem, st>>>(s_mo, n_mo, n, p.bra_lists, ksh, p.ket_lists, kk, p.ckt,
+                                                         ldg, chunk_len, t0_chunks, p.gpart);
+        } else {
+            size_t smem = blk_smem_bytes(n);
+#define CALL_FU(W, SL)                                                                                        \
+    WFO_TRY(persistent_grid(ctx, t0_fused_blk_kernel<W, SL>, W * 32, smem, items, &grid));                    \
+    if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev0, st));                                                 \
+    t0_fused_blk_kernel<W, SL><<<grid, W * 32, smem, st>>>(s_mo, n_mo, n, p.bra_lists, ksh, p.ket_lists, kk, \
+                                                           p.ckt, ldg, chunk_len, t0_chunks, p.gpart)
+            WFO_BLK_DISPATCH(n, CALL_FU);
+#undef CALL_FU
+        }
         WFO_LAUNCH_CHECK(ctx);
         if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev1, st));
         d00_ptr = p.d00;
@@ -589,6 +647,141 @@ int wfo_overlaps_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos
     if (!bra_mos || !ket_mos || !c_inv) return set_err(WFO_ERR_ARG, "overlaps_host: NULL MO pointer%s");
     return host_front(ctx, nullptr, bra_mos, ket_mos, c_inv, n_mo, n_occ, bra_exc, kb, Cb, n_bra, ket_exc, kk, Ck,
                       n_ket, sigma, tier, k_begin, k_end, out);
+}
+
+/* ---- the whole path from RAW CI tensors: selection of excitations on the device ---- */
+struct DevTables {
+    int32_t *exc;     // (K, 2)
+    double *coeff;    // (n_states, K)
+    int K;
+};
+
+// build one side's tables.  ci_dev: (n_states, n, v) on the device.  flags/offs/exc_buf are
+// caller-provided device buffers of n*v ints / n*v ints / 2*n*v ints; totals: 1 int + n_states ints.
+static int build_tables_dev(wfo_ctx *ctx, const double *ci_dev, int n_states, int n, int v, double thr, int strict,
+                            int order, int *flags, int *offs, int *totals, cudaStream_t st) {
+    const int count = n * v;
+    if (count <= 0) return WFO_OK;
+    union_flags_kernel<<<cdiv(count, 256), 256, 0, st>>>(ci_dev, n_states, n, v, thr, strict, order, flags);
+    WFO_LAUNCH_CHECK(ctx);
+    scan_flags_kernel<<<1, 1024, 0, st>>>(flags, count, offs, totals);
+    WFO_LAUNCH_CHECK(ctx);
+    state_counts_kernel<<<n_states, 256, 0, st>>>(ci_dev, n, v, thr, strict, totals + 1);
+    WFO_LAUNCH_CHECK(ctx);
+    return WFO_OK;
+}
+
+int wfo_overlaps_ci_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos, const double *c_inv, int n_mo,
+                         int n_occ, const double *bra_ci, int n_bra, const double *ket_ci, int n_ket,
+                         double ci_thresh, int semantics, int tier, int rank, int world, double *out,
+                         int32_t *info) {
+    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL%s");
+    if (!bra_mos || !ket_mos || !c_inv || !bra_ci || !ket_ci || !out)
+        return set_err(WFO_ERR_ARG, "overlaps_ci_host: NULL pointer%s");
+    if (n_mo < 1 || n_occ < 1 || n_occ > n_mo || n_bra < 1 || n_ket < 1 || world < 1 || rank < 0 || rank >= world)
+        return set_err(WFO_ERR_ARG, "overlaps_ci_host: bad sizes%s");
+    if (semantics != 0 && semantics != 1) return set_err(WFO_ERR_ARG, "overlaps_ci_host: semantics must be 0 or 1%s");
+    WFO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int n = n_occ, v = n_mo - n_occ, count = n * v;
+    const int strict = semantics == 1;
+    const double sigma = semantics == 1 ? -1.0 : 1.0;
+    const size_t nsq = (size_t)n_mo * n_mo;
+    if (info) { info[0] = info[1] = 0; info[2] = 0; info[3] = -1; }
+    if (count == 0) {   // no virtual orbitals: no excitations, all sums are empty
+        memset(out, 0, (size_t)n_bra * n_ket * sizeof(double));
+        return WFO_OK;
+    }
+    // ---- phase 1: uploads, S_MO chain, flags + scans
+    Sizer sz;
+    sz.take<double>(nsq); sz.take<double>(nsq); sz.take<double>(nsq); sz.take<double>(nsq); sz.take<double>(nsq); sz.take<double>(nsq);
+    sz.take<double>((size_t)n_bra * count); sz.take<double>((size_t)n_ket * count);
+    sz.take<int>(count); sz.take<int>(count); sz.take<int>(count); sz.take<int>(count);
+    sz.take<int>(1 + n_bra); sz.take<int>(1 + n_ket);
+    sz.take<int32_t>(2 * (size_t)count); sz.take<int32_t>(2 * (size_t)count);
+    sz.take<double>((size_t)n_bra * n_ket);
+    WFO_TRY(ensure_scratch(ctx, sz.off));
+    Arena ar{ctx->scratch, ctx->scratch_bytes, 0};
+    double *d_smo = ar.take<double>(nsq), *d_bra = ar.take<double>(nsq), *d_ket = ar.take<double>(nsq),
+           *d_inv = ar.take<double>(nsq), *d_sao = ar.take<double>(nsq), *d_work = ar.take<double>(nsq);
+    double *d_bci = ar.take<double>((size_t)n_bra * count), *d_kci = ar.take<double>((size_t)n_ket * count);
+    int *fl_b = ar.take<int>(count), *of_b = ar.take<int>(count), *fl_k = ar.take<int>(count), *of_k = ar.take<int>(count);
+    int *tot_b = ar.take<int>(1 + n_bra), *tot_k = ar.take<int>(1 + n_ket);
+    int32_t *exc_b = ar.take<int32_t>(2 * (size_t)count), *exc_k = ar.take<int32_t>(2 * (size_t)count);
+    double *d_out = ar.take<double>((size_t)n_bra * n_ket);
+    const size_t front1 = ar.off;
+    WFO_CUDA(cudaMemcpyAsync(d_bci, bra_ci, (size_t)n_bra * count * 8, cudaMemcpyHostToDevice, st));
+    WFO_CUDA(cudaMemcpyAsync(d_kci, ket_ci, (size_t)n_ket * count * 8, cudaMemcpyHostToDevice, st));
+    WFO_TRY(build_tables_dev(ctx, d_bci, n_bra, n, v, ci_thresh, strict, 0, fl_b, of_b, tot_b, st));
+    WFO_TRY(build_tables_dev(ctx, d_kci, n_ket, n, v, ci_thresh, strict, 1, fl_k, of_k, tot_k, st));
+    WFO_CUDA(cudaMemcpyAsync(d_bra, bra_mos, nsq * 8, cudaMemcpyHostToDevice, st));
+    WFO_CUDA(cudaMemcpyAsync(d_ket, ket_mos, nsq * 8, cudaMemcpyHostToDevice, st));
+    WFO_CUDA(cudaMemcpyAsync(d_inv, c_inv, nsq * 8, cudaMemcpyHostToDevice, st));
+    WFO_TRY(wfo_sao_dev(ctx, d_inv, n_mo, d_sao, st));
+    WFO_TRY(wfo_smo_dev(ctx, d_bra, d_sao, d_ket, n_mo, n_mo, n_mo, n_mo, d_smo, d_work, st));
+    // ---- the table sizes (and per-state counts) come back: 2 small copies, one sync
+    int hb[1 + 64], hk[1 + 64];
+    if (n_bra > 64 || n_ket > 64) return set_err(WFO_ERR_ARG, "overlaps_ci_host: more than 64 states not supported%s");
+    WFO_CUDA(cudaMemcpyAsync(hb, tot_b, (1 + n_bra) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    WFO_CUDA(cudaMemcpyAsync(hk, tot_k, (1 + n_ket) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    WFO_CUDA(cudaStreamSynchronize(st));
+    const int kb = hb[0], kk = hk[0];
+    if (info) { info[0] = kb; info[1] = kk; }
+    if (semantics == 1) {   // pywfo/main.py:186: a state without excitations cannot be unpacked
+        for (int i = 0; i < n_bra; i++) if (hb[1 + i] == 0) { if (info) info[2] = 1; }
+        for (int i = 0; i < n_ket; i++) if (hk[1 + i] == 0) { if (info) info[2] = 1; }
+        if (info && info[2]) return set_err(WFO_ERR_EMPTY_STATE, "overlaps: a state keeps no excitation above the threshold%s");
+    }
+    if (kb == 0 || kk == 0) {
+        memset(out, 0, (size_t)n_bra * n_ket * sizeof(double));
+        return WFO_OK;
+    }
+    // ---- phase 2: coefficient matrices, then the fused stages on this rank's shard
+    const int base = kb / world, rem = kb % world;
+    const int k_begin = rank * base + (rank < rem ? rank : rem);
+    const int k_end = k_begin + base + (rank < rem ? 1 : 0);
+    size_t total = front1 + align_up((size_t)n_bra * kb * 8, 256) + align_up((size_t)n_ket * kk * 8, 256);
+    {
+        bool want_t1 = false, may_t0 = false;
+        WFO_TRY(resolve_tier(ctx, n, tier, &want_t1, &may_t0));
+        const int ksh = k_end - k_begin;
+        if (ksh > 0) {
+            Part q = make_part(ctx, ksh, kk, n_ket, may_t0, want_t1);
+            Plan p;
+            Sizer s2;
+            s2.off = total;
+            carve(s2, p, n, v, ksh, kk, n_bra, q.ldg, q.n_parts, q.n_slabs, may_t0, want_t1);
+            total = s2.off;
+        }
+    }
+    char *before = ctx->scratch;
+    WFO_TRY(ensure_scratch_keep(ctx, total, front1));
+    const ptrdiff_t shift = ctx->scratch - before;   // arena may have moved: rebase the pointers
+    d_smo = (double *)((char *)d_smo + shift); d_bci = (double *)((char *)d_bci + shift); d_kci = (double *)((char *)d_kci + shift);
+    fl_b = (int *)((char *)fl_b + shift); of_b = (int *)((char *)of_b + shift);
+    fl_k = (int *)((char *)fl_k + shift); of_k = (int *)((char *)of_k + shift);
+    exc_b = (int32_t *)((char *)exc_b + shift); exc_k = (int32_t *)((char *)exc_k + shift);
+    d_out = (double *)((char *)d_out + shift);
+    Arena ar2{ctx->scratch, ctx->scratch_bytes, front1};
+    double *d_cb = ar2.take<double>((size_t)n_bra * kb), *d_ck = ar2.take<double>((size_t)n_ket * kk);
+    emit_exc_kernel<<<cdiv(count, 256), 256, 0, st>>>(fl_b, of_b, n, v, 0, exc_b);
+    WFO_LAUNCH_CHECK(ctx);
+    emit_exc_kernel<<<cdiv(count, 256), 256, 0, st>>>(fl_k, of_k, n, v, 1, exc_k);
+    WFO_LAUNCH_CHECK(ctx);
+    emit_coeff_kernel<<<dim3(cdiv(count, 256), n_bra), 256, 0, st>>>(d_bci, fl_b, of_b, n, v, ci_thresh, strict, 0,
+                                                                    semantics == 1, kb, d_cb);
+    WFO_LAUNCH_CHECK(ctx);
+    emit_coeff_kernel<<<dim3(cdiv(count, 256), n_ket), 256, 0, st>>>(d_kci, fl_k, of_k, n, v, ci_thresh, strict, 1,
+                                                                    semantics == 1, kk, d_ck);
+    WFO_LAUNCH_CHECK(ctx);
+    char *before2 = ctx->scratch;
+    WFO_TRY(state_overlaps_impl(ctx, ar2.off, d_smo, n_mo, n, exc_b, kb, d_cb, n_bra, exc_k, kk, d_ck, n_ket, sigma,
+                                tier, k_begin, k_end, d_out, st));
+    if (ctx->scratch != before2) return set_err(WFO_ERR_CUDA, "internal: arena moved during a host call%s");
+    if (info) info[3] = ctx->last_tier;
+    WFO_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n_bra * n_ket * 8, cudaMemcpyDeviceToHost, st));
+    WFO_CUDA(cudaStreamSynchronize(st));
+    return WFO_OK;
 }
 
 /* ------------------------------------------------------------ measurement */

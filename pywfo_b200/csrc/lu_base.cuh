@@ -28,11 +28,9 @@ base_inverse_kernel(const double *__restrict__ A_src, int ld_src, int n, double 
     extern __shared__ double sm[];
     const int ld = n | 1;                  // odd stride: conflict-free column walks
     double *a = sm;                        // n x ld
-    double *colj = a + (size_t)n * ld;     // n   (eliminated column)
+    double *colj = a + (size_t)n * ld;     // n   (unused spare column)
     int *piv = (int *)(colj + n);          // n
-    __shared__ double red_v[LUB_THREADS / 32];
     __shared__ int red_i[LUB_THREADS / 32];
-    __shared__ int s_p;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int idx = tid; idx < n * n; idx += LUB_THREADS) {
@@ -43,60 +41,54 @@ base_inverse_kernel(const double *__restrict__ A_src, int ld_src, int n, double 
     int singular = 0;
     __syncthreads();
 
+    const int nwarps = LUB_THREADS / 32;
     for (int j = 0; j < n; j++) {
-        // pivot search over rows j..n-1 of column j
-        double best = -1.0;
-        int bi = j;
-        for (int r = j + tid; r < n; r += LUB_THREADS) {
-            double v = fabs(a[r * ld + j]);
-            if (v > best) { best = v; bi = r; }
-        }
+        // ---- pivot search over rows j..n-1 of column j: REDUX over (|a| high word | row)
+        unsigned key = 0;
+        for (int r = j + tid; r < n; r += LUB_THREADS)
+            key = max(key, (hi_abs(a[r * ld + j]) & 0xffffff00u) | (unsigned)r);   // n <= 160 < 256
+        key = __reduce_max_sync(0xffffffffu, key);
+        if (lane == 0) red_i[warp] = (int)key;
+        __syncthreads();
+        unsigned kmax = 0;
 #pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            double ov = __shfl_xor_sync(0xffffffffu, best, o);
-            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-        }
-        if (lane == 0) { red_v[warp] = best; red_i[warp] = bi; }
-        __syncthreads();
-        if (tid == 0) {
-            double bv = red_v[0];
-            int bb = red_i[0];
-            for (int w = 1; w < LUB_THREADS / 32; w++)
-                if (red_v[w] > bv || (red_v[w] == bv && red_i[w] < bb)) { bv = red_v[w]; bb = red_i[w]; }
-            s_p = bb;
-            piv[j] = bb;
-        }
-        __syncthreads();
-        const int p = s_p;
-        if (p != j) {
-            for (int c = tid; c < n; c += LUB_THREADS) {
-                double x = a[j * ld + c];
-                a[j * ld + c] = a[p * ld + c];
-                a[p * ld + c] = x;
-            }
-            det = -det;
-        }
-        __syncthreads();
-        const double d = a[j * ld + j];
-        det *= d;
+        for (int w = 0; w < nwarps; w++) kmax = max(kmax, (unsigned)red_i[w]);
+        const int p = (int)(kmax & 0xffu);
+        if (tid == 0) piv[j] = p;
+        const double d = a[p * ld + j];          // pivot value (before the swap)
         const double ad = fabs(d);
+        if (!(ad > 0.0) || !isfinite(d)) { singular = 1; break; }   // uniform
+        det *= (p != j) ? -d : d;
         minp = fmin(minp, ad);
         maxp = fmax(maxp, ad);
-        if (!(ad > 0.0) || !isfinite(d)) { singular = 1; break; }   // uniform: d is shared
         const double rd = 1.0 / d;
-        // save column j, scale pivot row
-        for (int r = tid; r < n; r += LUB_THREADS) colj[r] = a[r * ld + j];
-        __syncthreads();
-        for (int c = tid; c < n; c += LUB_THREADS) a[j * ld + c] = (c == j ? 1.0 : a[j * ld + c]) * rd;
-        __syncthreads();
-        // eliminate column j from every other row:  row_i -= colj[i] * row_j, a[i][j] = -colj[i]*rd
-        for (int idx = tid; idx < n * n; idx += LUB_THREADS) {
-            int r = idx / n, c = idx % n;
-            if (r == j) continue;
-            double f = colj[r];
-            double base = (c == j) ? 0.0 : a[r * ld + c];
-            a[r * ld + c] = base - f * a[j * ld + c];
+        // ---- lanes own columns (4 per lane), warps walk rows.  Row swap folded in:
+        //      new row j = old row p scaled, new row p = old row j eliminated.
+        double pr[5], oj[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const int c = lane + 32 * k;
+            pr[k] = (c < n) ? ((c == j) ? 1.0 : a[p * ld + c]) * rd : 0.0;   // scaled pivot row
+            oj[k] = (c < n) ? a[j * ld + c] : 0.0;                            // old row j
+        }
+        const double fj = a[j * ld + j];           // old a[j][j]: multiplier of the displaced row
+        __syncthreads();                          // everyone has read rows j and p
+        for (int r = warp; r < n; r += nwarps) {
+            if (r == j) {
+#pragma unroll
+                for (int k = 0; k < 5; k++) { const int c = lane + 32 * k; if (c < n) a[j * ld + c] = pr[k]; }
+            } else {
+                const bool is_p = (r == p);
+                const double f = is_p ? fj : a[r * ld + j];
+#pragma unroll
+                for (int k = 0; k < 5; k++) {
+                    const int c = lane + 32 * k;
+                    if (c < n) {
+                        const double base = (c == j) ? 0.0 : (is_p ? oj[k] : a[r * ld + c]);
+                        a[r * ld + c] = fma(-f, pr[k], base);
+                    }
+                }
+            }
         }
         __syncthreads();
     }

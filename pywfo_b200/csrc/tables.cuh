@@ -1,0 +1,120 @@
+// Device-side excitation selection (replaces the host loops pywfo/main.py:539-540,
+// 554-560, 589-611 and main.py:109-134): from the raw CI tensor ci[state][from][to]
+// build the union excitation table and the per-state coefficient matrix with exact
+// zeros where a state drops an excitation -- the form the determinant kernels consume.
+//
+//   flags   : union over states of |c| >= thr (">" when strict), one per (from, to)
+//   scan    : exclusive prefix sum in traversal order (single CTA, n_occ*n_virt flags)
+//   emit    : exc[k] = (from, to);  coeff[s][k] = keep(s) ? c * factor(from) : 0
+//
+// Traversal order 0 = row major (from, to) like np.nonzero; order 1 = "locality"
+// (to/32, from, to%32), the order the rank-update kernel wants for its ket list
+// (a CTA's window of W stays within 32 columns at a time).  factor(from) is 1 for
+// the singlet family and ((-1)^(occ-from+1))^occ for pywfo.main.overlaps
+// (main.py:154, 176: det(sign*M) = sign^occ det(M)).
+#pragma once
+#include "common.cuh"
+
+namespace wfo {
+
+__device__ __forceinline__ void pos_to_ft(int pos, int n, int v, int order, int &f, int &t) {
+    if (order == 0) {
+        f = pos / v;
+        t = pos - f * v;
+    } else {
+        const int nfull = v >> 5;
+        const int per = n << 5;
+        int b = pos / per;
+        if (b > nfull) b = nfull;
+        const int q = pos - b * per;
+        const int wb = (b < nfull) ? 32 : (v & 31);
+        f = q / wb;
+        t = (b << 5) + (q - f * wb);
+    }
+}
+
+__device__ __forceinline__ bool ci_keep(double c, double thr, int strict) {
+    const double a = fabs(c);
+    return strict ? (a > thr) : (a >= thr);
+}
+
+__global__ void union_flags_kernel(const double *__restrict__ ci, int n_states, int n, int v, double thr,
+                                   int strict, int order, int *__restrict__ flags) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= n * v) return;
+    int f, t;
+    pos_to_ft(pos, n, v, order, f, t);
+    const size_t off = (size_t)f * v + t, stride = (size_t)n * v;
+    int any = 0;
+    for (int s = 0; s < n_states; s++) any |= ci_keep(ci[s * stride + off], thr, strict) ? 1 : 0;
+    flags[pos] = any;
+}
+
+// kept[s] = number of excitations state s keeps (main.overlaps raises on 0, main.py:186)
+__global__ void __launch_bounds__(256)
+state_counts_kernel(const double *__restrict__ ci, int n, int v, double thr, int strict, int *__restrict__ kept) {
+    __shared__ int red[256];
+    const int s = blockIdx.x;
+    const size_t stride = (size_t)n * v;
+    int cnt = 0;
+    for (size_t i = threadIdx.x; i < stride; i += 256) cnt += ci_keep(ci[s * stride + i], thr, strict) ? 1 : 0;
+    red[threadIdx.x] = cnt;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) kept[s] = red[0];
+}
+
+// exclusive scan of `count` flags by one CTA of 1024 threads; total -> *total_out
+__global__ void __launch_bounds__(1024)
+scan_flags_kernel(const int *__restrict__ flags, int count, int *__restrict__ offs, int *__restrict__ total_out) {
+    __shared__ int part[1024];
+    const int tid = threadIdx.x;
+    const int per = (count + 1023) / 1024;
+    const int b = tid * per, e = min(count, b + per);
+    int sum = 0;
+    for (int i = b; i < e; i++) sum += flags[i];
+    part[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {   // Hillis-Steele inclusive scan
+        int v = (tid >= o) ? part[tid - o] : 0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    int run = part[tid] - sum;
+    for (int i = b; i < e; i++) {
+        offs[i] = run;
+        run += flags[i];
+    }
+    if (tid == 1023) *total_out = part[1023];
+}
+
+__global__ void emit_exc_kernel(const int *__restrict__ flags, const int *__restrict__ offs, int n, int v,
+                                int order, int32_t *__restrict__ exc) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= n * v || !flags[pos]) return;
+    int f, t;
+    pos_to_ft(pos, n, v, order, f, t);
+    exc[2 * offs[pos]] = f;
+    exc[2 * offs[pos] + 1] = t;
+}
+
+// coeff is n_states x K row-major.  grid.y = state.
+__global__ void emit_coeff_kernel(const double *__restrict__ ci, const int *__restrict__ flags,
+                                  const int *__restrict__ offs, int n, int v, double thr, int strict,
+                                  int order, int minus_sign, int K, double *__restrict__ coeff) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y;
+    if (pos >= n * v || !flags[pos]) return;
+    int f, t;
+    pos_to_ft(pos, n, v, order, f, t);
+    const double c = ci[(size_t)s * n * v + (size_t)f * v + t];
+    double val = ci_keep(c, thr, strict) ? c : 0.0;
+    if (minus_sign && (n & 1) && ((n - f + 1) & 1)) val = -val;   // ((-1)^(n-f+1))^n
+    coeff[(size_t)s * K + offs[pos]] = val;
+}
+
+}  // namespace wfo

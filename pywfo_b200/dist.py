@@ -43,6 +43,22 @@ def init_from_env(backend: str | None = None):
     return world()
 
 
+def sum_over_ranks(part, device=None):
+    """The one collective of the path: all-reduce(sum) of the per-rank partial matrices."""
+    rank, ws = world()
+    if ws == 1:
+        return part
+    import torch
+    import torch.distributed as dist
+
+    was_numpy = isinstance(part, np.ndarray)
+    t = torch.from_numpy(np.ascontiguousarray(part)) if was_numpy else part
+    if dist.get_backend() == "nccl" and not t.is_cuda:
+        t = t.cuda(device if device is not None else torch.cuda.current_device())
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy() if was_numpy else t
+
+
 def sharded_state_overlaps(partial_fn, K_bra: int, n_bra: int, n_ket: int, device=None):
     """Run ``partial_fn(k_begin, k_end) -> (n_bra, n_ket)`` on this rank's slice of the
     bra excitations and sum the partial matrices over all ranks.
@@ -52,20 +68,8 @@ def sharded_state_overlaps(partial_fn, K_bra: int, n_bra: int, n_ket: int, devic
     The product passes a closure over the CUDA entry point; the CPU tests pass
     the oracle so that the sharding logic is exercised without a GPU.
     """
-    import torch
-    import torch.distributed as dist
-
     rank, ws = world()
     lo, hi = shard_bounds(K_bra, ws, rank)
     part = partial_fn(lo, hi)
-    if ws == 1:
-        return part
-    was_numpy = isinstance(part, np.ndarray)
-    t = torch.from_numpy(np.ascontiguousarray(part)) if was_numpy else part
-    if dist.get_backend() == "nccl" and not t.is_cuda:
-        t = t.cuda(device if device is not None else torch.cuda.current_device())
-    assert tuple(t.shape) == (n_bra, n_ket)
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    if was_numpy:
-        return t.cpu().numpy()
-    return t
+    assert tuple(part.shape) == (n_bra, n_ket)
+    return sum_over_ranks(part, device)

@@ -74,26 +74,31 @@ def _state_overlaps(semantics, sigma, bra_mos, ket_mos, bra_ci, ket_ci, occ, ci_
     if bra_ci.shape[1] != occ or ket_ci.shape[1] != occ:
         raise ValueError("CI coefficients do not match occ")
     ctx = _lib.context(device)
+    n_bra, n_ket = bra_ci.shape[0], ket_ci.shape[0]
+    if isinstance(ao_ovlps, str):
+        # host: the one LAPACK call upstream makes here (main.py:303); device: everything else,
+        # including the selection of excitations above the threshold
+        c_inv = np.linalg.inv({"bra": bra_mos, "ket": ket_mos}[ao_ovlps])
+        rank, world = dist.world()
+        part, _ = ctx.overlaps_ci_host(bra_mos, ket_mos, c_inv, occ, bra_ci, ket_ci, ci_thresh,
+                                       semantics=0 if semantics == "cache" else 1, tier=tier,
+                                       rank=rank, world=world)
+        return dist.sum_over_ranks(part, device=ctx.device)
+    if not isinstance(ao_ovlps, np.ndarray):
+        raise Exception("Invalid AO overlaps!")
+    # explicit AO overlap matrix (documented upstream, main.py:305): tables built on the host
+    if semantics == "minus":
+        check_minus_inputs(bra_ci, ket_ci, ci_thresh)
     bra_t = build_tables(bra_ci, ci_thresh, semantics)
     ket_t = build_tables(ket_ci, ci_thresh, semantics, order="locality")
-    n_bra, n_ket = bra_ci.shape[0], ket_ci.shape[0]
     if bra_t.K == 0 or ket_t.K == 0:
         return np.zeros((n_bra, n_ket))
+    s_mo = ctx.smo_host(bra_mos, ao_ovlps, ket_mos)
 
-    if isinstance(ao_ovlps, str):
-        c_inv = np.linalg.inv({"bra": bra_mos, "ket": ket_mos}[ao_ovlps])   # main.py:303
+    def partial(lo, hi):
+        return ctx.state_overlaps_host(s_mo, occ, bra_t.exc, bra_t.coeff, ket_t.exc, ket_t.coeff,
+                                       sigma=sigma, tier=tier, k_begin=lo, k_end=hi)
 
-        def partial(lo, hi):
-            return ctx.overlaps_host(bra_mos, ket_mos, c_inv, occ, bra_t.exc, bra_t.coeff, ket_t.exc,
-                                     ket_t.coeff, sigma=sigma, tier=tier, k_begin=lo, k_end=hi)
-    elif isinstance(ao_ovlps, np.ndarray):
-        s_mo = ctx.smo_host(bra_mos, ao_ovlps, ket_mos)
-
-        def partial(lo, hi):
-            return ctx.state_overlaps_host(s_mo, occ, bra_t.exc, bra_t.coeff, ket_t.exc, ket_t.coeff,
-                                           sigma=sigma, tier=tier, k_begin=lo, k_end=hi)
-    else:
-        raise Exception("Invalid AO overlaps!")
     return dist.sharded_state_overlaps(partial, bra_t.K, n_bra, n_ket, device=ctx.device)
 
 
@@ -123,5 +128,4 @@ def overlaps(bra_mos, ket_mos, bra_ci, ket_ci, occ, ci_thresh=1e-4, ao_ovlps="ke
     assert bra_ci.shape == ket_ci.shape
     if not isinstance(ao_ovlps, (str, np.ndarray)):
         raise Exception("Invalid AO overlaps!")
-    check_minus_inputs(bra_ci, ket_ci, ci_thresh)
     return _state_overlaps("minus", -1.0, bra_mos, ket_mos, bra_ci, ket_ci, occ, ci_thresh, ao_ovlps, **kw)

@@ -210,6 +210,23 @@ def test_shards_add_up_on_gpu(ctx):
         np.testing.assert_allclose(parts, full, rtol=1e-12, atol=1e-14 * np.abs(full).max())
 
 
+def test_raw_ci_entry_point_shards_add_up(ctx):
+    """wfo_overlaps_ci_host: excitation selection on the device, rank/world sharding."""
+    g = load_golden("r_n17")
+    occ = int(g["occ"])
+    inv = np.linalg.inv(g["ket_mos"])
+    for sem, key in ((0, "ref_overlaps_cache"), (1, "ref_overlaps")):
+        nmin = min(g["bra_ci"].shape[0], g["ket_ci"].shape[0]) if sem else None
+        bci, kci = g["bra_ci"][:nmin], g["ket_ci"][:nmin]
+        full, info = ctx.overlaps_ci_host(g["bra_mos"], g["ket_mos"], inv, occ, bci, kci, float(g["ci_thresh"]), sem)
+        assert_parity(full, g[key])
+        from pywfo_b200 import excitations as ex
+        assert info[0] == ex.build_tables(bci, float(g["ci_thresh"]), "minus" if sem else "cache").K
+        parts = sum(ctx.overlaps_ci_host(g["bra_mos"], g["ket_mos"], inv, occ, bci, kci, float(g["ci_thresh"]), sem,
+                                         rank=r, world=3)[0] for r in range(3))
+        np.testing.assert_allclose(parts, full, rtol=1e-12, atol=1e-14 * np.abs(full).max())
+
+
 def test_singular_base_block_falls_back_to_lu(ctx):
     """S_oo singular: the rank-update tier is not applicable, AUTO must use the brute force LU."""
     rng = np.random.default_rng(8)
