@@ -196,7 +196,7 @@ struct Part {   // how the pair space of one call is cut up
     bool may_t0, want_t1;
 };
 
-static size_t base_smem_bytes(int n) { return (size_t)n * (n | 1) * 8 + (size_t)n * 8 + (size_t)n * 4; }
+static size_t base_smem_bytes(int n) { return n <= LUB_MAXN ? 0 : (size_t)1 << 40; }   // register resident, n <= 128
 
 // which tiers can / should run for this call
 static int resolve_tier(const wfo_ctx *ctx, int n, int tier, bool *want_t1, bool *may_t0) {
@@ -209,7 +209,7 @@ static int resolve_tier(const wfo_ctx *ctx, int n, int tier, bool *want_t1, bool
     if (tier == WFO_TIER_LU && !t0_fits)
         return set_err(WFO_ERR_ARG, "state_overlaps: tier LU supports n_occ <= 128, got %lld%s", "", n);
     if (tier == WFO_TIER_UPDATE && !t1_fits)
-        return set_err(WFO_ERR_ARG, "state_overlaps: tier UPDATE supports n_occ <= 160, got %lld%s", "", n);
+        return set_err(WFO_ERR_ARG, "state_overlaps: tier UPDATE supports n_occ <= 128, got %lld%s", "", n);
     if (tier == WFO_TIER_AUTO) {
         if (!t1_fits) *want_t1 = false;
         if (!t0_fits) *may_t0 = false;
@@ -455,9 +455,7 @@ static int state_overlaps_impl(wfo_ctx *ctx, size_t arena_off, const double *s_m
 
     if (want_t1) {
         // ---- one base factorisation, then the three block products
-        size_t smem = base_smem_bytes(n);
-        WFO_CUDA(cudaFuncSetAttribute(base_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        base_inverse_kernel<<<1, LUB_THREADS, smem, st>>>(s_mo, n_mo, n, p.Ai, p.info);
+        base_inverse_kernel<<<1, LUB_THREADS, 0, st>>>(s_mo, n_mo, n, p.Ai, p.info);
         WFO_LAUNCH_CHECK(ctx);
         // the conditioning of the base block decides whether the rank-update tier is usable:
         // one 32-byte read-back (the only host synchronisation of the call)

@@ -1,11 +1,15 @@
-// Base-block factorisation for the rank-update tiers: in-place Gauss-Jordan
-// inverse with partial (row) pivoting of A = S_MO[:n,:n] (n x n, n <= 160) in
-// one CTA, shared-memory resident.  Produces Ai = A^-1, det(A) and a
-// conditioning indicator (min |pivot| / max |pivot|).
+// Base-block factorisation for the rank-update tiers: Gauss-Jordan inverse with
+// partial (row) pivoting of A = S_MO[:n,:n] (n <= 128) in ONE CTA of 512 threads,
+// REGISTER resident: warp w owns rows {w, w+16, ..., w+112}, lane l owns columns
+// {l, l+32, l+64, l+96} -> 32 matrix elements per thread.  Per elimination step only
+// the pivot row and the multiplier column travel through shared memory (2 block
+// barriers per step); pivoting is implicit (rows never move), the row/column
+// permutation is undone when the inverse is written out.
+// Produces Ai = A^-1, det(A) and min/max |pivot| as a conditioning indicator.
 //
-// This is the "one base LU" that north_star's rank-1 (Sherman-Morrison /
-// cofactor) updates reuse; in the reference the same numbers would come from
-// np.linalg.det / np.linalg.inv of S_MO[:occ,:occ] (pywfo/main.py:548).
+// This is the "one base LU" that north_star's rank-1 (Sherman-Morrison / cofactor)
+// updates reuse; upstream the same numbers would come from np.linalg.det /
+// np.linalg.inv of S_MO[:occ,:occ] (pywfo/main.py:548).
 #pragma once
 #include "common.cuh"
 
@@ -19,99 +23,128 @@ struct BaseInfo {     // device-resident result block
     int pad;
 };
 
-constexpr int LUB_THREADS = 256;
+constexpr int LUB_MAXN = 128;
+constexpr int LUB_THREADS = 512;
+constexpr int LUB_WARPS = LUB_THREADS / 32;   // 16
+constexpr int LUB_RS = LUB_MAXN / LUB_WARPS;     // 8 row slots per thread
 
 // A_src: n x n block with leading dimension ld_src.  Ai_out: n x n, ld = n.
 __global__ void __launch_bounds__(LUB_THREADS)
 base_inverse_kernel(const double *__restrict__ A_src, int ld_src, int n, double *__restrict__ Ai_out,
                     BaseInfo *__restrict__ info) {
-    extern __shared__ double sm[];
-    const int ld = n | 1;                  // odd stride: conflict-free column walks
-    double *a = sm;                        // n x ld
-    double *colj = a + (size_t)n * ld;     // n   (unused spare column)
-    int *piv = (int *)(colj + n);          // n
-    __shared__ int red_i[LUB_THREADS / 32];
-
+    // double buffered by step parity: a step's writes never race the previous step's reads
+    __shared__ unsigned keys[2][32];   // LUB_WARPS used, rest stays 0
+    __shared__ double prow[2][LUB_MAXN];   // scaled pivot row
+    __shared__ double mcol[2][LUB_MAXN];   // multiplier column
+    __shared__ int piv_of_col[LUB_MAXN];   // p_j: pivot row chosen for column j
+    __shared__ int col_of_piv[LUB_MAXN];   // inverse map
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int idx = tid; idx < n * n; idx += LUB_THREADS) {
-        int r = idx / n, c = idx % n;
-        a[r * ld + c] = A_src[(size_t)r * ld_src + c];
+
+    double a[LUB_RS][4];
+    bool done[LUB_RS];
+    if (tid < 64) keys[tid >> 5][tid & 31] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < LUB_RS; s++) {
+        const int r = warp + LUB_WARPS * s;
+        done[s] = !(r < n);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int c = lane + 32 * k;
+            a[s][k] = (r < n && c < n) ? A_src[(size_t)r * ld_src + c] : 0.0;
+        }
     }
     double det = 1.0, minp = 1e300, maxp = 0.0;
     int singular = 0;
-    __syncthreads();
 
-    const int nwarps = LUB_THREADS / 32;
-    for (int j = 0; j < n; j++) {
-        // ---- pivot search over rows j..n-1 of column j: REDUX over (|a| high word | row)
-        unsigned key = 0;
-        for (int r = j + tid; r < n; r += LUB_THREADS)
-            key = max(key, (hi_abs(a[r * ld + j]) & 0xffffff00u) | (unsigned)r);   // n <= 160 < 256
-        key = __reduce_max_sync(0xffffffffu, key);
-        if (lane == 0) red_i[warp] = (int)key;
-        __syncthreads();
-        unsigned kmax = 0;
 #pragma unroll
-        for (int w = 0; w < nwarps; w++) kmax = max(kmax, (unsigned)red_i[w]);
-        const int p = (int)(kmax & 0xffu);
-        if (tid == 0) piv[j] = p;
-        const double d = a[p * ld + j];          // pivot value (before the swap)
-        const double ad = fabs(d);
-        if (!(ad > 0.0) || !isfinite(d)) { singular = 1; break; }   // uniform
-        det *= (p != j) ? -d : d;
-        minp = fmin(minp, ad);
-        maxp = fmax(maxp, ad);
-        const double rd = 1.0 / d;
-        // ---- lanes own columns (4 per lane), warps walk rows.  Row swap folded in:
-        //      new row j = old row p scaled, new row p = old row j eliminated.
-        double pr[5], oj[5];
+    for (int cj = 0; cj < 4; cj++) {          // column slot (static register index)
+        for (int lj = 0; lj < 32; lj++) {     // owning lane
+            const int j = lj + 32 * cj;
+            if (j >= n || singular) break;    // uniform
+            const int b = j & 1;
+            // ---- pivot search: per-warp candidate from lane lj, combined through shared memory
+            if (lane == lj) {
+                unsigned key = 0;
 #pragma unroll
-        for (int k = 0; k < 5; k++) {
-            const int c = lane + 32 * k;
-            pr[k] = (c < n) ? ((c == j) ? 1.0 : a[p * ld + c]) * rd : 0.0;   // scaled pivot row
-            oj[k] = (c < n) ? a[j * ld + c] : 0.0;                            // old row j
-        }
-        const double fj = a[j * ld + j];           // old a[j][j]: multiplier of the displaced row
-        __syncthreads();                          // everyone has read rows j and p
-        for (int r = warp; r < n; r += nwarps) {
-            if (r == j) {
+                for (int s = 0; s < LUB_RS; s++) {
+                    const unsigned k = (hi_abs(a[s][cj]) & 0xffffff00u) | 0x80u | (unsigned)(warp + LUB_WARPS * s);
+                    if (!done[s]) key = max(key, k);
+                }
+                keys[b][warp] = key;
 #pragma unroll
-                for (int k = 0; k < 5; k++) { const int c = lane + 32 * k; if (c < n) a[j * ld + c] = pr[k]; }
-            } else {
-                const bool is_p = (r == p);
-                const double f = is_p ? fj : a[r * ld + j];
+                for (int s = 0; s < LUB_RS; s++) mcol[b][warp + LUB_WARPS * s] = a[s][cj];
+            }
+            __syncthreads();
+            unsigned kmax = keys[b][lane];
+            kmax = __reduce_max_sync(0xffffffffu, kmax);
+            const int p = (int)(kmax & 0x7fu);          // pivot row
+            const int wp = p % LUB_WARPS, sp = p / LUB_WARPS;
+            const double d = mcol[b][p];
+            const double ad = fabs(d);
+            if (kmax == 0 || !(ad > 0.0) || !isfinite(d)) { singular = 1; break; }   // uniform
+            det *= d;
+            minp = fmin(minp, ad);
+            maxp = fmax(maxp, ad);
+            const double rd = 1.0 / d;
+            if (warp == wp) {                           // publish the scaled pivot row
 #pragma unroll
-                for (int k = 0; k < 5; k++) {
-                    const int c = lane + 32 * k;
-                    if (c < n) {
-                        const double base = (c == j) ? 0.0 : (is_p ? oj[k] : a[r * ld + c]);
-                        a[r * ld + c] = fma(-f, pr[k], base);
+                for (int s = 0; s < LUB_RS; s++) {
+                    if (s == sp) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const int c = lane + 32 * k;
+                            if (c < n) prow[b][c] = ((c == j) ? 1.0 : a[s][k]) * rd;
+                        }
+                        done[s] = true;
+                    }
+                }
+                if (lane == 0) { piv_of_col[j] = p; col_of_piv[p] = j; }
+            }
+            __syncthreads();
+            double pr[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) pr[k] = (lane + 32 * k < n) ? prow[b][lane + 32 * k] : 0.0;
+#pragma unroll
+            for (int s = 0; s < LUB_RS; s++) {
+                const int r = warp + LUB_WARPS * s;
+                if (r == p) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) a[s][k] = pr[k];
+                } else if (r < n) {
+                    const double f = mcol[b][r];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const double base = (lane + 32 * k == j) ? 0.0 : a[s][k];
+                        a[s][k] = fma(-f, pr[k], base);
                     }
                 }
             }
         }
-        __syncthreads();
     }
+    // ---- write out: stored[r][j'] = M[r][p_j'],  Ai[j][c] = M[p_j][c]  =>  Ai[col_of_piv[r]][piv_of_col[j']] = stored[r][j']
     if (!singular) {
-        // undo the row interchanges as column interchanges, last first
-        for (int j = n - 1; j >= 0; j--) {
-            int p = piv[j];
-            if (p != j) {
-                for (int r = tid; r < n; r += LUB_THREADS) {
-                    double x = a[r * ld + j];
-                    a[r * ld + j] = a[r * ld + p];
-                    a[r * ld + p] = x;
+#pragma unroll
+        for (int s = 0; s < LUB_RS; s++) {
+            const int r = warp + LUB_WARPS * s;
+            if (r < n) {
+                const int orow = col_of_piv[r];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int c = lane + 32 * k;
+                    if (c < n) Ai_out[(size_t)orow * n + piv_of_col[c]] = a[s][k];
                 }
-                __syncthreads();
             }
         }
-        for (int idx = tid; idx < n * n; idx += LUB_THREADS) {
-            int r = idx / n, c = idx % n;
-            Ai_out[(size_t)r * n + c] = a[r * ld + c];
-        }
     }
+    // sign of the permutation j -> piv_of_col[j]: parallel inversion count
+    __syncthreads();
+    int inv = 0;
+    if (!singular && tid < n)
+        for (int k = tid + 1; k < n; k++) inv += piv_of_col[k] < piv_of_col[tid];
+    const int par = __syncthreads_count(inv & 1) & 1;
     if (tid == 0) {
-        info->det = singular ? 0.0 : det;
+        info->det = singular ? 0.0 : (par ? -det : det);
         info->min_piv = minp;
         info->max_piv = maxp;
         info->singular = singular;
