@@ -13,7 +13,7 @@ import threading
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libwfo_b200.so")
+LIB_PATH = os.environ.get("WFO_B200_LIB") or os.path.join(HERE, "libwfo_b200.so")   # env: tuning builds only
 
 TIER_AUTO, TIER_LU, TIER_UPDATE, TIER_CLOSED = -1, 0, 1, 2
 TIERS = {"auto": TIER_AUTO, "lu": TIER_LU, "update": TIER_UPDATE, "closed": TIER_CLOSED,

@@ -36,6 +36,18 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps())
 
 
+def build_variant(out_name: str, defines=()) -> str:
+    """Scratch builds for kernel tuning (selected at run time with WFO_B200_LIB)."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    out = os.path.join(HERE, out_name)
+    cmd = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + sources() + ["-o", out]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB

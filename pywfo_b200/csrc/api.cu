@@ -91,14 +91,45 @@ static bool use_v1() {
     return v == 1;
 }
 
-// blocked-kernel configuration by matrix size: (warps, rows per lane of the panel warp)
-#define WFO_BLK_DISPATCH(n, CALL)                      \
-    do {                                               \
-        if ((n) <= 32) { CALL(2, 1); }                 \
-        else if ((n) <= 64) { CALL(4, 2); }            \
-        else if ((n) <= 96) { CALL(8, 3); }            \
-        else { CALL(8, 4); }                           \
+// blocked-kernel configuration by matrix size: (warps per CTA, panel warps = ceil(n/32)).
+// WFO_T0_WARPS overrides the warp count (tuning only).
+static int t0_warps_override() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("WFO_T0_WARPS"); v = e ? atoi(e) : 0; }
+    return v;
+}
+#define WFO_BLK_DISPATCH(n, CALL)                                                   \
+    do {                                                                            \
+        const int ov_ = t0_warps_override();                                        \
+        if ((n) <= 32) {                                                            \
+            if (ov_ == 1) { CALL(1, 1); } else if (ov_ == 4) { CALL(4, 1); } else { CALL(2, 1); }      \
+        } else if ((n) <= 64) {                                                     \
+            if (ov_ == 2) { CALL(2, 2); } else if (ov_ == 8) { CALL(8, 2); } else { CALL(4, 2); }      \
+        } else if ((n) <= 96) {                                                     \
+            if (ov_ == 4) { CALL(4, 3); } else { CALL(8, 3); }                      \
+        } else {                                                                    \
+            if (ov_ == 4) { CALL(4, 4); } else { CALL(8, 4); }                      \
+        }                                                                           \
     } while (0)
+
+// keep the LU working matrices in global memory (L2) instead of shared memory?
+static bool t0_global_scratch(int n) {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("WFO_T0_GLOBAL"); v = e ? atoi(e) : 0; }
+    (void)n;
+    return v == 1;
+}
+
+static int ensure_gscratch(wfo_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->gscratch_bytes) return WFO_OK;
+    WFO_CUDA(cudaDeviceSynchronize());
+    if (ctx->gscratch) WFO_CUDA(cudaFree(ctx->gscratch));
+    ctx->gscratch = nullptr;
+    ctx->gscratch_bytes = 0;
+    WFO_CUDA(cudaMalloc(&ctx->gscratch, bytes));
+    ctx->gscratch_bytes = bytes;
+    return WFO_OK;
+}
 
 template <typename K>
 static int persistent_grid(wfo_ctx *ctx, K kernel, int threads, size_t smem, long long items, unsigned *grid) {
@@ -125,10 +156,19 @@ static int det_table(wfo_ctx *ctx, const double *S, int ld_s, int n, const int32
         WFO_TRY(persistent_grid(ctx, det_table_kernel, threads, smem, npairs, &grid));
         det_table_kernel<<<grid, threads, smem, st>>>(S, ld_s, n, rows, kb, cols, kk, D);
     } else {
-        size_t smem = blk_smem_bytes(n);
-#define CALL_DT(W, SL)                                                                                   \
-    WFO_TRY(persistent_grid(ctx, det_table_blk_kernel<W, SL>, W * 32, smem, npairs, &grid));             \
-    det_table_blk_kernel<W, SL><<<grid, W * 32, smem, st>>>(S, ld_s, n, rows, kb, cols, kk, D)
+        const bool gl = t0_global_scratch(n);
+        size_t smem = blk_smem_bytes(n, gl);
+#define CALL_DT(W, SL)                                                                                       \
+    if (gl) {                                                                                                \
+        WFO_TRY(persistent_grid(ctx, det_table_blk_kernel<W, SL, true>, W * 32, smem, npairs, &grid));       \
+        WFO_TRY(ensure_gscratch(ctx, (size_t)grid * blk_mat_bytes(n)));                                      \
+        det_table_blk_kernel<W, SL, true><<<grid, W * 32, smem, st>>>(S, ld_s, n, rows, kb, cols, kk, D,     \
+                                                                      ctx->gscratch);                        \
+    } else {                                                                                                 \
+        WFO_TRY(persistent_grid(ctx, det_table_blk_kernel<W, SL, false>, W * 32, smem, npairs, &grid));      \
+        det_table_blk_kernel<W, SL, false><<<grid, W * 32, smem, st>>>(S, ld_s, n, rows, kb, cols, kk, D,    \
+                                                                       nullptr);                             \
+    }
         WFO_BLK_DISPATCH(n, CALL_DT);
 #undef CALL_DT
     }
@@ -297,6 +337,7 @@ int wfo_destroy(wfo_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->gscratch) cudaFree(ctx->gscratch);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -525,12 +566,21 @@ static int state_overlaps_impl(wfo_ctx *ctx, size_t arena_off, const double *s_m
             t0_fused_kernel<<<grid, threads, smem, st>>>(s_mo, n_mo, n, p.bra_lists, ksh, p.ket_lists, kk, p.ckt,
                                                          ldg, chunk_len, t0_chunks, p.gpart);
         } else {
-            size_t smem = blk_smem_bytes(n);
-#define CALL_FU(W, SL)                                                                                        \
-    WFO_TRY(persistent_grid(ctx, t0_fused_blk_kernel<W, SL>, W * 32, smem, items, &grid));                    \
-    if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev0, st));                                                 \
-    t0_fused_blk_kernel<W, SL><<<grid, W * 32, smem, st>>>(s_mo, n_mo, n, p.bra_lists, ksh, p.ket_lists, kk, \
-                                                           p.ckt, ldg, chunk_len, t0_chunks, p.gpart)
+            const bool gl = t0_global_scratch(n);
+            size_t smem = blk_smem_bytes(n, gl);
+#define CALL_FU(W, SL)                                                                                          \
+    if (gl) {                                                                                                   \
+        WFO_TRY(persistent_grid(ctx, t0_fused_blk_kernel<W, SL, true>, W * 32, smem, items, &grid));            \
+        WFO_TRY(ensure_gscratch(ctx, (size_t)grid * blk_mat_bytes(n)));                                         \
+        if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev0, st));                                               \
+        t0_fused_blk_kernel<W, SL, true><<<grid, W * 32, smem, st>>>(s_mo, n_mo, n, p.bra_lists, ksh,           \
+            p.ket_lists, kk, p.ckt, ldg, chunk_len, t0_chunks, p.gpart, ctx->gscratch);                         \
+    } else {                                                                                                    \
+        WFO_TRY(persistent_grid(ctx, t0_fused_blk_kernel<W, SL, false>, W * 32, smem, items, &grid));           \
+        if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev0, st));                                               \
+        t0_fused_blk_kernel<W, SL, false><<<grid, W * 32, smem, st>>>(s_mo, n_mo, n, p.bra_lists, ksh,          \
+            p.ket_lists, kk, p.ckt, ldg, chunk_len, t0_chunks, p.gpart, nullptr);                               \
+    }
             WFO_BLK_DISPATCH(n, CALL_FU);
 #undef CALL_FU
         }
@@ -781,6 +831,14 @@ int wfo_overlaps_ci_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_
     WFO_CUDA(cudaStreamSynchronize(st));
     return WFO_OK;
 }
+
+#ifdef WFO_PHASE_TIMING
+int wfo_debug_phases(long long *out16, int reset) {
+    if (out16) cudaMemcpyFromSymbol(out16, g_phase, sizeof(long long) * 16);
+    if (reset) { long long z[16] = {0}; cudaMemcpyToSymbol(g_phase, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 /* ------------------------------------------------------------ measurement */
 int wfo_fp64_peak(wfo_ctx *ctx, int kind, int iters, double *tflops) {

@@ -48,6 +48,18 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                  : "d"(a), "d"(b));
 }
 
+// 1/x without the library's special-case slow path: MUFU.RCP64H seed (~20 bits) and two Newton
+// steps (4 dependent DFMA).  x = 0 / subnormal gives inf/NaN, which callers treat as singular.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
 __device__ __forceinline__ unsigned hi_abs(double x) {
     return (unsigned)__double2hiint(x) & 0x7fffffffu;
 }
@@ -61,8 +73,8 @@ struct wfo_ctx {
     cudaStream_t stream;   // private stream of the *_host entry points
     char *scratch;         // device arena, grown on demand
     size_t scratch_bytes;
-    char *hscratch;        // pinned host staging for the *_host entry points
-    size_t hscratch_bytes;
+    double *gscratch;      // per-CTA LU working matrices (global-scratch variant of the T0 kernel)
+    size_t gscratch_bytes;
     long long launches;
     int last_tier;
     int timing;

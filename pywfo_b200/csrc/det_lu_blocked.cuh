@@ -1,174 +1,183 @@
-// T0 (brute force), blocked kernel for 16 < n <= 128: one CTA per determinant pair.
+// T0 (brute force), blocked kernel for n <= 128: one CTA per determinant pair.
 //
-// The gathered n x n minor of S_MO lives in shared memory (row-major, padded
-// stride).  Right-looking LU with partial pivoting in 16-column panels, each
-// factored as two 8-column sub-panels:
-//   * sub-panel factorisation by ONE warp, register resident (lane = row,
-//     up to 4 rows per lane, 8 columns each): the pivot search is a single
-//     REDUX.MAX over a key that packs the high word of |a| with (slot, lane),
-//     the pivot row is broadcast with warp shuffles, no block barrier inside;
-//   * rows are physically compacted after every sub-panel (pivot rows to the
-//     top, displaced rows into the vacated positions), an original-row-id
-//     column travels with the data and gives the permutation sign at the end;
-//   * triangular solve for the U block row: one thread per trailing column;
-//   * trailing update A22 -= L21 U12 on the FP64 tensor cores (DMMA.8x8x4),
-//     rank 16, operands read from shared memory as fragments, each warp
-//     working on 16x32 macro tiles (8 accumulators tiles in registers).
-// The determinant is the signed product of the pivots -- the quantity
-// np.linalg.det returns for S_MO[rows][:, cols] (pywfo/main.py:583-584).
+// The gathered n x n minor of S_MO lives in shared memory (row-major, padded stride).
+// Right-looking LU with partial pivoting in 16-column panels:
+//   * panel factorisation by the first ceil(n/32) warps, register resident (one row per
+//     lane, 16 columns per lane): per column ONE REDUX.MAX over a key that packs the high
+//     word of |a| with (warp, lane); each warp's candidate publishes its row, one named
+//     barrier, every lane reads the winning row; branch-free elimination; the reciprocal
+//     of the pivot is computed speculatively by every lane for its own candidate while
+//     the search is in flight;
+//   * rows are physically compacted after every panel (pivot rows to the top, displaced
+//     rows into the vacated positions); an original-row-id column travels with the data
+//     and gives the permutation sign at the end;
+//   * triangular solve for the 16-row U block: one thread per trailing column;
+//   * trailing update A22 -= L21 U12 on the FP64 tensor cores (DMMA.8x8x4), rank 16,
+//     operands read from shared memory as fragments, 16x32 macro tiles per warp.
+// The determinant is the signed product of the pivots -- the quantity np.linalg.det
+// returns for S_MO[rows][:, cols] (pywfo/main.py:583-584).
 #pragma once
 #include "common.cuh"
 
 namespace wfo {
 
+#ifdef WFO_PHASE_TIMING
+// scratch-build instrumentation: cycles per phase, accumulated by thread 0 of block 0
+__device__ long long g_phase[16];
+#define PH_DECL long long ph_t = clock64();
+#define PH_MARK(i)                                                        \
+    do {                                                                  \
+        if (threadIdx.x == 0 && blockIdx.x == 0) {                        \
+            long long now_ = clock64();                                   \
+            g_phase[i] += now_ - ph_t;                                    \
+            ph_t = now_;                                                  \
+        }                                                                 \
+    } while (0)
+#else
+#define PH_DECL
+#define PH_MARK(i)
+#endif
+
 struct BlkShared {
-    double det;          // product of pivots (written by warp 0)
-    int singular;
-    int aff_dst[16];     // row positions that receive another row (-1: unused)
-    int aff_src[16];     // ... and the position the row comes from
-    int vac[8];          // scratch: vacated positions
-    double red[8];
+    double det;                  // product of pivots (written by thread 0)
+    int singular;                // an exactly zero pivot was met
+    unsigned key[2][4];          // per-warp pivot candidates, double buffered by column parity
+    double cand[2][4][18];       // per-warp candidate rows (+ reciprocal of the candidate at [16])
+    int piv_row[16];             // row chosen as pivot of step jj of the current panel
+    int aff_dst[32];             // row positions that receive another row (-1: unused)
+    int aff_src[32];             // ... and the position the row comes from
 };
 
-__device__ __forceinline__ int blk_ld(int n) {   // leading dimension, == 8 (mod 16), >= n rounded to 8
-    int ld = (n + 7) & ~7;
-    if ((ld & 15) == 0) ld += 8;
-    return ld;
+__device__ __forceinline__ void panel_bar(int nthreads) {   // named barrier 1: the panel warps only
+    asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
 }
 
 // ---------------------------------------------------------------------------------
-// sub-panel factorisation: rows [j0, n), columns [j0, j0+w), w <= 8.  Warp 0 only.
-// On exit the panel columns are written back at the rows' FINAL positions, the
-// affected-row list is published in sh, det is multiplied by the w pivots.
-template <int SLOTS>
-__device__ __forceinline__ void factor_subpanel(double *A, int *rowid, int LD, int n, int j0, int w,
-                                                BlkShared *sh, int lane, double &det, bool &singular) {
+// panel factorisation: rows [j0, n), columns [j0, j0+16) of which w are inside the matrix,
+// by the first PW warps of the CTA (warp p owns rows j0+32p..j0+32p+31, one row per lane).
+// On exit the panel columns are written back at the rows' FINAL positions, the affected-row
+// list is published in sh, det is multiplied by the w pivots, zero is set on a zero pivot.
+template <int PW>
+__device__ __forceinline__ void factor_panel16(double *A, int LD, int n, int j0, int w, BlkShared *sh, int warp,
+                                               int lane, double &det, bool &zero) {
     const unsigned FULL = 0xffffffffu;
-    double a[SLOTS][8];
-    bool done[SLOTS];
-    int pstep[SLOTS];
+    constexpr int NT = PW * 32;
+    const int r = j0 + 32 * warp + lane;
+    const bool valid = r < n;
+    double a[16];
+    {
+        const double2 *src = reinterpret_cast<const double2 *>(A + (size_t)(valid ? r : j0) * LD + j0);
 #pragma unroll
-    for (int s = 0; s < SLOTS; s++) {
-        const int r = j0 + lane + 32 * s;
-        done[s] = !(r < n);
-        pstep[s] = -1;
-        if (r < n) {
-            const double2 *src = reinterpret_cast<const double2 *>(A + (size_t)r * LD + j0);
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                double2 v = src[c];
-                a[s][2 * c] = v.x;
-                a[s][2 * c + 1] = v.y;
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < 8; c++) a[s][c] = 0.0;
+        for (int c = 0; c < 8; c++) {
+            const double2 v = src[c];
+            a[2 * c] = v.x;
+            a[2 * c + 1] = v.y;
         }
     }
-    int piv_pos[8];
+    bool done = !valid;
+    int pstep = -1;
+    const unsigned tag = 0x80u | (unsigned)(warp << 5) | (unsigned)lane;
 #pragma unroll
-    for (int jj = 0; jj < 8; jj++) {
-        piv_pos[jj] = j0 + jj;
-        if (jj < w && !singular) {
-            // ---- pivot search: one REDUX over (|a| high word, slot, lane)
-            unsigned key = 0;
+    for (int jj = 0; jj < 16; jj++) {
+        if (jj < w) {   // uniform
+            const int b = jj & 1;
+            const unsigned key = done ? 0u : ((hi_abs(a[jj]) & 0xffffff00u) | tag);
+            const unsigned kw = __reduce_max_sync(FULL, key);
+            const double rc_own = fast_rcp(done ? 1.0 : a[jj]);   // speculative, overlaps the search
+            unsigned kmax = kw;
+            double u[16], rcp;
+            if (PW > 1) {
+                if (key == kw && key != 0u) {            // this warp's candidate publishes its row
+                    sh->key[b][warp] = kw;
 #pragma unroll
-            for (int s = 0; s < SLOTS; s++) {
-                unsigned k = (hi_abs(a[s][jj]) & 0xffffff00u) | 0x80u | (unsigned)(s << 5) | (unsigned)lane;
-                if (!done[s]) key = max(key, k);
-            }
-            const unsigned kmax = __reduce_max_sync(FULL, key);
-            const int wl = kmax & 31, ws = (kmax >> 5) & 3;
-            // ---- broadcast the pivot row (ws is warp-uniform: no divergence)
-            double u[8];
-#pragma unroll
-            for (int s = 0; s < SLOTS; s++) {
-                if (ws == s) {
-#pragma unroll
-                    for (int c = jj; c < 8; c++) u[c] = __shfl_sync(FULL, a[s][c], wl);
+                    for (int c = jj; c < 16; c++) sh->cand[b][warp][c] = a[c];
+                    sh->cand[b][warp][16] = rc_own;
                 }
+                if (kw == 0u && lane == 0) sh->key[b][warp] = 0u;
+                panel_bar(NT);
+#pragma unroll
+                for (int q = 0; q < PW; q++) kmax = max(kmax, sh->key[b][q]);
+                const int ww = (kmax >> 5) & 3;
+#pragma unroll
+                for (int c = jj; c < 16; c++) u[c] = sh->cand[b][ww][c];
+                rcp = sh->cand[b][ww][16];
+            } else {
+                const int wl = kmax & 31;
+#pragma unroll
+                for (int c = jj; c < 16; c++) u[c] = __shfl_sync(FULL, a[c], wl);
+                rcp = __shfl_sync(FULL, rc_own, wl);
             }
             const double piv = u[jj];
-            if (piv == 0.0) {
-                singular = true;
-            } else {
-                det *= piv;
-                const double rcp = 1.0 / piv;
-                piv_pos[jj] = j0 + wl + 32 * ws;
+            det *= piv;
+            zero = zero || (piv == 0.0);
+            const bool win = (key == kmax) && (key != 0u);
+            if (win) sh->piv_row[jj] = r;
+            pstep = win ? jj : pstep;
+            done = done || win;
+            // branch-free elimination: finished rows use a zero multiplier
+            const double l = done ? 0.0 : a[jj] * rcp;
+            a[jj] = done ? a[jj] : l;
 #pragma unroll
-                for (int s = 0; s < SLOTS; s++) {
-                    if (lane == wl && ws == s) { done[s] = true; pstep[s] = jj; }
-                    if (!done[s]) {
-                        const double l = a[s][jj] * rcp;
-                        a[s][jj] = l;
+            for (int c = jj + 1; c < 16; c++) a[c] = fma(-l, u[c], a[c]);
+        }
+    }
+    if (PW > 1) panel_bar(NT); else __syncwarp();   // piv_row[] complete
+    // ---- final positions: pivot of step jj -> j0+jj; displaced rows (top w rows that are not
+    //      pivots, all in warp 0) -> the positions vacated by pivots from below, in step order
+    int newpos = (pstep >= 0) ? j0 + pstep : r;
+    if (warp == 0) {
+        const bool displaced = (lane < w) && pstep < 0 && valid;
+        const unsigned dbal = __ballot_sync(FULL, displaced);
+        const int drank = __popc(dbal & ((1u << lane) - 1));
+        if (displaced) {
+            int seen = 0;
 #pragma unroll
-                        for (int c = jj + 1; c < 8; c++) a[s][c] = fma(-l, u[c], a[s][c]);
-                    }
+            for (int q = 0; q < 16; q++) {
+                const int pr = sh->piv_row[q];
+                if (q < w && pr >= j0 + w) {
+                    if (seen == drank) newpos = pr;
+                    seen++;
                 }
             }
         }
-    }
-    if (singular) return;   // warp-uniform: nothing below is needed, det = 0
-    // ---- final positions: pivot row jj -> j0+jj; displaced rows -> vacated positions
-    int newpos[SLOTS];
-    unsigned vac_before = 0;
-#pragma unroll
-    for (int s = 0; s < SLOTS; s++) {
-        const int r = j0 + lane + 32 * s;
-        newpos[s] = (pstep[s] >= 0) ? j0 + pstep[s] : r;
-        const bool vacated = pstep[s] >= 0 && r >= j0 + w;
-        const unsigned bal = __ballot_sync(FULL, vacated);
-        if (vacated) sh->vac[vac_before + __popc(bal & ((1u << lane) - 1))] = r;
-        vac_before += __popc(bal);
-    }
-    const bool displaced = (lane < w) && pstep[0] < 0 && (j0 + lane < n);
-    const unsigned dbal = __ballot_sync(FULL, displaced);
-    const int drank = __popc(dbal & ((1u << lane) - 1));
-    __syncwarp();
-    if (displaced) newpos[0] = sh->vac[drank];
-    // ---- affected list: entries 0..7 pivots, 8..15 displaced
-    if (lane < 16) { sh->aff_dst[lane] = -1; sh->aff_src[lane] = -1; }
-    __syncwarp();
-#pragma unroll
-    for (int s = 0; s < SLOTS; s++) {
-        const int r = j0 + lane + 32 * s;
-        if (pstep[s] >= 0 && newpos[s] != r) { sh->aff_dst[pstep[s]] = newpos[s]; sh->aff_src[pstep[s]] = r; }
-    }
-    if (displaced) { sh->aff_dst[8 + drank] = newpos[0]; sh->aff_src[8 + drank] = j0 + lane; }
-    // ---- write the panel columns back at the final positions
-#pragma unroll
-    for (int s = 0; s < SLOTS; s++) {
-        const int r = j0 + lane + 32 * s;
-        if (r < n) {
-            double2 *dst = reinterpret_cast<double2 *>(A + (size_t)newpos[s] * LD + j0);
-#pragma unroll
-            for (int c = 0; c < 4; c++) dst[c] = make_double2(a[s][2 * c], a[s][2 * c + 1]);
+        // affected list: entries 0..15 pivots, 16..31 displaced rows
+        if (lane < 16) {
+            const int pr = (lane < w) ? sh->piv_row[lane] : -1;
+            const bool moved = (lane < w) && pr != j0 + lane;
+            sh->aff_dst[lane] = moved ? j0 + lane : -1;
+            sh->aff_src[lane] = moved ? pr : -1;
+            sh->aff_dst[16 + lane] = -1;
+            sh->aff_src[16 + lane] = -1;
         }
+        __syncwarp();
+        if (displaced) { sh->aff_dst[16 + drank] = newpos; sh->aff_src[16 + drank] = r; }
     }
-    (void)piv_pos;
-    (void)rowid;
+    if (valid) {
+        double2 *dst = reinterpret_cast<double2 *>(A + (size_t)newpos * LD + j0);
+#pragma unroll
+        for (int c = 0; c < 8; c++) dst[c] = make_double2(a[2 * c], a[2 * c + 1]);
+    }
 }
 
-// Apply the published row moves to the column ranges [c0a,c1a) and [c0b,c1b) and to rowid.
-// All threads; one warp per moved row, lanes over columns; one block barrier between the
-// reads and the writes.
-template <int WARPS>
-__device__ __forceinline__ void permute_rows(double *A, int *rowid, int LD, const BlkShared *sh, int c0a, int c1a,
-                                             int c0b, int c1b) {
-    constexpr int EPW = 16 / WARPS;          // entries per warp
+// Apply the published row moves to the columns [c0, c1) and to rowid.  All threads; one warp
+// per moved row, lanes over columns (CH chunks of 32); one block barrier between the reads
+// and the writes.
+template <int WARPS, int CH>
+__device__ __forceinline__ void permute_rows(double *A, int *rowid, int LD, const BlkShared *sh, int c0, int c1) {
+    constexpr int EPW = 32 / WARPS;          // entries per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int wa = c1a - c0a, wt = wa + (c1b - c0b);
-    double tmp[EPW][4];
+    const int wt = c1 - c0;
+    double tmp[EPW][CH];
     int rid[EPW];
 #pragma unroll
     for (int e = 0; e < EPW; e++) {
         const int src = sh->aff_src[warp * EPW + e];
         rid[e] = -1;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < CH; k++) {
             const int cc = lane + 32 * k;
             tmp[e][k] = 0.0;
-            if (src >= 0 && cc < wt) tmp[e][k] = A[(size_t)src * LD + (cc < wa ? c0a + cc : c0b + (cc - wa))];
+            if (src >= 0 && cc < wt) tmp[e][k] = A[(size_t)src * LD + c0 + cc];
         }
         if (src >= 0) rid[e] = rowid[src];
     }
@@ -178,41 +187,30 @@ __device__ __forceinline__ void permute_rows(double *A, int *rowid, int LD, cons
         const int dst = sh->aff_dst[warp * EPW + e];
         if (dst >= 0) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
+            for (int k = 0; k < CH; k++) {
                 const int cc = lane + 32 * k;
-                if (cc < wt) A[(size_t)dst * LD + (cc < wa ? c0a + cc : c0b + (cc - wa))] = tmp[e][k];
+                if (cc < wt) A[(size_t)dst * LD + c0 + cc] = tmp[e][k];
             }
             if (lane == 0) rowid[dst] = rid[e];
         }
     }
 }
 
-// U block row: rows [r0, r0+w) are pivot rows; for every trailing column solve with the
-// unit-lower block L[r0.., r0..]; if r0 > p0 first subtract L[r0.., p0..r0) * U[p0..r0) (rank-8
-// contribution of the first sub-panel of this panel).  One thread per column.
+// U block row: rows [r0, r0+16) are the pivot rows of the panel; for every trailing column
+// solve with the unit-lower block L[r0.., r0..].  One thread per column.
 template <int THREADS>
-__device__ __forceinline__ void trsm_block_row(double *A, int LD, int n, int p0, int r0, int w, int c_begin) {
-    for (int c = c_begin + threadIdx.x; c < n; c += THREADS) {
-        double x[8];
+__device__ __forceinline__ void trsm_block_row16(double *A, int LD, int n, int r0) {
+    for (int c = r0 + 16 + threadIdx.x; c < n; c += THREADS) {
+        double x[16];
 #pragma unroll
-        for (int i = 0; i < 8; i++) x[i] = (i < w) ? A[(size_t)(r0 + i) * LD + c] : 0.0;
-        for (int q = p0; q < r0; q++) {
-            const double uq = A[(size_t)q * LD + c];
+        for (int i = 0; i < 16; i++) x[i] = A[(size_t)(r0 + i) * LD + c];
 #pragma unroll
-            for (int i = 0; i < 8; i++)
-                if (i < w) x[i] = fma(-A[(size_t)(r0 + i) * LD + q], uq, x[i]);
+        for (int q = 0; q < 15; q++) {
+#pragma unroll
+            for (int i = q + 1; i < 16; i++) x[i] = fma(-A[(size_t)(r0 + i) * LD + r0 + q], x[q], x[i]);
         }
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
-            if (q < w) {
-#pragma unroll
-                for (int i = q + 1; i < 8; i++)
-                    if (i < w) x[i] = fma(-A[(size_t)(r0 + i) * LD + r0 + q], x[q], x[i]);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-            if (i < w) A[(size_t)(r0 + i) * LD + c] = x[i];
+        for (int i = 1; i < 16; i++) A[(size_t)(r0 + i) * LD + c] = x[i];
     }
 }
 
@@ -275,56 +273,40 @@ __device__ __forceinline__ void dmma_update(double *A, int LD, int n, int R0, in
 template <int WARPS, int SLOTS>
 __device__ __forceinline__ double cta_lu_det_blocked(double *A, int *rowid, int LD, int n, BlkShared *sh) {
     constexpr int THREADS = WARPS * 32;
+    constexpr int CH = SLOTS;   // column chunks of 32 that cover n
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < n; i += THREADS) rowid[i] = i;
-    if (tid == 0) sh->singular = 0;
     double det = 1.0;
-    bool singular = false;
+    bool zero = false;
     __syncthreads();
+    PH_DECL
     for (int j = 0; j < n; j += 16) {
-        const int w1 = min(8, n - j);
-        // ---- first sub-panel
-        if (warp == 0) {
-            factor_subpanel<SLOTS>(A, rowid, LD, n, j, w1, sh, lane, det, singular);
-            if (lane == 0 && singular) sh->singular = 1;
-        }
+        const int w = min(16, n - j);
+        if (warp < SLOTS) factor_panel16<SLOTS>(A, LD, n, j, w, sh, warp, lane, det, zero);
         __syncthreads();
-        if (sh->singular) break;
-        if (j + w1 >= n) { permute_rows<WARPS>(A, rowid, LD, sh, 0, 0, 0, 0); __syncthreads(); break; }
-        permute_rows<WARPS>(A, rowid, LD, sh, j + 8, n, 0, 0);
+        PH_MARK(1);
+        const bool last = (j + 16 >= n);
+        permute_rows<WARPS, CH>(A, rowid, LD, sh, last ? 0 : j + 16, last ? 0 : n);
         __syncthreads();
-        trsm_block_row<THREADS>(A, LD, n, j, j, 8, j + 8);
+        PH_MARK(2);
+        if (last) break;
+        trsm_block_row16<THREADS>(A, LD, n, j);
         __syncthreads();
-        const int w2 = min(8, n - j - 8);
-        // rank-8 update of the second sub-panel's columns only
-        dmma_update<WARPS>(A, LD, n, j + 8, j + 8, j + 8 + w2, j, 8);
-        __syncthreads();
-        // ---- second sub-panel
-        if (warp == 0) {
-            factor_subpanel<SLOTS>(A, rowid, LD, n, j + 8, w2, sh, lane, det, singular);
-            if (lane == 0 && singular) sh->singular = 1;
-        }
-        __syncthreads();
-        if (sh->singular) break;
-        if (j + 8 + w2 >= n) { permute_rows<WARPS>(A, rowid, LD, sh, 0, 0, 0, 0); __syncthreads(); break; }
-        permute_rows<WARPS>(A, rowid, LD, sh, j, j + 8, j + 16, n);
-        __syncthreads();
-        trsm_block_row<THREADS>(A, LD, n, j, j + 8, 8, j + 16);
-        __syncthreads();
-        // ---- rank-16 trailing update on the tensor cores
+        PH_MARK(3);
         dmma_update<WARPS>(A, LD, n, j + 16, j + 16, n, j, 16);
         __syncthreads();
+        PH_MARK(5);
     }
-    // ---- publish |det| from warp 0, sign from the row permutation (inversion count)
-    if (tid == 0) sh->det = det;
-    __syncthreads();
-    if (sh->singular) return 0.0;
+    // ---- |det| from thread 0 (a panel lane), sign from the row permutation (inversion count)
+    if (tid == 0) { sh->det = det; sh->singular = zero ? 1 : 0; }
     int inv = 0;
     for (int i = tid; i < n; i += THREADS) {
         const int ri = rowid[i];
         for (int k = i + 1; k < n; k++) inv += (rowid[k] < ri);
     }
     const int par = __syncthreads_count(inv & 1) & 1;
+    PH_MARK(6);
+    if (sh->singular) return 0.0;
     const double d = sh->det;
     return par ? -d : d;
 }
@@ -341,26 +323,48 @@ __host__ __device__ inline int blk_ld_h(int n) {
     if ((ld & 15) == 0) ld += 8;
     return ld;
 }
-inline size_t blk_smem_bytes(int n) {
-    return (size_t)blk_rows(n) * blk_ld_h(n) * sizeof(double) + 3 * (size_t)n * sizeof(int) + 64;
+inline size_t blk_mat_bytes(int n) { return (size_t)blk_rows(n) * blk_ld_h(n) * sizeof(double); }
+inline size_t blk_smem_bytes(int n, bool global_scratch = false) {
+    return (global_scratch ? 0 : blk_mat_bytes(n)) + 3 * (size_t)n * sizeof(int) + 64;
 }
 
+// gather the minor: warps walk rows, lanes walk columns (column indices cached in registers),
+// four rows in flight per warp so that 16 independent L2 loads are outstanding per thread
 __device__ __forceinline__ void gather_minor_ld(const double *__restrict__ S, int ld_s, const int *rows,
                                                 const int *cols, int n, double *a, int ld) {
-    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
-        int r = idx / n, c = idx - r * n;
-        a[r * ld + c] = __ldg(S + (size_t)rows[r] * ld_s + cols[c]);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int cc[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) cc[k] = (lane + 32 * k < n) ? cols[lane + 32 * k] : 0;
+    for (int r0 = warp * 4; r0 < n; r0 += nw * 4) {
+        double v[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int r = r0 + i;
+            const double *src = S + (size_t)rows[r < n ? r : 0] * ld_s;
+#pragma unroll
+            for (int k = 0; k < 4; k++) v[i][k] = (r < n && lane + 32 * k < n) ? __ldg(src + cc[k]) : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int r = r0 + i;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (r < n && lane + 32 * k < n) a[(size_t)r * ld + lane + 32 * k] = v[i][k];
+        }
     }
 }
 
-template <int WARPS, int SLOTS>
+// GLOBAL = true keeps the working matrix in a per-CTA global scratch (L2 resident) instead of
+// shared memory: more CTAs per SM for the larger n, at L2 instead of shared-memory latency.
+template <int WARPS, int SLOTS, bool GLOBAL>
 __global__ void __launch_bounds__(WARPS * 32)
 det_table_blk_kernel(const double *__restrict__ S, int ld_s, int n, const int32_t *__restrict__ rows, int kb,
-                     const int32_t *__restrict__ cols, int kk, double *__restrict__ D) {
+                     const int32_t *__restrict__ cols, int kk, double *__restrict__ D, double *gscratch) {
     extern __shared__ __align__(16) double sm[];
     const int LD = blk_ld_h(n);
-    double *a = sm;
-    int *ridx = (int *)(a + (size_t)blk_rows(n) * LD);
+    double *a = GLOBAL ? gscratch + (size_t)blockIdx.x * blk_rows(n) * LD : sm;
+    int *ridx = GLOBAL ? (int *)sm : (int *)(sm + (size_t)blk_rows(n) * LD);
     int *cidx = ridx + n;
     int *rowid = cidx + n;
     __shared__ BlkShared sh;
@@ -372,23 +376,29 @@ det_table_blk_kernel(const double *__restrict__ S, int ld_s, int n, const int32_
             cidx[i] = cols[(size_t)l * n + i];
         }
         __syncthreads();
+#ifdef WFO_PHASE_TIMING
+        long long g0_ = clock64();
+#endif
         gather_minor_ld(S, ld_s, ridx, cidx, n, a, LD);
         __syncthreads();
+#ifdef WFO_PHASE_TIMING
+        if (threadIdx.x == 0 && blockIdx.x == 0) { g_phase[0] += clock64() - g0_; g_phase[7] += 1; }
+#endif
         double det = cta_lu_det_blocked<WARPS, SLOTS>(a, rowid, LD, n, &sh);
         if (threadIdx.x == 0) D[pair] = det;
         __syncthreads();
     }
 }
 
-template <int WARPS, int SLOTS>
+template <int WARPS, int SLOTS, bool GLOBAL>
 __global__ void __launch_bounds__(WARPS * 32)
 t0_fused_blk_kernel(const double *__restrict__ S, int ld_s, int n, const int32_t *__restrict__ rows, int ksh,
                     const int32_t *__restrict__ cols, int kk, const double *__restrict__ ckt, int ldg,
-                    int chunk_len, int n_chunks, double *__restrict__ gpart) {
+                    int chunk_len, int n_chunks, double *__restrict__ gpart, double *gscratch) {
     extern __shared__ __align__(16) double sm[];
     const int LD = blk_ld_h(n);
-    double *a = sm;
-    int *ridx = (int *)(a + (size_t)blk_rows(n) * LD);
+    double *a = GLOBAL ? gscratch + (size_t)blockIdx.x * blk_rows(n) * LD : sm;
+    int *ridx = GLOBAL ? (int *)sm : (int *)(sm + (size_t)blk_rows(n) * LD);
     int *cidx = ridx + n;
     int *rowid = cidx + n;
     __shared__ BlkShared sh;
