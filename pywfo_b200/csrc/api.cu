@@ -73,11 +73,22 @@ static int gemm(wfo_ctx *ctx, bool ta, bool tb, int m, int n, int k, double alph
     if (m <= 0 || n <= 0) return WFO_OK;
     if (kslab <= 0) kslab = k > 0 ? k : 1;
     int nz = k > 0 ? cdiv(k, kslab) : 1;
-    dim3 grid(cdiv(n, GN), cdiv(m, GM), nz), block(128);
-    if (!ta && !tb) gemm_f64_kernel<false, false><<<grid, block, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kslab, slab_stride);
-    else if (!ta && tb) gemm_f64_kernel<false, true><<<grid, block, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kslab, slab_stride);
-    else if (ta && !tb) gemm_f64_kernel<true, false><<<grid, block, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kslab, slab_stride);
-    else gemm_f64_kernel<true, true><<<grid, block, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kslab, slab_stride);
+    // 64-row CTA tiles unless that leaves SMs idle
+    const bool small = (long long)cdiv(n, GN) * cdiv(m, 64) * nz < ctx->sm_count;
+    const int gm = small ? 32 : 64;
+    dim3 grid(cdiv(n, GN), cdiv(m, gm), nz), block(128);
+#define GEMM_LAUNCH(TA_, TB_)                                                                                     \
+    do {                                                                                                          \
+        if (small) gemm_f64_kernel<TA_, TB_, 32><<<grid, block, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, \
+                                                                         ldc, kslab, slab_stride);                \
+        else gemm_f64_kernel<TA_, TB_, 64><<<grid, block, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc,   \
+                                                                   kslab, slab_stride);                           \
+    } while (0)
+    if (!ta && !tb) GEMM_LAUNCH(false, false);
+    else if (!ta && tb) GEMM_LAUNCH(false, true);
+    else if (ta && !tb) GEMM_LAUNCH(true, false);
+    else GEMM_LAUNCH(true, true);
+#undef GEMM_LAUNCH
     WFO_LAUNCH_CHECK(ctx);
     return WFO_OK;
 }
@@ -177,10 +188,19 @@ static int det_table(wfo_ctx *ctx, const double *S, int ld_s, int n, const int32
 }
 
 template <int NT>
-static void launch_t1(dim3 grid, cudaStream_t st, const double *Ai, const double *W, const BraMeta *bra,
-                      const double *bscale, int ksh, const KetMeta *ket, const double *ckts, int kk,
-                      int lps, double *gpart) {
-    t1_fused_kernel<NT><<<grid, T1_WARPS * 32, 0, st>>>(Ai, W, bra, bscale, ksh, ket, ckts, kk, lps, gpart);
+static int launch_t1(wfo_ctx *ctx, int ktiles, int splits, cudaStream_t st, const double *Ai, const double *W,
+                     const BraMeta *bra, const double *bscale, int ksh, const KetMeta *ket, const double *ckts,
+                     int kk, int lps, int *counter, double *gpart) {
+    int per_sm = 1;
+    WFO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, t1_fused_kernel<NT>, T1_WARPS * 32, 0));
+    if (per_sm < 1) per_sm = 1;
+    const int items = ktiles * splits;
+    int grid = ctx->sm_count * per_sm;
+    if (grid > items) grid = items;
+    WFO_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
+    t1_fused_kernel<NT><<<grid, T1_WARPS * 32, 0, st>>>(Ai, W, bra, bscale, ksh, ket, ckts, kk, lps, ktiles, items,
+                                                        counter, gpart);
+    return WFO_OK;
 }
 
 struct Plan {   // everything wfo_state_overlaps needs from the arena
@@ -264,8 +284,8 @@ static Part make_part(const wfo_ctx *ctx, int ksh, int kk, int n_ket, bool may_t
     q.may_t0 = may_t0;
     q.want_t1 = want_t1;
     q.ldg = pick_ldg(n_ket);
-    const int target_ctas = ctx->sm_count * 16;
-    // T1: grid (k tiles of 128, l splits)
+    const int target_ctas = ctx->sm_count * 48;
+    // T1: work items (k tile, l split), fetched dynamically by persistent CTAs
     q.ktiles = cdiv(ksh, T1_KTILE);
     int splits = cdiv(target_ctas, q.ktiles);
     int max_splits = cdiv(kk, 4 * T1_LT);
@@ -522,13 +542,12 @@ static int state_overlaps_impl(wfo_ctx *ctx, size_t arena_off, const double *s_m
             long long ctot = (long long)kk * ldg;
             ckt_kernel<<<(unsigned)((ctot + 255) / 256), 256, 0, st>>>(Ck, kk, n_ket, p.ksgn, ldg, p.ckt);
             WFO_LAUNCH_CHECK(ctx);
-            dim3 grid(ktiles, t1_splits);
             if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev0, st));
+            int *counter = reinterpret_cast<int *>(p.w);   // w is written later in the stream
             switch (ldg / 8) {
-                case 1: launch_t1<1>(grid, st, p.Ai, p.Wb, p.bmeta, p.bscale, ksh, p.kmeta, p.ckt, kk, lps, p.gpart); break;
-                case 3: launch_t1<3>(grid, st, p.Ai, p.Wb, p.bmeta, p.bscale, ksh, p.kmeta, p.ckt, kk, lps, p.gpart); break;
-                case 5: launch_t1<5>(grid, st, p.Ai, p.Wb, p.bmeta, p.bscale, ksh, p.kmeta, p.ckt, kk, lps, p.gpart); break;
-                case 7: launch_t1<7>(grid, st, p.Ai, p.Wb, p.bmeta, p.bscale, ksh, p.kmeta, p.ckt, kk, lps, p.gpart); break;
+#define T1_CASE(NT_) case NT_: WFO_TRY(launch_t1<NT_>(ctx, ktiles, t1_splits, st, p.Ai, p.Wb, p.bmeta, p.bscale, ksh, p.kmeta, p.ckt, kk, lps, counter, p.gpart)); break;
+                T1_CASE(1) T1_CASE(3) T1_CASE(5) T1_CASE(7)
+#undef T1_CASE
                 default: return set_err(WFO_ERR_ARG, "state_overlaps: unsupported ldg %lld%s", "", ldg);
             }
             WFO_LAUNCH_CHECK(ctx);

@@ -4,8 +4,8 @@
 // for the base-block products X = C Ai, Y = Ai B, W = Dv - C Y of the rank-update
 // tier, and (with split-K slabs) for the final CI contraction S = Cb G.
 //
-// CTA tile 64x64, 4 warps in a 2x2 grid, warp tile 32x32 = 4x4 DMMA.8x8x4 tiles
-// (32 FP64 accumulators per thread), K tile 16, register-prefetched global loads
+// CTA tile GM x 64 (GM = 64, or 32 when that is needed to fill the 148 SMs), 4 warps in a
+// 2x2 grid, warp tile (GM/2) x 32 = (GM/16) x 4 DMMA.8x8x4 tiles, K tile 16, register-prefetched global loads
 // and padded shared tiles so both fragment loads are conflict-free
 // (A: stride 20 doubles, B: stride 72 doubles).  blockIdx.z selects a K slab
 // (split-K): slab z covers k in [z*kslab, min(k,(z+1)*kslab)) and writes
@@ -15,11 +15,11 @@
 
 namespace wfo {
 
-constexpr int GM = 64, GN = 64, GK = 16;
+constexpr int GN = 64, GK = 16;   // GM (64 or 32 rows per CTA) is a template parameter
 constexpr int GLDA = GK + 4;   // 20
 constexpr int GLDB = GN + 8;   // 72
 
-template <bool TA, bool TB>
+template <bool TA, bool TB, int GM>
 __global__ void __launch_bounds__(128)
 gemm_f64_kernel(int m, int n, int k, double alpha, const double *__restrict__ A, int lda,
                 const double *__restrict__ B, int ldb, double beta, double *__restrict__ C, int ldc,
@@ -30,23 +30,25 @@ gemm_f64_kernel(int m, int n, int k, double alpha, const double *__restrict__ A,
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+    constexpr int MT = GM / 16;               // 8-row tiles per warp (warps are 2 x 2)
+    constexpr int EA = GM * GK / 128;         // A elements per thread and k tile
+    const int wm = (warp >> 1) * (GM / 2), wn = (warp & 1) * 32;
     const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
     const int kbeg = blockIdx.z * kslab;
     const int kend = min(k, kbeg + kslab);
     C += (long long)blockIdx.z * slab_stride;
 
-    double acc[4][4][2];
+    double acc[MT][4][2];
 #pragma unroll
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < MT; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     // per-thread global->shared assignment: 8 elements of each tile
-    double ra[8], rb[8];
+    double ra[EA], rb[8];
     auto load_tiles = [&](int k0) {
 #pragma unroll
-        for (int e = 0; e < 8; e++) {
+        for (int e = 0; e < EA; e++) {
             int idx = tid + e * 128;
             int mm, kk;
             if (TA) { kk = idx / GM; mm = idx % GM; } else { mm = idx / GK; kk = idx % GK; }
@@ -54,6 +56,10 @@ gemm_f64_kernel(int m, int n, int k, double alpha, const double *__restrict__ A,
             double v = 0.0;
             if (gm < m && gk < kend) v = TA ? A[(long long)gk * lda + gm] : A[(long long)gm * lda + gk];
             ra[e] = v;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            int idx = tid + e * 128;
             int nn, kb;
             if (TB) { nn = idx / GK; kb = idx % GK; } else { kb = idx / GN; nn = idx % GN; }
             int gn = n0 + nn, gkb = k0 + kb;
@@ -64,11 +70,15 @@ gemm_f64_kernel(int m, int n, int k, double alpha, const double *__restrict__ A,
     };
     auto store_tiles = [&]() {
 #pragma unroll
-        for (int e = 0; e < 8; e++) {
+        for (int e = 0; e < EA; e++) {
             int idx = tid + e * 128;
             int mm, kk;
             if (TA) { kk = idx / GM; mm = idx % GM; } else { mm = idx / GK; kk = idx % GK; }
             As[mm * GLDA + kk] = ra[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            int idx = tid + e * 128;
             int nn, kb;
             if (TB) { nn = idx / GK; kb = idx % GK; } else { kb = idx / GN; nn = idx % GN; }
             Bs[kb * GLDB + nn] = rb[e];
@@ -83,20 +93,20 @@ gemm_f64_kernel(int m, int n, int k, double alpha, const double *__restrict__ A,
         if (k0 + GK < kend) load_tiles(k0 + GK);
 #pragma unroll
         for (int ks = 0; ks < GK; ks += 4) {
-            double a[4], b[4];
+            double a[MT], b[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) a[i] = As[(wm + 8 * i + g) * GLDA + ks + t];
+            for (int i = 0; i < MT; i++) a[i] = As[(wm + 8 * i + g) * GLDA + ks + t];
 #pragma unroll
             for (int j = 0; j < 4; j++) b[j] = Bs[(ks + t) * GLDB + wn + 8 * j + g];
 #pragma unroll
-            for (int i = 0; i < 4; i++)
+            for (int i = 0; i < MT; i++)
 #pragma unroll
                 for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
     }
 
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
+    for (int i = 0; i < MT; i++) {
         int row = m0 + wm + 8 * i + g;
         if (row >= m) continue;
 #pragma unroll

@@ -57,11 +57,13 @@ base_inverse_kernel(const double *__restrict__ A_src, int ld_src, int n, double 
     double det = 1.0, minp = 1e300, maxp = 0.0;
     int singular = 0;
 
+    // straight-line step body (no early exits, selects instead of branches): the compiler keeps
+    // the 32 matrix registers in place; a zero pivot only sets a sticky flag
 #pragma unroll
     for (int cj = 0; cj < 4; cj++) {          // column slot (static register index)
-        for (int lj = 0; lj < 32; lj++) {     // owning lane
+        const int nsteps = min(32, n - 32 * cj);
+        for (int lj = 0; lj < nsteps; lj++) { // owning lane
             const int j = lj + 32 * cj;
-            if (j >= n || singular) break;    // uniform
             const int b = j & 1;
             // ---- pivot search: per-warp candidate from lane lj, combined through shared memory
             if (lane == lj) {
@@ -69,55 +71,52 @@ base_inverse_kernel(const double *__restrict__ A_src, int ld_src, int n, double 
 #pragma unroll
                 for (int s = 0; s < LUB_RS; s++) {
                     const unsigned k = (hi_abs(a[s][cj]) & 0xffffff00u) | 0x80u | (unsigned)(warp + LUB_WARPS * s);
-                    if (!done[s]) key = max(key, k);
+                    key = max(key, done[s] ? 0u : k);
+                    mcol[b][warp + LUB_WARPS * s] = a[s][cj];
                 }
                 keys[b][warp] = key;
-#pragma unroll
-                for (int s = 0; s < LUB_RS; s++) mcol[b][warp + LUB_WARPS * s] = a[s][cj];
             }
             __syncthreads();
-            unsigned kmax = keys[b][lane];
-            kmax = __reduce_max_sync(0xffffffffu, kmax);
+            const unsigned kmax = __reduce_max_sync(0xffffffffu, keys[b][lane]);
             const int p = (int)(kmax & 0x7fu);          // pivot row
             const int wp = p % LUB_WARPS, sp = p / LUB_WARPS;
             const double d = mcol[b][p];
             const double ad = fabs(d);
-            if (kmax == 0 || !(ad > 0.0) || !isfinite(d)) { singular = 1; break; }   // uniform
+            singular |= (kmax == 0u || !(ad > 0.0) || !(ad < 1e300)) ? 1 : 0;
             det *= d;
             minp = fmin(minp, ad);
             maxp = fmax(maxp, ad);
-            const double rd = 1.0 / d;
+            const double rd = fast_rcp(d);
             if (warp == wp) {                           // publish the scaled pivot row
+                double row[4];
 #pragma unroll
-                for (int s = 0; s < LUB_RS; s++) {
-                    if (s == sp) {
+                for (int k = 0; k < 4; k++) row[k] = a[0][k];
 #pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const int c = lane + 32 * k;
-                            if (c < n) prow[b][c] = ((c == j) ? 1.0 : a[s][k]) * rd;
-                        }
-                        done[s] = true;
-                    }
+                for (int s = 1; s < LUB_RS; s++)
+#pragma unroll
+                    for (int k = 0; k < 4; k++) row[k] = (s == sp) ? a[s][k] : row[k];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int c = lane + 32 * k;
+                    prow[b][c] = ((c == j) ? 1.0 : row[k]) * rd;
                 }
                 if (lane == 0) { piv_of_col[j] = p; col_of_piv[p] = j; }
             }
             __syncthreads();
             double pr[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) pr[k] = (lane + 32 * k < n) ? prow[b][lane + 32 * k] : 0.0;
+            for (int k = 0; k < 4; k++) pr[k] = prow[b][lane + 32 * k];
 #pragma unroll
             for (int s = 0; s < LUB_RS; s++) {
                 const int r = warp + LUB_WARPS * s;
-                if (r == p) {
+                const bool is_p = (r == p);
+                done[s] = done[s] || is_p;
+                const double f = is_p ? 0.0 : mcol[b][r];
 #pragma unroll
-                    for (int k = 0; k < 4; k++) a[s][k] = pr[k];
-                } else if (r < n) {
-                    const double f = mcol[b][r];
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const double base = (lane + 32 * k == j) ? 0.0 : a[s][k];
-                        a[s][k] = fma(-f, pr[k], base);
-                    }
+                for (int k = 0; k < 4; k++) {
+                    const double base = (lane + 32 * k == j) ? 0.0 : a[s][k];
+                    const double upd = fma(-f, pr[k], base);
+                    a[s][k] = is_p ? pr[k] : upd;
                 }
             }
         }

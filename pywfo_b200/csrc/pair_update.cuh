@@ -16,7 +16,8 @@
 // (CkTs = s_l * Ck^T, zero padded to ldg columns).  Pair values never reach HBM
 // (pywfo/main.py:613-626 is the loop this replaces).
 //
-// CTA = 4 warps, 128 bra excitations (4 m-tiles of 8 per warp); the ket
+// CTA = 4 warps, 96 bra excitations (3 m-tiles of 8 per warp, 168 registers, 3 CTAs/SM);
+// persistent CTAs fetch (k tile, l split) work items from an atomic counter; the ket
 // coefficient tiles (32 excitations x ldg) are staged in shared memory with
 // cp.async double buffering and shared by the 4 warps.  Ai and W are gathered
 // through L1 (the host orders the ket excitations so that a CTA's working set
@@ -26,8 +27,17 @@
 
 namespace wfo {
 
-constexpr int T1_WARPS = 4;
-constexpr int T1_MT = 4;                         // m-tiles (8 bra excitations) per warp
+#ifndef WFO_T1_WARPS
+#define WFO_T1_WARPS 4
+#endif
+#ifndef WFO_T1_MT
+#define WFO_T1_MT 3
+#endif
+#ifndef WFO_T1_MINB
+#define WFO_T1_MINB 3
+#endif
+constexpr int T1_WARPS = WFO_T1_WARPS;
+constexpr int T1_MT = WFO_T1_MT;                 // m-tiles (8 bra excitations) per warp
 constexpr int T1_KTILE = T1_WARPS * T1_MT * 8;   // 128 bra excitations per CTA
 constexpr int T1_LT = 32;                        // ket excitations per shared tile
 
@@ -50,22 +60,31 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// NT = ldg / 8 column tiles of G.  grid = (k tiles, l splits).
+// NT = ldg / 8 column tiles of G.  Work item = (k tile, l split), fetched dynamically.
 // gpart[(split*ksh + k)*ldg + j]
 template <int NT>
-__global__ void __launch_bounds__(T1_WARPS * 32)
+__global__ void __launch_bounds__(T1_WARPS * 32, WFO_T1_MINB)
 t1_fused_kernel(const double *__restrict__ Ai, const double *__restrict__ W,
                 const BraMeta *__restrict__ bra, const double *__restrict__ bra_scale, int ksh,
                 const KetMeta *__restrict__ ket, const double *__restrict__ ckts, int kk,
-                int l_per_split, double *__restrict__ gpart) {
+                int l_per_split, int n_ktiles, int n_items, int *__restrict__ counter,
+                double *__restrict__ gpart) {
     constexpr int LDG = NT * 8;
     __shared__ __align__(16) double Bs[2][T1_LT * LDG];
     __shared__ __align__(16) KetMeta Ms[2][T1_LT];
+    __shared__ int s_item;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int k0 = blockIdx.x * T1_KTILE + warp * (T1_MT * 8);
-    const int l_begin = blockIdx.y * l_per_split;
+  for (;;) {
+    if (tid == 0) s_item = atomicAdd(counter, 1);
+    __syncthreads();
+    const int item = s_item;
+    __syncthreads();
+    if (item >= n_items) break;
+    const int split = item / n_ktiles, ktile = item - split * n_ktiles;
+    const int k0 = ktile * T1_KTILE + warp * (T1_MT * 8);
+    const int l_begin = split * l_per_split;
     const int l_end = min(kk, l_begin + l_per_split);
 
     // per-thread bra data for its 4 rows (one per m-tile)
@@ -156,13 +175,14 @@ t1_fused_kernel(const double *__restrict__ Ai, const double *__restrict__ W,
         int k = k0 + 8 * mi + g;
         if (k >= ksh) continue;
         double sc = bra_scale[k];
-        double *dst = gpart + ((size_t)blockIdx.y * ksh + k) * LDG + 2 * t;
+        double *dst = gpart + ((size_t)split * ksh + k) * LDG + 2 * t;
 #pragma unroll
         for (int ni = 0; ni < NT; ni++) {
             double2 v = make_double2(sc * acc[mi][ni][0], sc * acc[mi][ni][1]);
             *reinterpret_cast<double2 *>(dst + 8 * ni) = v;
         }
     }
+  }
 }
 
 }  // namespace wfo
