@@ -388,6 +388,11 @@ def hbm_peak():
 
 
 def main():
+    # the contract is ONE JSON line on stdout: everything else a library prints there (NCCL's
+    # version banner, ...) is diverted to stderr, the JSON goes to the saved descriptor
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -79,10 +79,18 @@ static int gemm(wfo_ctx *ctx, bool ta, bool tb, int m, int n, int k, double alph
     dim3 grid(cdiv(n, GN), cdiv(m, gm), nz), block(128);
 #define GEMM_LAUNCH(TA_, TB_)                                                                                     \
     do {                                                                                                          \
-        if (small) gemm_f64_kernel<TA_, TB_, 32><<<grid, block, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, \
-                                                                         ldc, kslab, slab_stride);                \
-        else gemm_f64_kernel<TA_, TB_, 64><<<grid, block, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc,   \
-                                                                   kslab, slab_stride);                           \
+        static bool attr_done_ = false;                                                                           \
+        if (!attr_done_) {                                                                                        \
+            WFO_CUDA(cudaFuncSetAttribute(gemm_f64_kernel<TA_, TB_, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)gemm_smem_bytes<32>()));                                           \
+            WFO_CUDA(cudaFuncSetAttribute(gemm_f64_kernel<TA_, TB_, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)gemm_smem_bytes<64>()));                                           \
+            attr_done_ = true;                                                                                    \
+        }                                                                                                         \
+        if (small) gemm_f64_kernel<TA_, TB_, 32><<<grid, block, gemm_smem_bytes<32>(), st>>>(                     \
+            m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kslab, slab_stride);                                    \
+        else gemm_f64_kernel<TA_, TB_, 64><<<grid, block, gemm_smem_bytes<64>(), st>>>(                           \
+            m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kslab, slab_stride);                                    \
     } while (0)
     if (!ta && !tb) GEMM_LAUNCH(false, false);
     else if (!ta && tb) GEMM_LAUNCH(false, true);
@@ -222,7 +230,7 @@ static void carve(AR &ar, Plan &p, int n, int v, int ksh, int kk, int n_bra, int
     p.gpart = ar.template take<double>((size_t)n_parts * ksh * ldg);
     p.G = ar.template take<double>((size_t)ksh * ldg);
     p.P = ar.template take<double>((size_t)n_slabs * n_bra * ldg);
-    p.w = ar.template take<double>(ldg);
+    p.w = ar.template take<double>((size_t)KGS_SLABS * ldg);
     p.dk0 = ar.template take<double>(ksh > 0 ? ksh : 1);
     p.d0l = ar.template take<double>(kk > 0 ? kk : 1);
     p.d00 = ar.template take<double>(1);
@@ -288,7 +296,7 @@ static Part make_part(const wfo_ctx *ctx, int ksh, int kk, int n_ket, bool may_t
     // T1: work items (k tile, l split), fetched dynamically by persistent CTAs
     q.ktiles = cdiv(ksh, T1_KTILE);
     int splits = cdiv(target_ctas, q.ktiles);
-    int max_splits = cdiv(kk, 4 * T1_LT);
+    int max_splits = cdiv(kk, 16 * T1_LT);   // at least 16 ket tiles per work item
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     q.lps = (int)align_up((size_t)cdiv(kk, splits), T1_LT);
@@ -616,7 +624,7 @@ static int state_overlaps_impl(wfo_ctx *ctx, size_t arena_off, const double *s_m
     WFO_LAUNCH_CHECK(ctx);
     WFO_TRY(gemm(ctx, false, false, n_bra, ldg, ksh, 1.0, Cb + k_begin, kb, p.G, ldg, 0.0, p.P, ldg, kslab,
                  (long long)n_bra * ldg, st));
-    ket_gs_dot_kernel<<<n_ket, 256, 0, st>>>(Ck, kk, p.d0l, p.w);
+    ket_gs_dot_kernel<<<dim3(n_ket, KGS_SLABS), 256, 0, st>>>(Ck, kk, n_ket, p.d0l, p.w);
     WFO_LAUNCH_CHECK(ctx);
     finalize_kernel<<<cdiv(n_bra * n_ket, 128), 128, 0, st>>>(p.P, n_slabs, n_bra, ldg, n_ket, p.w, d00_ptr, sigma, out);
     WFO_LAUNCH_CHECK(ctx);

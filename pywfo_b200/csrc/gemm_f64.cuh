@@ -5,27 +5,40 @@
 // tier, and (with split-K slabs) for the final CI contraction S = Cb G.
 //
 // CTA tile GM x 64 (GM = 64, or 32 when that is needed to fill the 148 SMs), 4 warps in a
-// 2x2 grid, warp tile (GM/2) x 32 = (GM/16) x 4 DMMA.8x8x4 tiles, K tile 16, register-prefetched global loads
-// and padded shared tiles so both fragment loads are conflict-free
-// (A: stride 20 doubles, B: stride 72 doubles).  blockIdx.z selects a K slab
-// (split-K): slab z covers k in [z*kslab, min(k,(z+1)*kslab)) and writes
-// C + z*slab_stride; deterministic, summed by a later kernel in fixed order.
+// 2x2 grid, warp tile (GM/2) x 32 = (GM/16) x 4 DMMA.8x8x4 tiles, K tile 16.  Operand tiles
+// are brought in with cp.async (8-byte elements, zero fill at the edges) through a 3-stage
+// shared-memory ring, so the L2 latency of tile t+2 hides behind the DMMAs of tile t with one
+// block barrier per K tile.  Padded shared tiles make both fragment loads conflict-free
+// (A: stride 20 doubles, B: stride 72 doubles).  blockIdx.z selects a K slab (split-K): slab z
+// covers k in [z*kslab, min(k,(z+1)*kslab)) and writes C + z*slab_stride; deterministic,
+// summed by a later kernel in fixed order.
 #pragma once
 #include "common.cuh"
 
 namespace wfo {
 
 constexpr int GN = 64, GK = 16;   // GM (64 or 32 rows per CTA) is a template parameter
-constexpr int GLDA = GK + 4;   // 20
-constexpr int GLDB = GN + 8;   // 72
+constexpr int GLDA = GK + 4;      // 20
+constexpr int GLDB = GN + 8;      // 72
+constexpr int GSTAGES = 3;
+
+template <int GM>
+constexpr size_t gemm_smem_bytes() { return (size_t)GSTAGES * (GM * GLDA + GK * GLDB) * sizeof(double); }
+
+// 8-byte async copy global -> shared; bytes = 0 zero-fills (out-of-range elements)
+__device__ __forceinline__ void cp_async8(double *dst, const double *src, bool ok) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int bytes = ok ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(src), "r"(bytes));
+}
 
 template <bool TA, bool TB, int GM>
 __global__ void __launch_bounds__(128)
 gemm_f64_kernel(int m, int n, int k, double alpha, const double *__restrict__ A, int lda,
                 const double *__restrict__ B, int ldb, double beta, double *__restrict__ C, int ldc,
                 int kslab, long long slab_stride) {
-    __shared__ double As[GM * GLDA];
-    __shared__ double Bs[GK * GLDB];
+    extern __shared__ __align__(16) double gsm[];
+    constexpr int STAGE = GM * GLDA + GK * GLDB;   // doubles per stage
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -44,53 +57,45 @@ gemm_f64_kernel(int m, int n, int k, double alpha, const double *__restrict__ A,
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    // per-thread global->shared assignment: 8 elements of each tile
-    double ra[EA], rb[8];
-    auto load_tiles = [&](int k0) {
+    auto issue_tile = [&](int stage, int k0) {
+        double *As = gsm + stage * STAGE;
+        double *Bs = As + GM * GLDA;
 #pragma unroll
         for (int e = 0; e < EA; e++) {
-            int idx = tid + e * 128;
+            const int idx = tid + e * 128;
             int mm, kk;
             if (TA) { kk = idx / GM; mm = idx % GM; } else { mm = idx / GK; kk = idx % GK; }
-            int gm = m0 + mm, gk = k0 + kk;
-            double v = 0.0;
-            if (gm < m && gk < kend) v = TA ? A[(long long)gk * lda + gm] : A[(long long)gm * lda + gk];
-            ra[e] = v;
+            const int gm = m0 + mm, gk = k0 + kk;
+            const bool ok = gm < m && gk < kend;
+            const double *src = ok ? (TA ? A + (long long)gk * lda + gm : A + (long long)gm * lda + gk) : A;
+            cp_async8(As + mm * GLDA + kk, src, ok);
         }
 #pragma unroll
         for (int e = 0; e < 8; e++) {
-            int idx = tid + e * 128;
+            const int idx = tid + e * 128;
             int nn, kb;
             if (TB) { nn = idx / GK; kb = idx % GK; } else { kb = idx / GN; nn = idx % GN; }
-            int gn = n0 + nn, gkb = k0 + kb;
-            double w = 0.0;
-            if (gn < n && gkb < kend) w = TB ? B[(long long)gn * ldb + gkb] : B[(long long)gkb * ldb + gn];
-            rb[e] = w;
-        }
-    };
-    auto store_tiles = [&]() {
-#pragma unroll
-        for (int e = 0; e < EA; e++) {
-            int idx = tid + e * 128;
-            int mm, kk;
-            if (TA) { kk = idx / GM; mm = idx % GM; } else { mm = idx / GK; kk = idx % GK; }
-            As[mm * GLDA + kk] = ra[e];
-        }
-#pragma unroll
-        for (int e = 0; e < 8; e++) {
-            int idx = tid + e * 128;
-            int nn, kb;
-            if (TB) { nn = idx / GK; kb = idx % GK; } else { kb = idx / GN; nn = idx % GN; }
-            Bs[kb * GLDB + nn] = rb[e];
+            const int gn = n0 + nn, gkb = k0 + kb;
+            const bool ok = gn < n && gkb < kend;
+            const double *src = ok ? (TB ? B + (long long)gn * ldb + gkb : B + (long long)gkb * ldb + gn) : B;
+            cp_async8(Bs + kb * GLDB + nn, src, ok);
         }
     };
 
-    if (kbeg < kend) load_tiles(kbeg);
-    for (int k0 = kbeg; k0 < kend; k0 += GK) {
-        __syncthreads();
-        store_tiles();
-        __syncthreads();
-        if (k0 + GK < kend) load_tiles(k0 + GK);
+    const int ntiles = (kend > kbeg) ? (kend - kbeg + GK - 1) / GK : 0;
+    // prologue: tiles 0 and 1 in flight (one commit group per tile, empty groups keep the count)
+#pragma unroll
+    for (int s = 0; s < GSTAGES - 1; s++) {
+        if (s < ntiles) issue_tile(s, kbeg + s * GK);
+        asm volatile("cp.async.commit_group;\n");
+    }
+    for (int it = 0; it < ntiles; it++) {
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(GSTAGES - 2));   // tile `it` has landed
+        __syncthreads();                                                  // ... for everyone; tile it-1 is consumed
+        if (it + GSTAGES - 1 < ntiles) issue_tile((it + GSTAGES - 1) % GSTAGES, kbeg + (it + GSTAGES - 1) * GK);
+        asm volatile("cp.async.commit_group;\n");
+        const double *As = gsm + (it % GSTAGES) * STAGE;
+        const double *Bs = As + GM * GLDA;
 #pragma unroll
         for (int ks = 0; ks < GK; ks += 4) {
             double a[MT], b[4];
@@ -104,6 +109,7 @@ gemm_f64_kernel(int m, int n, int k, double alpha, const double *__restrict__ A,
                 for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
     }
+    asm volatile("cp.async.wait_group 0;\n");
 
 #pragma unroll
     for (int i = 0; i < MT; i++) {

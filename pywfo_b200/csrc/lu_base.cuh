@@ -114,7 +114,8 @@ base_inverse_kernel(const double *__restrict__ A_src, int ld_src, int n, double 
                 const double f = is_p ? 0.0 : mcol[b][r];
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    const double base = (lane + 32 * k == j) ? 0.0 : a[s][k];
+                    // the eliminated column (static slot cj, lane lj) restarts from zero
+                    const double base = (k == cj && lane == lj) ? 0.0 : a[s][k];
                     const double upd = fma(-f, pr[k], base);
                     a[s][k] = is_p ? pr[k] : upd;
                 }

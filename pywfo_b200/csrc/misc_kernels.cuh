@@ -92,37 +92,42 @@ __global__ void sum_parts_kernel(const double *__restrict__ gpart, int n_parts, 
     G[idx] = s;
 }
 
-// w[j] = sum_l Ck[j][l] * d0l[l]   (one CTA per ket state, fixed-shape tree)
+// wpart[z][j] = sum over slab z of Ck[j][l] * d0l[l]  (grid (n_ket, KGS_SLABS), fixed-shape tree)
+constexpr int KGS_SLABS = 8;
 __global__ void __launch_bounds__(256)
-ket_gs_dot_kernel(const double *__restrict__ Ck, int kk, const double *__restrict__ d0l,
-                  double *__restrict__ w) {
+ket_gs_dot_kernel(const double *__restrict__ Ck, int kk, int n_ket, const double *__restrict__ d0l,
+                  double *__restrict__ wpart) {
     __shared__ double red[256];
-    const int j = blockIdx.x;
+    const int j = blockIdx.x, z = blockIdx.y;
+    const int per = (kk + KGS_SLABS - 1) / KGS_SLABS;
+    const int lb = z * per, le = min(kk, lb + per);
     double s = 0.0;
-    for (int l = threadIdx.x; l < kk; l += 256) s += Ck[(size_t)j * kk + l] * d0l[l];
+    for (int l = lb + threadIdx.x; l < le; l += 256) s += Ck[(size_t)j * kk + l] * d0l[l];
     red[threadIdx.x] = s;
     __syncthreads();
     for (int o = 128; o; o >>= 1) {
         if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) w[j] = red[0];
+    if (threadIdx.x == 0) wpart[z * n_ket + j] = red[0];
 }
 
-// out[i][j] = d00 * sum_z P[z][i][j] + sigma * (sum_z P[z][i][n_ket]) * w[j]
+// out[i][j] = d00 * sum_z P[z][i][j] + sigma * (sum_z P[z][i][n_ket]) * sum_z wpart[z][j]
 __global__ void finalize_kernel(const double *__restrict__ P, int n_slabs, int n_bra, int ldg, int n_ket,
-                                const double *__restrict__ w, const double *__restrict__ d00,
+                                const double *__restrict__ wpart, const double *__restrict__ d00,
                                 double sigma, double *__restrict__ out) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_bra * n_ket) return;
     int i = idx / n_ket, j = idx - i * n_ket;
-    double a = 0.0, u = 0.0;
+    double a = 0.0, u = 0.0, wj = 0.0;
+#pragma unroll
+    for (int z = 0; z < KGS_SLABS; z++) wj += wpart[z * n_ket + j];
     size_t slab = (size_t)n_bra * ldg;
     for (int z = 0; z < n_slabs; z++) {
         a += P[z * slab + (size_t)i * ldg + j];
         u += P[z * slab + (size_t)i * ldg + n_ket];
     }
-    out[idx] = (*d00) * a + sigma * u * w[j];
+    out[idx] = (*d00) * a + sigma * u * wj;
 }
 
 // ---- FP64 peak microbenchmarks (roofline denominators, bench.py) -------------
