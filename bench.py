@@ -315,8 +315,11 @@ def run_ours(args, w):
         flops_pair = f_det(n) + 2 * w["n_ket"]
         kname = "t0_fused_kernel (pivoted LU per pair + CI contraction)"
     achieved = pairs_shard * flops_pair / (k_ms * 1e-3) / 1e12
+    # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this
+    # exact configuration (profiles/r01_t1_fused_kernel_ncu_full_excerpt.csv); null for other configs
+    traffic = 22013952 + 270981376 if (args.workload == "c4" and world == 1 and used_tier == 1) else None
     roofline = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "measured in this run: max of register-resident DFMA loop and DMMA.8x8x4 loop "
                                "(MEASURED_PEAKS.json has no FP64 entry)",
                 "fp64_peaks_tflops": peaks, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,

@@ -39,7 +39,10 @@ namespace wfo {
 constexpr int T1_WARPS = WFO_T1_WARPS;
 constexpr int T1_MT = WFO_T1_MT;                 // m-tiles (8 bra excitations) per warp
 constexpr int T1_KTILE = T1_WARPS * T1_MT * 8;   // 128 bra excitations per CTA
-constexpr int T1_LT = 32;                        // ket excitations per shared tile
+#ifndef WFO_T1_LT
+#define WFO_T1_LT 32
+#endif
+constexpr int T1_LT = WFO_T1_LT;                 // ket excitations per shared tile
 
 struct KetMeta {   // one per ket excitation (16 bytes)
     int aoff;      // f' * n      (row offset into Ai)
