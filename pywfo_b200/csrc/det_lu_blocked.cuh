@@ -11,9 +11,12 @@
 //   * rows are physically compacted after every panel (pivot rows to the top, displaced
 //     rows into the vacated positions); an original-row-id column travels with the data
 //     and gives the permutation sign at the end;
-//   * triangular solve for the 16-row U block: one thread per trailing column;
-//   * trailing update A22 -= L21 U12 on the FP64 tensor cores (DMMA.8x8x4), rank 16,
-//     operands read from shared memory as fragments, 16x32 macro tiles per warp.
+//   * no triangular solve: the panel lanes turn their multipliers L21 into
+//     M = L21 L11^-1 in registers (120 FMA per row), so that the Schur complement is
+//     A22 - M A12 with the RAW pivot rows A12 (U12 is never needed for a determinant);
+//   * trailing update A22 -= M A12 on the FP64 tensor cores (DMMA.8x8x4), rank 16,
+//     operands read from shared memory as fragments, 16x32 macro tiles per warp,
+//     branch-free (clamped edge tiles, predicated stores).
 // The determinant is the signed product of the pivots -- the quantity np.linalg.det
 // returns for S_MO[rows][:, cols] (pywfo/main.py:583-584).
 #pragma once
@@ -44,6 +47,7 @@ struct BlkShared {
     unsigned key[2][4];          // per-warp pivot candidates, double buffered by column parity
     double cand[2][4][18];       // per-warp candidate rows (+ reciprocal of the candidate at [16])
     int piv_row[16];             // row chosen as pivot of step jj of the current panel
+    double L11[16][16];          // unit-lower factor of the pivot block (strict lower part used)
     int aff_dst[32];             // row positions that receive another row (-1: unused)
     int aff_src[32];             // ... and the position the row comes from
 };
@@ -111,7 +115,11 @@ __device__ __forceinline__ void factor_panel16(double *A, int LD, int n, int j0,
             det *= piv;
             zero = zero || (piv == 0.0);
             const bool win = (key == kmax) && (key != 0u);
-            if (win) sh->piv_row[jj] = r;
+            if (win) {
+                sh->piv_row[jj] = r;
+#pragma unroll
+                for (int c = 0; c < jj; c++) sh->L11[jj][c] = a[c];   // its multipliers: row jj of L11
+            }
             pstep = win ? jj : pstep;
             done = done || win;
             // branch-free elimination: finished rows use a zero multiplier
@@ -121,7 +129,17 @@ __device__ __forceinline__ void factor_panel16(double *A, int LD, int n, int j0,
             for (int c = jj + 1; c < 16; c++) a[c] = fma(-l, u[c], a[c]);
         }
     }
-    if (PW > 1) panel_bar(NT); else __syncwarp();   // piv_row[] complete
+    if (PW > 1) panel_bar(NT); else __syncwarp();   // piv_row[], L11[][] complete
+    // ---- M = L21 L11^-1 (row-wise back substitution x L11 = l) for the rows that stay in the
+    //      trailing matrix; only needed when a trailing matrix exists (full panel)
+    if (w == 16 && j0 + 16 < n && pstep < 0) {
+        // column-oriented (axpy) form: once x[q] is final, it updates all x[c], c < q, independently
+#pragma unroll
+        for (int q = 15; q >= 1; q--) {
+#pragma unroll
+            for (int c = 0; c < q; c++) a[c] = fma(-a[q], sh->L11[q][c], a[c]);
+        }
+    }
     // ---- final positions: pivot of step jj -> j0+jj; displaced rows (top w rows that are not
     //      pivots, all in warp 0) -> the positions vacated by pivots from below, in step order
     int newpos = (pstep >= 0) ? j0 + pstep : r;
@@ -151,6 +169,16 @@ __device__ __forceinline__ void factor_panel16(double *A, int LD, int n, int j0,
         }
         __syncwarp();
         if (displaced) { sh->aff_dst[16 + drank] = newpos; sh->aff_src[16 + drank] = r; }
+        __syncwarp();
+        // sign of this panel's row permutation = parity of the inversions among the moved rows
+        const int md = sh->aff_dst[lane], ms = sh->aff_src[lane];
+        int cnt = 0;
+#pragma unroll 8
+        for (int o = 0; o < 32; o++) {
+            const int d2 = __shfl_sync(FULL, md, o), s2 = __shfl_sync(FULL, ms, o);
+            cnt += (md >= 0 && d2 > md && s2 < ms && d2 >= 0) ? 1 : 0;
+        }
+        if (__popc(__ballot_sync(FULL, cnt & 1)) & 1) det = -det;
     }
     if (valid) {
         double2 *dst = reinterpret_cast<double2 *>(A + (size_t)newpos * LD + j0);
@@ -159,27 +187,24 @@ __device__ __forceinline__ void factor_panel16(double *A, int LD, int n, int j0,
     }
 }
 
-// Apply the published row moves to the columns [c0, c1) and to rowid.  All threads; one warp
+// Apply the published row moves to the columns [c0, c1).  All threads; one warp
 // per moved row, lanes over columns (CH chunks of 32); one block barrier between the reads
 // and the writes.
 template <int WARPS, int CH>
-__device__ __forceinline__ void permute_rows(double *A, int *rowid, int LD, const BlkShared *sh, int c0, int c1) {
+__device__ __forceinline__ void permute_rows(double *A, int LD, const BlkShared *sh, int c0, int c1) {
     constexpr int EPW = 32 / WARPS;          // entries per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wt = c1 - c0;
     double tmp[EPW][CH];
-    int rid[EPW];
 #pragma unroll
     for (int e = 0; e < EPW; e++) {
         const int src = sh->aff_src[warp * EPW + e];
-        rid[e] = -1;
 #pragma unroll
         for (int k = 0; k < CH; k++) {
             const int cc = lane + 32 * k;
             tmp[e][k] = 0.0;
             if (src >= 0 && cc < wt) tmp[e][k] = A[(size_t)src * LD + c0 + cc];
         }
-        if (src >= 0) rid[e] = rowid[src];
     }
     __syncthreads();
 #pragma unroll
@@ -191,7 +216,6 @@ __device__ __forceinline__ void permute_rows(double *A, int *rowid, int LD, cons
                 const int cc = lane + 32 * k;
                 if (cc < wt) A[(size_t)dst * LD + c0 + cc] = tmp[e][k];
             }
-            if (lane == 0) rowid[dst] = rid[e];
         }
     }
 }
@@ -214,101 +238,88 @@ __device__ __forceinline__ void trsm_block_row16(double *A, int LD, int n, int r
     }
 }
 
-// Trailing update C[R0.., C0..C1) -= L[R0.., KC..KC+KW) * U[KC..KC+KW, C0..C1) with DMMA.
-// KW in {8, 16}.  Rows/columns are processed in 8x8 tiles from R0/C0; the shared matrix has
-// round_up(n, 8) rows and LD >= round_up(n, 8) columns, so edge tiles stay in bounds.
+// Trailing update A[R0.., R0..) -= M[R0.., J..J+16) * A[J..J+16, R0..) with R0 = J+16, on the
+// tensor cores.  8x8 tiles from R0; macro tile = 2 tile rows x 4 tile columns per warp.  Edge
+// macro tiles clamp their tile indices (a duplicate tile is computed twice, stored once), so
+// there is no branch between the loads and the 32 DMMAs.  The shared matrix has
+// round_up(n, 8) rows and LD >= round_up(n, 8) columns, so every tile stays in bounds.
 template <int WARPS>
-__device__ __forceinline__ void dmma_update(double *A, int LD, int n, int R0, int C0, int C1, int KC, int KW) {
+__device__ __forceinline__ void dmma_update16(double *A, int LD, int n, int J) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int TR = (n - R0 + 7) >> 3, TC = (C1 - C0 + 7) >> 3;
-    if (TR <= 0 || TC <= 0) return;
-    const int MR = (TR + 1) >> 1, MC = (TC + 3) >> 2;   // macro tiles: 2 tile rows x 4 tile cols
-    const int ksteps = KW >> 2;
+    const int R0 = J + 16;
+    const int TR = (n - R0 + 7) >> 3;
+    if (TR <= 0) return;
+    const int MR = (TR + 1) >> 1, MC = (TR + 3) >> 2;
+    const double *Brow = A + (size_t)(J + t) * LD + R0 + g;      // B fragment base: row J+t, col R0+g
     for (int m = warp; m < MR * MC; m += WARPS) {
         const int mr = m / MC, mc = m - mr * MC;
-        const int tr0 = mr * 2, tc0 = mc * 4;
-        const int nr = min(2, TR - tr0), nc = min(4, TC - tc0);
+        int ri[2], cj[4];
+        bool vr[2], vc[4];
+#pragma unroll
+        for (int i = 0; i < 2; i++) { vr[i] = 2 * mr + i < TR; ri[i] = min(2 * mr + i, TR - 1); }
+#pragma unroll
+        for (int j = 0; j < 4; j++) { vc[j] = 4 * mc + j < TR; cj[j] = min(4 * mc + j, TR - 1); }
+        double *crow[2];
+#pragma unroll
+        for (int i = 0; i < 2; i++) crow[i] = A + (size_t)(R0 + 8 * ri[i] + g) * LD;
         double acc[2][4][2];
-        // load C fragments
 #pragma unroll
         for (int i = 0; i < 2; i++)
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                if (i < nr && j < nc) {
-                    const double2 v = *reinterpret_cast<const double2 *>(
-                        A + (size_t)(R0 + 8 * (tr0 + i) + g) * LD + C0 + 8 * (tc0 + j) + 2 * t);
-                    acc[i][j][0] = v.x;
-                    acc[i][j][1] = v.y;
-                } else {
-                    acc[i][j][0] = acc[i][j][1] = 0.0;
-                }
+                const double2 v = *reinterpret_cast<const double2 *>(crow[i] + R0 + 8 * cj[j] + 2 * t);
+                acc[i][j][0] = v.x;
+                acc[i][j][1] = v.y;
             }
-        for (int ks = 0; ks < ksteps; ks++) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++) {
             double af[2], bf[4];
 #pragma unroll
-            for (int i = 0; i < 2; i++)
-                af[i] = (i < nr) ? -A[(size_t)(R0 + 8 * (tr0 + i) + g) * LD + KC + 4 * ks + t] : 0.0;
+            for (int i = 0; i < 2; i++) af[i] = -crow[i][J + 4 * ks + t];
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-                bf[j] = (j < nc) ? A[(size_t)(KC + 4 * ks + t) * LD + C0 + 8 * (tc0 + j) + g] : 0.0;
+            for (int j = 0; j < 4; j++) bf[j] = Brow[(size_t)(4 * ks) * LD + 8 * cj[j]];
 #pragma unroll
             for (int i = 0; i < 2; i++)
 #pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if (i < nr && j < nc) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
 #pragma unroll
         for (int i = 0; i < 2; i++)
 #pragma unroll
             for (int j = 0; j < 4; j++)
-                if (i < nr && j < nc)
-                    *reinterpret_cast<double2 *>(A + (size_t)(R0 + 8 * (tr0 + i) + g) * LD + C0 + 8 * (tc0 + j) + 2 * t) =
+                if (vr[i] && vc[j])
+                    *reinterpret_cast<double2 *>(crow[i] + R0 + 8 * cj[j] + 2 * t) =
                         make_double2(acc[i][j][0], acc[i][j][1]);
     }
 }
 
 // Whole factorisation; all threads of the CTA call it.  A: round_up(n,8) x LD in shared
-// memory (destroyed), rowid: n ints.  Returns the determinant to every thread.
+// memory (destroyed).  Returns the determinant to every thread.
 template <int WARPS, int SLOTS>
-__device__ __forceinline__ double cta_lu_det_blocked(double *A, int *rowid, int LD, int n, BlkShared *sh) {
-    constexpr int THREADS = WARPS * 32;
+__device__ __forceinline__ double cta_lu_det_blocked(double *A, int LD, int n, BlkShared *sh) {
     constexpr int CH = SLOTS;   // column chunks of 32 that cover n
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < n; i += THREADS) rowid[i] = i;
-    double det = 1.0;
+    double det = 1.0;           // signed: the panel warps fold the permutation sign in
     bool zero = false;
-    __syncthreads();
     PH_DECL
     for (int j = 0; j < n; j += 16) {
         const int w = min(16, n - j);
         if (warp < SLOTS) factor_panel16<SLOTS>(A, LD, n, j, w, sh, warp, lane, det, zero);
+        if (j + 16 >= n) break;   // last panel: nothing left to permute or update
         __syncthreads();
         PH_MARK(1);
-        const bool last = (j + 16 >= n);
-        permute_rows<WARPS, CH>(A, rowid, LD, sh, last ? 0 : j + 16, last ? 0 : n);
+        permute_rows<WARPS, CH>(A, LD, sh, j + 16, n);
         __syncthreads();
         PH_MARK(2);
-        if (last) break;
-        trsm_block_row16<THREADS>(A, LD, n, j);
-        __syncthreads();
-        PH_MARK(3);
-        dmma_update<WARPS>(A, LD, n, j + 16, j + 16, n, j, 16);
+        dmma_update16<WARPS>(A, LD, n, j);
         __syncthreads();
         PH_MARK(5);
     }
-    // ---- |det| from thread 0 (a panel lane), sign from the row permutation (inversion count)
     if (tid == 0) { sh->det = det; sh->singular = zero ? 1 : 0; }
-    int inv = 0;
-    for (int i = tid; i < n; i += THREADS) {
-        const int ri = rowid[i];
-        for (int k = i + 1; k < n; k++) inv += (rowid[k] < ri);
-    }
-    const int par = __syncthreads_count(inv & 1) & 1;
+    __syncthreads();
     PH_MARK(6);
-    if (sh->singular) return 0.0;
-    const double d = sh->det;
-    return par ? -d : d;
+    return sh->singular ? 0.0 : sh->det;
 }
 
 }  // namespace wfo
@@ -325,28 +336,29 @@ __host__ __device__ inline int blk_ld_h(int n) {
 }
 inline size_t blk_mat_bytes(int n) { return (size_t)blk_rows(n) * blk_ld_h(n) * sizeof(double); }
 inline size_t blk_smem_bytes(int n, bool global_scratch = false) {
-    return (global_scratch ? 0 : blk_mat_bytes(n)) + 3 * (size_t)n * sizeof(int) + 64;
+    return (global_scratch ? 0 : blk_mat_bytes(n)) + 2 * (size_t)n * sizeof(int) + 64;
 }
 
 // gather the minor: warps walk rows, lanes walk columns (column indices cached in registers),
-// four rows in flight per warp so that 16 independent L2 loads are outstanding per thread
+// eight rows in flight per warp so that 32 independent L2 loads are outstanding per thread
 __device__ __forceinline__ void gather_minor_ld(const double *__restrict__ S, int ld_s, const int *rows,
                                                 const int *cols, int n, double *a, int ld) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     int cc[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) cc[k] = (lane + 32 * k < n) ? cols[lane + 32 * k] : 0;
-    for (int r0 = warp * 4; r0 < n; r0 += nw * 4) {
-        double v[4][4];
+    constexpr int RF = 8;   // rows in flight per warp: 32 independent L2 loads per thread
+    for (int r0 = warp * RF; r0 < n; r0 += nw * RF) {
+        double v[RF][4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < RF; i++) {
             const int r = r0 + i;
             const double *src = S + (size_t)rows[r < n ? r : 0] * ld_s;
 #pragma unroll
             for (int k = 0; k < 4; k++) v[i][k] = (r < n && lane + 32 * k < n) ? __ldg(src + cc[k]) : 0.0;
         }
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < RF; i++) {
             const int r = r0 + i;
 #pragma unroll
             for (int k = 0; k < 4; k++)
@@ -357,8 +369,14 @@ __device__ __forceinline__ void gather_minor_ld(const double *__restrict__ S, in
 
 // GLOBAL = true keeps the working matrix in a per-CTA global scratch (L2 resident) instead of
 // shared memory: more CTAs per SM for the larger n, at L2 instead of shared-memory latency.
+#ifndef WFO_T0_MINB64
+#define WFO_T0_MINB64 5
+#endif
+// minimum resident CTAs asked of the compiler: the 4-warp (n <= 64) configuration is register limited
+constexpr int blk_minb(int warps) { return warps == 4 ? WFO_T0_MINB64 : 1; }
+
 template <int WARPS, int SLOTS, bool GLOBAL>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, blk_minb(WARPS))
 det_table_blk_kernel(const double *__restrict__ S, int ld_s, int n, const int32_t *__restrict__ rows, int kb,
                      const int32_t *__restrict__ cols, int kk, double *__restrict__ D, double *gscratch) {
     extern __shared__ __align__(16) double sm[];
@@ -366,7 +384,6 @@ det_table_blk_kernel(const double *__restrict__ S, int ld_s, int n, const int32_
     double *a = GLOBAL ? gscratch + (size_t)blockIdx.x * blk_rows(n) * LD : sm;
     int *ridx = GLOBAL ? (int *)sm : (int *)(sm + (size_t)blk_rows(n) * LD);
     int *cidx = ridx + n;
-    int *rowid = cidx + n;
     __shared__ BlkShared sh;
     const long long npairs = (long long)kb * kk;
     for (long long pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
@@ -384,14 +401,14 @@ det_table_blk_kernel(const double *__restrict__ S, int ld_s, int n, const int32_
 #ifdef WFO_PHASE_TIMING
         if (threadIdx.x == 0 && blockIdx.x == 0) { g_phase[0] += clock64() - g0_; g_phase[7] += 1; }
 #endif
-        double det = cta_lu_det_blocked<WARPS, SLOTS>(a, rowid, LD, n, &sh);
+        double det = cta_lu_det_blocked<WARPS, SLOTS>(a, LD, n, &sh);
         if (threadIdx.x == 0) D[pair] = det;
         __syncthreads();
     }
 }
 
 template <int WARPS, int SLOTS, bool GLOBAL>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, blk_minb(WARPS))
 t0_fused_blk_kernel(const double *__restrict__ S, int ld_s, int n, const int32_t *__restrict__ rows, int ksh,
                     const int32_t *__restrict__ cols, int kk, const double *__restrict__ ckt, int ldg,
                     int chunk_len, int n_chunks, double *__restrict__ gpart, double *gscratch) {
@@ -400,7 +417,6 @@ t0_fused_blk_kernel(const double *__restrict__ S, int ld_s, int n, const int32_t
     double *a = GLOBAL ? gscratch + (size_t)blockIdx.x * blk_rows(n) * LD : sm;
     int *ridx = GLOBAL ? (int *)sm : (int *)(sm + (size_t)blk_rows(n) * LD);
     int *cidx = ridx + n;
-    int *rowid = cidx + n;
     __shared__ BlkShared sh;
     const long long nitems = (long long)ksh * n_chunks;
     for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
@@ -413,7 +429,7 @@ t0_fused_blk_kernel(const double *__restrict__ S, int ld_s, int n, const int32_t
             __syncthreads();
             gather_minor_ld(S, ld_s, ridx, cidx, n, a, LD);
             __syncthreads();
-            const double det = cta_lu_det_blocked<WARPS, SLOTS>(a, rowid, LD, n, &sh);
+            const double det = cta_lu_det_blocked<WARPS, SLOTS>(a, LD, n, &sh);
             if (threadIdx.x < ldg) g += det * __ldg(ckt + (size_t)l * ldg + threadIdx.x);
             __syncthreads();
         }
