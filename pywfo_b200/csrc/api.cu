@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "det_lu_blocked.cuh"
 #include "det_lu_v1.cuh"
+#include "det_lu_warp.cuh"
 #include "gemm_f64.cuh"
 #include "lu_base.cuh"
 #include "misc_kernels.cuh"
@@ -150,6 +151,20 @@ static int ensure_gscratch(wfo_ctx *ctx, size_t bytes) {
     return WFO_OK;
 }
 
+static bool use_warp_kernels(int n) {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("WFO_T0_NOWARP"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1 && n <= 32;
+}
+// register-resident segment kernels for n <= 32: (padded columns, lanes per determinant)
+#define WFO_WARP_DISPATCH(n, CALL)             \
+    do {                                       \
+        if ((n) <= 8) { CALL(8, 8); }          \
+        else if ((n) <= 16) { CALL(16, 16); }  \
+        else if ((n) <= 24) { CALL(24, 32); }  \
+        else { CALL(32, 32); }                 \
+    } while (0)
+
 template <typename K>
 static int persistent_grid(wfo_ctx *ctx, K kernel, int threads, size_t smem, long long items, unsigned *grid) {
     WFO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -174,6 +189,12 @@ static int det_table(wfo_ctx *ctx, const double *S, int ld_s, int n, const int32
         int threads = t0_threads(n);
         WFO_TRY(persistent_grid(ctx, det_table_kernel, threads, smem, npairs, &grid));
         det_table_kernel<<<grid, threads, smem, st>>>(S, ld_s, n, rows, kb, cols, kk, D);
+    } else if (use_warp_kernels(n)) {
+#define CALL_DW(NC_, SEG_)                                                                                 \
+    WFO_TRY(persistent_grid(ctx, det_table_warp_kernel<NC_, SEG_>, 128, 0, (npairs + 3) / 4, &grid));      \
+    det_table_warp_kernel<NC_, SEG_><<<grid, 128, 0, st>>>(S, ld_s, n, rows, kb, cols, kk, D)
+        WFO_WARP_DISPATCH(n, CALL_DW);
+#undef CALL_DW
     } else {
         const bool gl = t0_global_scratch(n);
         size_t smem = blk_smem_bytes(n, gl);
@@ -592,6 +613,14 @@ static int state_overlaps_impl(wfo_ctx *ctx, size_t arena_off, const double *s_m
             if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev0, st));
             t0_fused_kernel<<<grid, threads, smem, st>>>(s_mo, n_mo, n, p.bra_lists, ksh, p.ket_lists, kk, p.ckt,
                                                          ldg, chunk_len, t0_chunks, p.gpart);
+        } else if (use_warp_kernels(n)) {
+#define CALL_FW(NC_, SEG_)                                                                                      \
+    WFO_TRY(persistent_grid(ctx, t0_fused_warp_kernel<NC_, SEG_>, 128, 0, (items + 3) / 4, &grid));             \
+    if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev0, st));                                                   \
+    t0_fused_warp_kernel<NC_, SEG_><<<grid, 128, 0, st>>>(s_mo, n_mo, n, p.bra_lists, ksh, p.ket_lists, kk,     \
+                                                          p.ckt, ldg, chunk_len, t0_chunks, p.gpart)
+            WFO_WARP_DISPATCH(n, CALL_FW);
+#undef CALL_FW
         } else {
             const bool gl = t0_global_scratch(n);
             size_t smem = blk_smem_bytes(n, gl);
