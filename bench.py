@@ -351,6 +351,30 @@ def run_ours(args, w):
             "note": "brute-force tier on a sample of the same workload; full workload at this rate: "
                     f"{n_pairs / (ks * kl / (t0m * 1e-3)):.1f} s"}
 
+    # ---- the opt-in closed-form tier (GEMMs only, pair determinants never formed): wall time only
+    if args.t2:
+        try:
+            for _ in range(2):
+                ctx.state_overlaps_dev(d_smo, n, d_be, d_cb, d_ke, d_ck, d_out, sigma=sigma, tier="closed",
+                                       k_begin=lo, k_end=hi, stream=stream)
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ctx.state_overlaps_dev(d_smo, n, d_be, d_cb, d_ke, d_ck, d_out, sigma=sigma, tier="closed",
+                                       k_begin=lo, k_end=hi, stream=stream)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            t2_res = d_out.cpu().numpy()
+            kernels["t2_closed_form"] = {
+                "ms_per_matrix_stages_2_3": float(np.mean(ts)),
+                "max_rel_diff_vs_default_tier": float(np.abs(t2_res - result_first).max() / max(np.abs(result_first).max(), 1e-300)),
+                "note": "same tables, stages 2+3 only (S_MO resident); no per-pair work, so no pairs/s is quoted"}
+        except Exception as exc:   # e.g. ground-state entries in the tables
+            kernels["t2_closed_form"] = {"error": str(exc)}
+
     cpu = None
     if world == 1 and args.cpu_budget > 0:
         v, dt, sample, _ = cpu_baseline_run(w, budget_s=args.cpu_budget)
@@ -407,6 +431,7 @@ def main():
     ap.add_argument("--t0-sample", type=int, default=16384, help="pairs in the brute-force sample leg (0 = skip)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU baseline work (0 = skip)")
     ap.add_argument("--no-check", dest="check", action="store_false")
+    ap.add_argument("--no-t2", dest="t2", action="store_false", help="skip the closed-form tier timing")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

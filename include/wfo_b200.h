@@ -42,7 +42,7 @@ extern "C" {
 /* algorithm tiers (identical results to ~1e-13) */
 #define WFO_TIER_LU 0      /* T0: one partially pivoted LU per determinant pair          */
 #define WFO_TIER_UPDATE 1  /* T1: one base LU + rank-1 row/column update per pair        */
-#define WFO_TIER_CLOSED 2  /* T2: closed-form contraction, pair determinants not formed  */
+#define WFO_TIER_CLOSED 2  /* T2: closed-form contraction (GEMMs only), pair determinants never formed; opt-in */
 #define WFO_TIER_AUTO (-1) /* T1, falling back to T0 when the base block is singular      */
 
 typedef struct wfo_ctx wfo_ctx;

@@ -70,10 +70,10 @@ static int ensure_scratch_keep(wfo_ctx *ctx, size_t bytes, size_t keep_bytes) {
 
 static int gemm(wfo_ctx *ctx, bool ta, bool tb, int m, int n, int k, double alpha, const double *A, int lda,
                 const double *B, int ldb, double beta, double *C, int ldc, int kslab, long long slab_stride,
-                cudaStream_t st) {
+                cudaStream_t st, int batch = 0, long long batch_a = 0, long long batch_b = 0) {
     if (m <= 0 || n <= 0) return WFO_OK;
-    if (kslab <= 0) kslab = k > 0 ? k : 1;
-    int nz = k > 0 ? cdiv(k, kslab) : 1;
+    if (kslab <= 0 || batch > 0) kslab = k > 0 ? k : 1;
+    int nz = batch > 0 ? batch : (k > 0 ? cdiv(k, kslab) : 1);
     // 64-row CTA tiles unless that leaves SMs idle
     const bool small = (long long)cdiv(n, GN) * cdiv(m, 64) * nz < ctx->sm_count;
     const int gm = small ? 32 : 64;
@@ -89,9 +89,9 @@ static int gemm(wfo_ctx *ctx, bool ta, bool tb, int m, int n, int k, double alph
             attr_done_ = true;                                                                                    \
         }                                                                                                         \
         if (small) gemm_f64_kernel<TA_, TB_, 32><<<grid, block, gemm_smem_bytes<32>(), st>>>(                     \
-            m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kslab, slab_stride);                                    \
+            m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kslab, slab_stride, batch_a, batch_b);                  \
         else gemm_f64_kernel<TA_, TB_, 64><<<grid, block, gemm_smem_bytes<64>(), st>>>(                           \
-            m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kslab, slab_stride);                                    \
+            m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kslab, slab_stride, batch_a, batch_b);                  \
     } while (0)
     if (!ta && !tb) GEMM_LAUNCH(false, false);
     else if (!ta && tb) GEMM_LAUNCH(false, true);
@@ -289,8 +289,15 @@ static size_t base_smem_bytes(int n) { return n <= LUB_MAXN ? 0 : (size_t)1 << 4
 
 // which tiers can / should run for this call
 static int resolve_tier(const wfo_ctx *ctx, int n, int tier, bool *want_t1, bool *may_t0) {
-    if (tier != WFO_TIER_AUTO && tier != WFO_TIER_LU && tier != WFO_TIER_UPDATE)
-        return set_err(WFO_ERR_ARG, "state_overlaps: tier %lld not available%s", "", tier);
+    if (tier != WFO_TIER_AUTO && tier != WFO_TIER_LU && tier != WFO_TIER_UPDATE && tier != WFO_TIER_CLOSED)
+        return set_err(WFO_ERR_ARG, "state_overlaps: unknown tier %lld%s", "", tier);
+    if (tier == WFO_TIER_CLOSED) {   // shares the base-block machinery (and its size limit) with UPDATE
+        *want_t1 = true;
+        *may_t0 = false;
+        if (base_smem_bytes(n) > ctx->smem_optin)
+            return set_err(WFO_ERR_ARG, "state_overlaps: tier CLOSED supports n_occ <= 128, got %lld%s", "", n);
+        return WFO_OK;
+    }
     *want_t1 = (tier == WFO_TIER_AUTO || tier == WFO_TIER_UPDATE);
     *may_t0 = (tier == WFO_TIER_AUTO || tier == WFO_TIER_LU);
     const bool t0_fits = n <= 128 && t0_smem_bytes(n) <= ctx->smem_optin;
@@ -506,6 +513,96 @@ int wfo_det_table_host(wfo_ctx *ctx, const double *s_mo, int n_mo, int n, const 
     return WFO_OK;
 }
 
+static size_t closed_form_bytes(int n, int v, int n_bra, int n_ket) {
+    const size_t nv = (size_t)n * v;
+    Sizer z;
+    z.take<double>((size_t)n * n); z.take<double>(nv); z.take<double>(nv); z.take<double>((size_t)(v + 1) * (v + 1));
+    z.take<double>((size_t)n_bra * nv); z.take<double>((size_t)n_ket * nv); z.take<double>((size_t)n_bra * nv);
+    z.take<double>((size_t)n_bra * nv); z.take<double>((size_t)cdiv((int)nv, 1024) * n_bra * n_ket);
+    z.take<double>(n_bra); z.take<double>(n_ket); z.take<BaseInfo>(1); z.take<int>(1);
+    return z.off;
+}
+
+// T2: closed-form contraction: pair determinants are never formed.
+//   S_ij = det(A)^2 [ (1+sigma) <c~_i, X^T> <c~'_j, Y> + < Ai c~_i W , c~'_j > ]
+// with dense signed CI tensors c~[s][f][t]; everything is DMMA GEMMs.
+static int closed_form_impl(wfo_ctx *ctx, size_t arena_off, const double *s_mo, int n_mo, int n,
+                            const int32_t *bra_exc, int kb, const double *Cb, int n_bra, const int32_t *ket_exc,
+                            int kk, const double *Ck, int n_ket, double sigma, int k_begin, int k_end, double *out,
+                            cudaStream_t st) {
+    const int v = n_mo - n;
+    const size_t nv = (size_t)n * v;
+    const int kslab = 1024, n_slabs = cdiv((int)nv, kslab);
+    Sizer sz;
+    sz.off = arena_off;
+    auto carve2 = [&](auto &ar, double *&Ai, double *&Xt, double *&Y, double *&Wb, double *&cb, double *&ck, double *&Z,
+                      double *&T, double *&P, double *&bx, double *&ky, BaseInfo *&info, int *&flag) {
+        Ai = ar.template take<double>((size_t)n * n);
+        Xt = ar.template take<double>(nv);
+        Y = ar.template take<double>(nv);
+        Wb = ar.template take<double>((size_t)(v + 1) * (v + 1));
+        cb = ar.template take<double>((size_t)n_bra * nv);
+        ck = ar.template take<double>((size_t)n_ket * nv);
+        Z = ar.template take<double>((size_t)n_bra * nv);
+        T = ar.template take<double>((size_t)n_bra * nv);
+        P = ar.template take<double>((size_t)n_slabs * n_bra * n_ket);
+        bx = ar.template take<double>(n_bra);
+        ky = ar.template take<double>(n_ket);
+        info = ar.template take<BaseInfo>(1);
+        flag = ar.template take<int>(1);
+    };
+    double *Ai, *Xt, *Y, *Wb, *cb, *ck, *Z, *T, *P, *bx, *ky;
+    BaseInfo *info;
+    int *flag;
+    carve2(sz, Ai, Xt, Y, Wb, cb, ck, Z, T, P, bx, ky, info, flag);
+    WFO_TRY(ensure_scratch(ctx, sz.off));
+    Arena ar{ctx->scratch, ctx->scratch_bytes, arena_off};
+    carve2(ar, Ai, Xt, Y, Wb, cb, ck, Z, T, P, bx, ky, info, flag);
+
+    base_inverse_kernel<<<1, LUB_THREADS, 0, st>>>(s_mo, n_mo, n, Ai, info);
+    WFO_LAUNCH_CHECK(ctx);
+    WFO_CUDA(cudaMemsetAsync(cb, 0, (size_t)n_bra * nv * 8, st));
+    WFO_CUDA(cudaMemsetAsync(ck, 0, (size_t)n_ket * nv * 8, st));
+    WFO_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    scatter_signed_ci_kernel<<<dim3(cdiv(k_end - k_begin, 256), n_bra), 256, 0, st>>>(bra_exc, Cb, n_bra, kb, k_begin,
+                                                                                   k_end, n, v, cb, flag);
+    WFO_LAUNCH_CHECK(ctx);
+    scatter_signed_ci_kernel<<<dim3(cdiv(kk, 256), n_ket), 256, 0, st>>>(ket_exc, Ck, n_ket, kk, 0, kk, n, v, ck, flag);
+    WFO_LAUNCH_CHECK(ctx);
+    struct { BaseInfo info; int flag; } h;
+    WFO_CUDA(cudaMemcpyAsync(&h.info, info, sizeof(BaseInfo), cudaMemcpyDeviceToHost, st));
+    WFO_CUDA(cudaMemcpyAsync(&h.flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    WFO_CUDA(cudaStreamSynchronize(st));
+    if (h.flag) return set_err(WFO_ERR_ARG, "state_overlaps: tier CLOSED takes excitation tables without ground-state entries%s");
+    if (h.info.singular || !(h.info.min_piv > 1e-6 * h.info.max_piv))
+        return set_err(WFO_ERR_SINGULAR, "state_overlaps: base block S_MO[:occ,:occ] is (numerically) singular, "
+                                         "tier CLOSED not applicable%s");
+    const double *Bblk = s_mo + n;                    // occ  x virt
+    const double *Cblk = s_mo + (size_t)n * n_mo;     // virt x occ
+    // Xt = (C Ai)^T = Ai^T C^T (n x v), Y = Ai B (n x v), W = Dv - C Y (v x v, ld v+1)
+    WFO_TRY(gemm(ctx, true, true, n, v, n, 1.0, Ai, n, Cblk, n_mo, 0.0, Xt, v, 0, 0, st));
+    WFO_TRY(gemm(ctx, false, false, n, v, n, 1.0, Ai, n, Bblk, n_mo, 0.0, Y, v, 0, 0, st));
+    long long wtot = (long long)(v + 1) * (v + 1);
+    w_init_kernel<<<(unsigned)((wtot + 255) / 256), 256, 0, st>>>(s_mo, n_mo, n, v, Wb);
+    WFO_LAUNCH_CHECK(ctx);
+    WFO_TRY(gemm(ctx, false, false, v, v, n, -1.0, Cblk, n_mo, Y, v, 1.0, Wb, v + 1, 0, 0, st));
+    if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev0, st));
+    // Z = c~_bra W  ((n_bra n) x v);  T_i = Ai Z_i (batched);  P = T c~_ket^T (split K)
+    WFO_TRY(gemm(ctx, false, false, n_bra * n, v, v, 1.0, cb, v, Wb, v + 1, 0.0, Z, v, 0, 0, st));
+    WFO_TRY(gemm(ctx, false, false, n, v, n, 1.0, Ai, n, Z, v, 0.0, T, v, 0, (long long)nv, st, n_bra, 0, (long long)nv));
+    WFO_TRY(gemm(ctx, false, true, n_bra, n_ket, (int)nv, 1.0, T, (int)nv, ck, (int)nv, 0.0, P, n_ket, kslab,
+                 (long long)n_bra * n_ket, st));
+    if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev1, st));
+    rowdot_kernel<<<n_bra, 256, 0, st>>>(cb, (long long)nv, Xt, bx);
+    WFO_LAUNCH_CHECK(ctx);
+    rowdot_kernel<<<n_ket, 256, 0, st>>>(ck, (long long)nv, Y, ky);
+    WFO_LAUNCH_CHECK(ctx);
+    closed_finalize_kernel<<<cdiv(n_bra * n_ket, 128), 128, 0, st>>>(P, n_slabs, n_bra, n_ket, bx, ky, info, sigma, out);
+    WFO_LAUNCH_CHECK(ctx);
+    ctx->last_tier = WFO_TIER_CLOSED;
+    return WFO_OK;
+}
+
 /* ----------------------------------------------------------- stages 2 + 3 */
 // `arena_off`: bytes at the start of the context arena owned by the caller (host wrappers)
 static int state_overlaps_impl(wfo_ctx *ctx, size_t arena_off, const double *s_mo, int n_mo, int n,
@@ -526,6 +623,9 @@ static int state_overlaps_impl(wfo_ctx *ctx, size_t arena_off, const double *s_m
         ctx->last_tier = want_t1 ? WFO_TIER_UPDATE : WFO_TIER_LU;
         return WFO_OK;
     }
+    if (tier == WFO_TIER_CLOSED)
+        return closed_form_impl(ctx, arena_off, s_mo, n_mo, n, bra_exc, kb, Cb, n_bra, ket_exc, kk, Ck, n_ket, sigma,
+                                k_begin, k_end, out, st);
     const Part q = make_part(ctx, ksh, kk, n_ket, may_t0, want_t1);
     const int ldg = q.ldg, ktiles = q.ktiles, t1_splits = q.t1_splits, lps = q.lps, t0_chunks = q.t0_chunks,
               chunk_len = q.chunk_len, kslab = q.kslab, n_slabs = q.n_slabs;
@@ -700,6 +800,7 @@ static int host_front(wfo_ctx *ctx, const double *s_mo_host, const double *bra_m
             s2.off = front;
             carve(s2, p, n, v, ksh, kk, n_bra, q.ldg, q.n_parts, q.n_slabs, may_t0, want_t1);
             total = s2.off;
+            if (tier == WFO_TIER_CLOSED) total = front + closed_form_bytes(n, v, n_bra, n_ket);
         }
         WFO_TRY(ensure_scratch(ctx, total));
     }
@@ -855,6 +956,7 @@ int wfo_overlaps_ci_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_
             Sizer s2;
             s2.off = total;
             carve(s2, p, n, v, ksh, kk, n_bra, q.ldg, q.n_parts, q.n_slabs, may_t0, want_t1);
+            if (tier == WFO_TIER_CLOSED) s2.off = total + closed_form_bytes(n, v, n_bra, n_ket);
             total = s2.off;
         }
     }

@@ -11,7 +11,7 @@
 // block barrier per K tile.  Padded shared tiles make both fragment loads conflict-free
 // (A: stride 20 doubles, B: stride 72 doubles).  blockIdx.z selects a K slab (split-K): slab z
 // covers k in [z*kslab, min(k,(z+1)*kslab)) and writes C + z*slab_stride; deterministic,
-// summed by a later kernel in fixed order.
+// summed by a later kernel in fixed order.  With batch strides blockIdx.z is a batch index.
 #pragma once
 #include "common.cuh"
 
@@ -36,7 +36,7 @@ template <bool TA, bool TB, int GM>
 __global__ void __launch_bounds__(128)
 gemm_f64_kernel(int m, int n, int k, double alpha, const double *__restrict__ A, int lda,
                 const double *__restrict__ B, int ldb, double beta, double *__restrict__ C, int ldc,
-                int kslab, long long slab_stride) {
+                int kslab, long long slab_stride, long long batch_a, long long batch_b) {
     extern __shared__ __align__(16) double gsm[];
     constexpr int STAGE = GM * GLDA + GK * GLDB;   // doubles per stage
 
@@ -47,8 +47,12 @@ gemm_f64_kernel(int m, int n, int k, double alpha, const double *__restrict__ A,
     constexpr int EA = GM * GK / 128;         // A elements per thread and k tile
     const int wm = (warp >> 1) * (GM / 2), wn = (warp & 1) * 32;
     const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
-    const int kbeg = blockIdx.z * kslab;
+    // blockIdx.z is either a K slab (batch strides 0) or a batch index (kslab >= k, batch strides set)
+    const bool batched = (batch_a | batch_b) != 0;
+    const int kbeg = batched ? 0 : blockIdx.z * kslab;
     const int kend = min(k, kbeg + kslab);
+    A += (long long)blockIdx.z * batch_a;
+    B += (long long)blockIdx.z * batch_b;
     C += (long long)blockIdx.z * slab_stride;
 
     double acc[MT][4][2];

@@ -130,6 +130,51 @@ __global__ void finalize_kernel(const double *__restrict__ P, int n_slabs, int n
     out[idx] = (*d00) * a + sigma * u * wj;
 }
 
+// ---- closed-form tier (T2) helpers ---------------------------------------------------------
+// dense signed CI tensor: dense[s][f][t] += coeff[s][k] * (-1)^(n-1-f) for k in [k0, k1)
+// (duplicate excitations, as pywfo.dets.get_dets produces them, add up).  flag is set when a
+// ground-state entry (f < 0) is met: the closed form takes excitations only.
+__global__ void scatter_signed_ci_kernel(const int32_t *__restrict__ exc, const double *__restrict__ coeff,
+                                         int n_states, int K, int k0, int k1, int n, int v,
+                                         double *__restrict__ dense, int *__restrict__ flag) {
+    const int k = k0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y;
+    if (k >= k1) return;
+    const int f = exc[2 * k], t = exc[2 * k + 1];
+    if (f < 0) { *flag = 1; return; }
+    const double c = coeff[(size_t)s * K + k];
+    if (c != 0.0) atomicAdd(dense + ((size_t)s * n + f) * v + t, c * app_sign(f, n));
+}
+
+// out[r] = sum_i M[r][i] * vec[i]   (one CTA per row, fixed-shape tree)
+__global__ void __launch_bounds__(256)
+rowdot_kernel(const double *__restrict__ M, long long len, const double *__restrict__ vec, double *__restrict__ out) {
+    __shared__ double red[256];
+    const double *row = M + (size_t)blockIdx.x * len;
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < len; i += 256) s += row[i] * vec[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = red[0];
+}
+
+// out[i][j] = det^2 * ( (1+sigma) bx[i] ky[j] + sum_z P[z][i][j] )
+__global__ void closed_finalize_kernel(const double *__restrict__ P, int n_slabs, int n_bra, int n_ket,
+                                       const double *__restrict__ bx, const double *__restrict__ ky,
+                                       const BaseInfo *__restrict__ info, double sigma, double *__restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_bra * n_ket) return;
+    const int i = idx / n_ket, j = idx - i * n_ket;
+    double a = 0.0;
+    for (int z = 0; z < n_slabs; z++) a += P[(size_t)z * n_bra * n_ket + idx];
+    const double d = info->det;
+    out[idx] = d * d * ((1.0 + sigma) * bx[i] * ky[j] + a);
+}
+
 // ---- FP64 peak microbenchmarks (roofline denominators, bench.py) -------------
 __global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double *out) {
     double a[16];

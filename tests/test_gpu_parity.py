@@ -100,7 +100,7 @@ def test_precompute_matches_reference_semantics(ctx):
 
 
 # ---------------------------------------------------------------- whole path, goldens
-@pytest.mark.parametrize("tier", ["auto", "lu", "update"])
+@pytest.mark.parametrize("tier", ["auto", "lu", "update", "closed"])
 def test_golden_pins(ctx, tier):
     from pywfo_b200 import main
     g = load_golden("simple")
@@ -117,7 +117,7 @@ def test_golden_pins(ctx, tier):
                   g["ref_overlaps"])
 
 
-@pytest.mark.parametrize("tier", ["auto", "lu", "update"])
+@pytest.mark.parametrize("tier", ["auto", "lu", "update", "closed"])
 def test_h2o2(ctx, tier):
     """pywfo/tests/test_pywfo.py:128-156 and the 4x4 variants, reference self-output."""
     from pywfo_b200 import dets, main
@@ -134,7 +134,7 @@ def test_h2o2(ctx, tier):
 
 
 @pytest.mark.parametrize("name", RANDOM_CASES)
-@pytest.mark.parametrize("tier", ["lu", "update"])
+@pytest.mark.parametrize("tier", ["lu", "update", "closed"])
 def test_random_goldens(ctx, name, tier):
     from pywfo_b200 import dets, main
     g = load_golden(name)
@@ -194,6 +194,29 @@ def test_kernel_form_tiers_agree_with_oracle(ctx, occ, n_mo, kb, kk, sigma):
         got = ctx.state_overlaps_host(S, occ, bra, Cb, ket, Ck, sigma=sigma, tier=tier)
         assert ctx.last_tier() == code
         assert_parity(got, want, rtol=1e-9)
+
+
+def test_closed_form_tier(ctx):
+    """T2: GEMM-only closed form == brute force; refuses ground-state entries; shards add up."""
+    from pywfo_b200._lib import WfoError
+    rng = np.random.default_rng(21)
+    occ, n_mo = 17, 50
+    np.random.seed(21)
+    _, bra_mos, ket_mos = orc.bra_ket_dummy_mos(n_mo, occ)
+    S = orc.mo_overlap(bra_mos, ket_mos, orc.get_S_AO(bra_mos, ket_mos, "ket"))
+    bra, Cb, ket, Ck = _random_tables(rng, occ, n_mo - occ, 60, 45, 3, 5)
+    bra[7] = bra[3]                                  # a duplicate excitation (dets.get_dets produces them)
+    for sigma in (1.0, -1.0):
+        want = orc.state_overlaps_bruteforce(S, occ, [tuple(e) for e in bra], Cb, [tuple(e) for e in ket], Ck, sigma)
+        got = ctx.state_overlaps_host(S, occ, bra, Cb, ket, Ck, sigma=sigma, tier="closed")
+        assert ctx.last_tier() == 2
+        assert_parity(got, want, rtol=1e-9)
+        parts = sum(ctx.state_overlaps_host(S, occ, bra, Cb, ket, Ck, sigma=sigma, tier="closed", k_begin=lo, k_end=hi)
+                    for lo, hi in ((0, 13), (13, 60)))
+        np.testing.assert_allclose(parts, got, rtol=1e-12, atol=1e-14 * np.abs(got).max())
+    bra[0] = (-1, -1)
+    with pytest.raises(WfoError, match="ground-state"):
+        ctx.state_overlaps_host(S, occ, bra, Cb, ket, Ck, tier="closed")
 
 
 def test_shards_add_up_on_gpu(ctx):
@@ -319,6 +342,10 @@ def test_config_large_full_space_properties(ctx):
     got2 = main.overlaps_cache(bra_mos, ket_mos, b2, kci, occ, ci_thresh=0.0, tier="update")
     np.testing.assert_allclose(got2[0], 0.25 * got[1] - 1.5 * got[2], rtol=1e-9, atol=1e-12 * np.abs(got).max())
     np.testing.assert_allclose(got2[1:], got[1:], rtol=1e-13, atol=0)
+    # the closed-form tier on the full problem
+    got_c = main.overlaps_cache(bra_mos, ket_mos, bci, kci, occ, ci_thresh=0.0, tier="closed")
+    assert_parity(got_c, want, rtol=1e-9)
+    assert_parity(got_c, got, rtol=1e-9)
 
 
 def test_config_large_lu_sample(ctx):
