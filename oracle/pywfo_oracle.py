@@ -370,3 +370,12 @@ def signed_ci(ci, occ):
     """c~[s, f, t] = c[s, f, t] * (-1)**(occ-1-f): appended-order signs folded in."""
     s = (-1.0) ** (occ - 1 - np.arange(occ))
     return ci * s[None, :, None]
+
+
+def ref_overlap_from_determinants(S_MO, bra_alpha, bra_beta, bra_coeffs, ket_alpha, ket_beta, ket_coeffs):
+    """General determinant lists: ``wfo = Bc^T (det_alpha * det_beta) Kc`` with every block
+    determinant from LAPACK (pywfo/dets.py:191-198 and :279-283; coefficients already carry
+    the string parity of dets.py:42-96)."""
+    da = det_from_lists(S_MO, bra_alpha, ket_alpha)
+    db = det_from_lists(S_MO, bra_beta, ket_beta)
+    return np.asarray(bra_coeffs).T @ (da * db) @ np.asarray(ket_coeffs)
