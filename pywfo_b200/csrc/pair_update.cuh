@@ -18,8 +18,9 @@
 //
 // CTA = 4 warps, 96 bra excitations (3 m-tiles of 8 per warp, 168 registers, 3 CTAs/SM);
 // persistent CTAs fetch (k tile, l split) work items from an atomic counter; the ket
-// coefficient tiles (32 excitations x ldg) are staged in shared memory with
-// cp.async double buffering and shared by the 4 warps.  Ai and W are gathered
+// coefficient tiles (32 excitations x ldg, one contiguous block of CkTs) are staged in shared
+// memory by TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP), double buffered, and
+// shared by the 4 warps.  Ai and W are gathered
 // through L1 (the host orders the ket excitations so that a CTA's working set
 // of W is a few KB at a time, see pywfo_b200/excitations.py).
 #pragma once
@@ -55,13 +56,33 @@ struct BraMeta {   // one per bra excitation (16 bytes)
     double x;      // X[t, f]
 };
 
-__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
-    unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src));
+// ---- TMA (bulk async copy) + mbarrier helpers: one elected thread moves a whole ket tile
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WFO_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WFO_DONE_%=;\n"
+        "bra WFO_WAIT_%=;\n"
+        "WFO_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
 
 // NT = ldg / 8 column tiles of G.  Work item = (k tile, l split), fetched dynamically.
 // gpart[(split*ksh + k)*ldg + j]
@@ -73,12 +94,20 @@ t1_fused_kernel(const double *__restrict__ Ai, const double *__restrict__ W,
                 int l_per_split, int n_ktiles, int n_items, int *__restrict__ counter,
                 double *__restrict__ gpart) {
     constexpr int LDG = NT * 8;
-    __shared__ __align__(16) double Bs[2][T1_LT * LDG];
+    __shared__ __align__(128) double Bs[2][T1_LT * LDG];
     __shared__ __align__(16) KetMeta Ms[2][T1_LT];
+    __shared__ __align__(8) unsigned long long full_bar[2];   // "tile landed" barriers of the two stages
     __shared__ int s_item;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
+    if (tid == 0) {
+        mbar_init(&full_bar[0], 1);
+        mbar_init(&full_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    unsigned phase0 = 0, phase1 = 0;   // parity of the next completion of each stage barrier
+    __syncthreads();
   for (;;) {
     if (tid == 0) s_item = atomicAdd(counter, 1);
     __syncthreads();
@@ -109,31 +138,30 @@ t1_fused_kernel(const double *__restrict__ Ai, const double *__restrict__ W,
 #pragma unroll
         for (int ni = 0; ni < NT; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
-    // stage one tile of ket data: T1_LT rows of LDG doubles + T1_LT metas (16 B chunks)
+    // stage one tile of ket data with TMA: the coefficient rows of T1_LT consecutive ket
+    // excitations are one contiguous block of CkTs (T1_LT * LDG * 8 bytes), their metadata another;
+    // one thread issues two bulk copies that complete on the stage's mbarrier.  Rows beyond the
+    // end of the split are zero-filled by the other threads (different addresses).
     auto stage = [&](int buf, int l0) {
-        constexpr int CH_B = T1_LT * LDG / 2;   // 16-byte chunks of the coefficient tile
-        for (int c = tid; c < CH_B + T1_LT; c += T1_WARPS * 32) {
-            if (c < CH_B) {
-                int row = c / (LDG / 2);
-                double *dst = &Bs[buf][0] + 2 * c;
-                if (l0 + row < l_end) cp_async16(dst, ckts + (size_t)l0 * LDG + 2 * c);
-                else { dst[0] = 0.0; dst[1] = 0.0; }
-            } else {
-                int row = c - CH_B;
-                KetMeta *dst = &Ms[buf][row];
-                if (l0 + row < l_end) cp_async16(dst, ket + l0 + row);
-                else { dst->aoff = 0; dst->tp = 0; dst->y = 0.0; }
-            }
+        const int rows = min(T1_LT, l_end - l0);
+        if (tid == 0) {
+            mbar_expect_tx(&full_bar[buf], (unsigned)(rows * (LDG * 8 + 16)));
+            tma_bulk_g2s(&Bs[buf][0], ckts + (size_t)l0 * LDG, (unsigned)(rows * LDG * 8), &full_bar[buf]);
+            tma_bulk_g2s(&Ms[buf][0], ket + l0, (unsigned)(rows * 16), &full_bar[buf]);
         }
-        cp_async_commit();
+        if (rows < T1_LT) {
+            for (int c = rows * LDG + tid; c < T1_LT * LDG; c += T1_WARPS * 32) Bs[buf][c] = 0.0;
+            for (int r = rows + tid; r < T1_LT; r += T1_WARPS * 32) { Ms[buf][r].aoff = 0; Ms[buf][r].tp = 0; Ms[buf][r].y = 0.0; }
+        }
     };
 
     int buf = 0;
     if (l_begin < l_end) stage(0, l_begin);
     for (int l0 = l_begin; l0 < l_end; l0 += T1_LT) {
-        if (l0 + T1_LT < l_end) { stage(buf ^ 1, l0 + T1_LT); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
-        __syncthreads();
+        if (l0 + T1_LT < l_end) stage(buf ^ 1, l0 + T1_LT);
+        if (buf == 0) { mbar_wait(&full_bar[0], phase0); phase0 ^= 1; }
+        else { mbar_wait(&full_bar[1], phase1); phase1 ^= 1; }
+        __syncthreads();   // also publishes the zero fill of a partial tile
         const double *bs = &Bs[buf][0];
         const KetMeta *ms = &Ms[buf][0];
         // software pipeline over the 8 k-steps (4 ket excitations each): gather one step ahead
