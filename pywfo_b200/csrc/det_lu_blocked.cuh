@@ -372,8 +372,9 @@ __device__ __forceinline__ void gather_minor_ld(const double *__restrict__ S, in
 #ifndef WFO_T0_MINB64
 #define WFO_T0_MINB64 5
 #endif
-// minimum resident CTAs asked of the compiler: the 4-warp (n <= 64) configuration is register limited
-constexpr int blk_minb(int warps) { return warps == 4 ? WFO_T0_MINB64 : 1; }
+// minimum resident CTAs asked of the compiler (caps the registers): 2 x 8 warps at 128 registers for
+// n > 64 (shared memory allows two 86 KB matrices anyway), 5 x 4 warps for n <= 64
+constexpr int blk_minb(int warps) { return warps == 8 ? 2 : (warps == 4 ? WFO_T0_MINB64 : (warps == 2 ? 8 : 16)); }
 
 template <int WARPS, int SLOTS, bool GLOBAL>
 __global__ void __launch_bounds__(WARPS * 32, blk_minb(WARPS))
