@@ -432,8 +432,13 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU baseline work (0 = skip)")
     ap.add_argument("--no-check", dest="check", action="store_false")
     ap.add_argument("--no-t2", dest="t2", action="store_false", help="skip the closed-form tier timing")
+    ap.add_argument("--k-exc", type=int, default=None,
+                    help="c5 only: excitations per side (BASELINE sweep 32/100/316/1000 -> 1e3..1e6 pairs)")
     args = ap.parse_args()
-    w = WORKLOADS[args.workload]
+    w = dict(WORKLOADS[args.workload])
+    if args.k_exc is not None and args.workload == "c5":
+        w["K"] = args.k_exc
+        w["desc"] = f"n_occ=64 n_mo=320 8x8 states, {args.k_exc}x{args.k_exc} random excitations"
     if args.impl == "reference":
         return run_reference(args, w)
     return run_ours(args, w)

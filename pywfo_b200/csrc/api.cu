@@ -2,6 +2,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <new>
+#include <vector>
 
 #include "common.cuh"
 #include "det_lu_blocked.cuh"
@@ -182,7 +183,7 @@ static int det_table(wfo_ctx *ctx, const double *S, int ld_s, int n, const int32
     long long npairs = (long long)kb * kk;
     if (npairs <= 0) return WFO_OK;
     if (n < 1 || n > 128)
-        return set_err(WFO_ERR_ARG, "det_table: n_occ=%lld outside the supported range 1..128%s", "", n);
+        return set_err(WFO_ERR_ARG, "det_table: n_occ=%lld outside the supported range 1..128", n);
     unsigned grid = 1;
     if (use_v1()) {
         size_t smem = t0_smem_bytes(n);
@@ -290,12 +291,12 @@ static size_t base_smem_bytes(int n) { return n <= LUB_MAXN ? 0 : (size_t)1 << 4
 // which tiers can / should run for this call
 static int resolve_tier(const wfo_ctx *ctx, int n, int tier, bool *want_t1, bool *may_t0) {
     if (tier != WFO_TIER_AUTO && tier != WFO_TIER_LU && tier != WFO_TIER_UPDATE && tier != WFO_TIER_CLOSED)
-        return set_err(WFO_ERR_ARG, "state_overlaps: unknown tier %lld%s", "", tier);
+        return set_err(WFO_ERR_ARG, "state_overlaps: unknown tier %lld", tier);
     if (tier == WFO_TIER_CLOSED) {   // shares the base-block machinery (and its size limit) with UPDATE
         *want_t1 = true;
         *may_t0 = false;
         if (base_smem_bytes(n) > ctx->smem_optin)
-            return set_err(WFO_ERR_ARG, "state_overlaps: tier CLOSED supports n_occ <= 128, got %lld%s", "", n);
+            return set_err(WFO_ERR_ARG, "state_overlaps: tier CLOSED supports n_occ <= 128, got %lld", n);
         return WFO_OK;
     }
     *want_t1 = (tier == WFO_TIER_AUTO || tier == WFO_TIER_UPDATE);
@@ -303,14 +304,14 @@ static int resolve_tier(const wfo_ctx *ctx, int n, int tier, bool *want_t1, bool
     const bool t0_fits = n <= 128 && t0_smem_bytes(n) <= ctx->smem_optin;
     const bool t1_fits = base_smem_bytes(n) <= ctx->smem_optin;
     if (tier == WFO_TIER_LU && !t0_fits)
-        return set_err(WFO_ERR_ARG, "state_overlaps: tier LU supports n_occ <= 128, got %lld%s", "", n);
+        return set_err(WFO_ERR_ARG, "state_overlaps: tier LU supports n_occ <= 128, got %lld", n);
     if (tier == WFO_TIER_UPDATE && !t1_fits)
-        return set_err(WFO_ERR_ARG, "state_overlaps: tier UPDATE supports n_occ <= 128, got %lld%s", "", n);
+        return set_err(WFO_ERR_ARG, "state_overlaps: tier UPDATE supports n_occ <= 128, got %lld", n);
     if (tier == WFO_TIER_AUTO) {
         if (!t1_fits) *want_t1 = false;
         if (!t0_fits) *may_t0 = false;
         if (!*want_t1 && !*may_t0)
-            return set_err(WFO_ERR_ARG, "state_overlaps: n_occ=%lld too large for every tier%s", "", n);
+            return set_err(WFO_ERR_ARG, "state_overlaps: n_occ=%lld too large for every tier", n);
     }
     return WFO_OK;
 }
@@ -364,18 +365,18 @@ int wfo_device_count(void) {
 }
 
 int wfo_create(int device, wfo_ctx **out) {
-    if (!out) return set_err(WFO_ERR_ARG, "wfo_create: out is NULL%s");
+    if (!out) return set_err(WFO_ERR_ARG, "wfo_create: out is NULL");
     *out = nullptr;
     int ndev = 0;
     WFO_CUDA(cudaGetDeviceCount(&ndev));
-    if (device < 0 || device >= ndev) return set_err(WFO_ERR_ARG, "wfo_create: no CUDA device %lld%s", "", device);
+    if (device < 0 || device >= ndev) return set_err(WFO_ERR_ARG, "wfo_create: no CUDA device %lld", device);
     WFO_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     WFO_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10)
-        return set_err(WFO_ERR_ARG, "wfo_create: device is sm_%lld%lld, this library is sm_100a only", "", prop.major, prop.minor);
+        return set_err(WFO_ERR_ARG, "wfo_create: device is sm_%lld%lld, this library is sm_100a only", prop.major, prop.minor);
     wfo_ctx *c = new (std::nothrow) wfo_ctx();
-    if (!c) return set_err(WFO_ERR_ARG, "wfo_create: out of host memory%s");
+    if (!c) return set_err(WFO_ERR_ARG, "wfo_create: out of host memory");
     memset(c, 0, sizeof(*c));
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
@@ -404,7 +405,7 @@ int wfo_destroy(wfo_ctx *ctx) {
 long long wfo_launch_count(const wfo_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int wfo_last_tier(const wfo_ctx *ctx) { return ctx ? ctx->last_tier : -1; }
 int wfo_set_timing(wfo_ctx *ctx, int on) {
-    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL%s");
+    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL");
     ctx->timing = on;
     return WFO_OK;
 }
@@ -419,13 +420,13 @@ double wfo_last_kernel_ms(const wfo_ctx *ctx) {
 /* ---------------------------------------------------------------- stage 1 */
 int wfo_gemm_dev(wfo_ctx *ctx, int ta, int tb, int m, int n, int k, double alpha, const double *A, int lda,
                  const double *B, int ldb, double beta, double *C, int ldc, void *stream) {
-    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL%s");
+    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL");
     WFO_CUDA(cudaSetDevice(ctx->device));
     return gemm(ctx, ta != 0, tb != 0, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, 0, 0, (cudaStream_t)stream);
 }
 
 int wfo_sao_dev(wfo_ctx *ctx, const double *c_inv, int n, double *s_ao, void *stream) {
-    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL%s");
+    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL");
     WFO_CUDA(cudaSetDevice(ctx->device));
     // S_AO = Cinv Cinv^T  (pywfo/main.py:304)
     return gemm(ctx, false, true, n, n, n, 1.0, c_inv, n, c_inv, n, 0.0, s_ao, n, 0, 0, (cudaStream_t)stream);
@@ -433,7 +434,7 @@ int wfo_sao_dev(wfo_ctx *ctx, const double *c_inv, int n, double *s_ao, void *st
 
 int wfo_smo_dev(wfo_ctx *ctx, const double *bra_mos, const double *s_ao, const double *ket_mos, int p, int u,
                 int v, int q, double *s_mo, double *work, void *stream) {
-    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL%s");
+    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL");
     WFO_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     if (!work) {
@@ -448,7 +449,7 @@ int wfo_smo_dev(wfo_ctx *ctx, const double *bra_mos, const double *s_ao, const d
 
 int wfo_smo_host(wfo_ctx *ctx, const double *bra_mos, const double *s_ao, const double *ket_mos, int p, int u,
                  int v, int q, double *s_mo) {
-    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL%s");
+    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL");
     WFO_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     size_t nb = (size_t)p * u, ns = (size_t)u * v, nk = (size_t)q * v, nw = (size_t)p * v, no = (size_t)p * q;
@@ -469,7 +470,7 @@ int wfo_smo_host(wfo_ctx *ctx, const double *bra_mos, const double *s_ao, const 
 
 /* ---------------------------------------------------------------- stage 2 */
 int wfo_exc_lists_dev(wfo_ctx *ctx, const int32_t *exc, int k, int n_occ, int32_t *lists, void *stream) {
-    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL%s");
+    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL");
     if (k <= 0) return WFO_OK;
     WFO_CUDA(cudaSetDevice(ctx->device));
     long long tot = (long long)k * n_occ;
@@ -480,8 +481,8 @@ int wfo_exc_lists_dev(wfo_ctx *ctx, const int32_t *exc, int k, int n_occ, int32_
 
 int wfo_det_table_dev(wfo_ctx *ctx, const double *s_mo, int n_mo, int ld_smo, int n, const int32_t *rows,
                       int kb, const int32_t *cols, int kk, double *D, void *stream) {
-    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL%s");
-    if (n > n_mo) return set_err(WFO_ERR_ARG, "det_table: n=%lld > n_mo=%lld%s", "", n, n_mo);
+    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL");
+    if (n > n_mo) return set_err(WFO_ERR_ARG, "det_table: n=%lld > n_mo=%lld", n, n_mo);
     WFO_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev0, st));
@@ -492,7 +493,7 @@ int wfo_det_table_dev(wfo_ctx *ctx, const double *s_mo, int n_mo, int ld_smo, in
 
 int wfo_det_table_host(wfo_ctx *ctx, const double *s_mo, int n_mo, int n, const int32_t *rows, int kb,
                        const int32_t *cols, int kk, double *D) {
-    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL%s");
+    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL");
     if (kb <= 0 || kk <= 0) return WFO_OK;
     WFO_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -529,7 +530,7 @@ static size_t closed_form_bytes(int n, int v, int n_bra, int n_ket) {
 static int closed_form_impl(wfo_ctx *ctx, size_t arena_off, const double *s_mo, int n_mo, int n,
                             const int32_t *bra_exc, int kb, const double *Cb, int n_bra, const int32_t *ket_exc,
                             int kk, const double *Ck, int n_ket, double sigma, int k_begin, int k_end, double *out,
-                            cudaStream_t st) {
+                            int ld_out, cudaStream_t st) {
     const int v = n_mo - n;
     const size_t nv = (size_t)n * v;
     const int kslab = 1024, n_slabs = cdiv((int)nv, kslab);
@@ -573,10 +574,10 @@ static int closed_form_impl(wfo_ctx *ctx, size_t arena_off, const double *s_mo, 
     WFO_CUDA(cudaMemcpyAsync(&h.info, info, sizeof(BaseInfo), cudaMemcpyDeviceToHost, st));
     WFO_CUDA(cudaMemcpyAsync(&h.flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     WFO_CUDA(cudaStreamSynchronize(st));
-    if (h.flag) return set_err(WFO_ERR_ARG, "state_overlaps: tier CLOSED takes excitation tables without ground-state entries%s");
+    if (h.flag) return set_err(WFO_ERR_ARG, "state_overlaps: tier CLOSED takes excitation tables without ground-state entries");
     if (h.info.singular || !(h.info.min_piv > 1e-6 * h.info.max_piv))
         return set_err(WFO_ERR_SINGULAR, "state_overlaps: base block S_MO[:occ,:occ] is (numerically) singular, "
-                                         "tier CLOSED not applicable%s");
+                                         "tier CLOSED not applicable");
     const double *Bblk = s_mo + n;                    // occ  x virt
     const double *Cblk = s_mo + (size_t)n * n_mo;     // virt x occ
     // Xt = (C Ai)^T = Ai^T C^T (n x v), Y = Ai B (n x v), W = Dv - C Y (v x v, ld v+1)
@@ -597,7 +598,8 @@ static int closed_form_impl(wfo_ctx *ctx, size_t arena_off, const double *s_mo, 
     WFO_LAUNCH_CHECK(ctx);
     rowdot_kernel<<<n_ket, 256, 0, st>>>(ck, (long long)nv, Y, ky);
     WFO_LAUNCH_CHECK(ctx);
-    closed_finalize_kernel<<<cdiv(n_bra * n_ket, 128), 128, 0, st>>>(P, n_slabs, n_bra, n_ket, bx, ky, info, sigma, out);
+    closed_finalize_kernel<<<cdiv(n_bra * n_ket, 128), 128, 0, st>>>(P, n_slabs, n_bra, n_ket, bx, ky, info, sigma, out,
+                                                                     ld_out);
     WFO_LAUNCH_CHECK(ctx);
     ctx->last_tier = WFO_TIER_CLOSED;
     return WFO_OK;
@@ -605,27 +607,29 @@ static int closed_form_impl(wfo_ctx *ctx, size_t arena_off, const double *s_mo, 
 
 /* ----------------------------------------------------------- stages 2 + 3 */
 // `arena_off`: bytes at the start of the context arena owned by the caller (host wrappers)
-static int state_overlaps_impl(wfo_ctx *ctx, size_t arena_off, const double *s_mo, int n_mo, int n,
-                               const int32_t *bra_exc, int kb, const double *Cb, int n_bra,
-                               const int32_t *ket_exc, int kk, const double *Ck, int n_ket, double sigma,
-                               int tier, int k_begin, int k_end, double *out, cudaStream_t st) {
-    if (n < 1 || n > n_mo) return set_err(WFO_ERR_ARG, "state_overlaps: n_occ=%lld must be in 1..n_mo=%lld%s", "", n, n_mo);
-    if (n_bra < 1 || n_ket < 1) return set_err(WFO_ERR_ARG, "state_overlaps: need at least one bra and one ket state%s");
-    if (n_ket > 62) return set_err(WFO_ERR_ARG, "state_overlaps: n_ket=%lld > 62 not supported yet%s", "", n_ket);
+constexpr int MAX_KET_BLOCK = 55;   // ket states per pass of the fused kernels: 55 + the D(k,0) column = 7 tiles of 8
+
+// one block of at most MAX_KET_BLOCK ket states (any number for the closed form); out has row stride ld_out
+static int state_overlaps_block(wfo_ctx *ctx, size_t arena_off, const double *s_mo, int n_mo, int n,
+                                const int32_t *bra_exc, int kb, const double *Cb, int n_bra,
+                                const int32_t *ket_exc, int kk, const double *Ck, int n_ket, double sigma,
+                                int tier, int k_begin, int k_end, double *out, int ld_out, cudaStream_t st) {
+    if (n < 1 || n > n_mo) return set_err(WFO_ERR_ARG, "state_overlaps: n_occ=%lld must be in 1..n_mo=%lld", n, n_mo);
+    if (n_bra < 1 || n_ket < 1) return set_err(WFO_ERR_ARG, "state_overlaps: need at least one bra and one ket state");
     if (k_begin < 0 || k_end > kb || k_begin > k_end)
-        return set_err(WFO_ERR_ARG, "state_overlaps: bad shard [%lld,%lld)%s", "", k_begin, k_end);
+        return set_err(WFO_ERR_ARG, "state_overlaps: bad shard [%lld,%lld)", k_begin, k_end);
     bool want_t1 = false, may_t0 = false;
     WFO_TRY(resolve_tier(ctx, n, tier, &want_t1, &may_t0));
     const int v = n_mo - n;
     const int ksh = k_end - k_begin;
     if (ksh == 0 || kk == 0) {   // empty shard / no ket determinants: the partial sum is zero
-        WFO_CUDA(cudaMemsetAsync(out, 0, (size_t)n_bra * n_ket * sizeof(double), st));
+        WFO_CUDA(cudaMemset2DAsync(out, (size_t)ld_out * sizeof(double), 0, (size_t)n_ket * sizeof(double), n_bra, st));
         ctx->last_tier = want_t1 ? WFO_TIER_UPDATE : WFO_TIER_LU;
         return WFO_OK;
     }
     if (tier == WFO_TIER_CLOSED)
         return closed_form_impl(ctx, arena_off, s_mo, n_mo, n, bra_exc, kb, Cb, n_bra, ket_exc, kk, Ck, n_ket, sigma,
-                                k_begin, k_end, out, st);
+                                k_begin, k_end, out, ld_out, st);
     const Part q = make_part(ctx, ksh, kk, n_ket, may_t0, want_t1);
     const int ldg = q.ldg, ktiles = q.ktiles, t1_splits = q.t1_splits, lps = q.lps, t0_chunks = q.t0_chunks,
               chunk_len = q.chunk_len, kslab = q.kslab, n_slabs = q.n_slabs;
@@ -677,7 +681,7 @@ static int state_overlaps_impl(wfo_ctx *ctx, size_t arena_off, const double *s_m
 #define T1_CASE(NT_) case NT_: WFO_TRY(launch_t1<NT_>(ctx, ktiles, t1_splits, st, p.Ai, p.Wb, p.bmeta, p.bscale, ksh, p.kmeta, p.ckt, kk, lps, counter, p.gpart)); break;
                 T1_CASE(1) T1_CASE(3) T1_CASE(5) T1_CASE(7)
 #undef T1_CASE
-                default: return set_err(WFO_ERR_ARG, "state_overlaps: unsupported ldg %lld%s", "", ldg);
+                default: return set_err(WFO_ERR_ARG, "state_overlaps: unsupported ldg %lld", ldg);
             }
             WFO_LAUNCH_CHECK(ctx);
             if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev1, st));
@@ -687,12 +691,12 @@ static int state_overlaps_impl(wfo_ctx *ctx, size_t arena_off, const double *s_m
         } else if (!may_t0) {
             return set_err(WFO_ERR_SINGULAR,
                            "state_overlaps: base block S_MO[:occ,:occ] is (numerically) singular, "
-                           "tier UPDATE not applicable%s");
+                           "tier UPDATE not applicable");
         }
     }
     if (used < 0) {
         if (!may_t0)
-            return set_err(WFO_ERR_SINGULAR, "state_overlaps: base block singular and n_occ too large for tier LU%s");
+            return set_err(WFO_ERR_SINGULAR, "state_overlaps: base block singular and n_occ too large for tier LU");
         // ---- brute force: ground-state row/column/corner first, then the fused pair kernel
         iota_kernel<<<cdiv(n, 128), 128, 0, st>>>(p.gs_list, n);
         WFO_LAUNCH_CHECK(ctx);
@@ -755,16 +759,34 @@ static int state_overlaps_impl(wfo_ctx *ctx, size_t arena_off, const double *s_m
                  (long long)n_bra * ldg, st));
     ket_gs_dot_kernel<<<dim3(n_ket, KGS_SLABS), 256, 0, st>>>(Ck, kk, n_ket, p.d0l, p.w);
     WFO_LAUNCH_CHECK(ctx);
-    finalize_kernel<<<cdiv(n_bra * n_ket, 128), 128, 0, st>>>(p.P, n_slabs, n_bra, ldg, n_ket, p.w, d00_ptr, sigma, out);
+    finalize_kernel<<<cdiv(n_bra * n_ket, 128), 128, 0, st>>>(p.P, n_slabs, n_bra, ldg, n_ket, p.w, d00_ptr, sigma, out,
+                                                              ld_out);
     WFO_LAUNCH_CHECK(ctx);
     ctx->last_tier = used;
+    return WFO_OK;
+}
+
+// any number of ket states: the fused tiers run in passes of MAX_KET_BLOCK states (the bra side and
+// the determinants are the same in every pass; only the ket coefficient columns change)
+static int state_overlaps_impl(wfo_ctx *ctx, size_t arena_off, const double *s_mo, int n_mo, int n,
+                               const int32_t *bra_exc, int kb, const double *Cb, int n_bra,
+                               const int32_t *ket_exc, int kk, const double *Ck, int n_ket, double sigma,
+                               int tier, int k_begin, int k_end, double *out, cudaStream_t st) {
+    if (tier == WFO_TIER_CLOSED || n_ket <= MAX_KET_BLOCK)
+        return state_overlaps_block(ctx, arena_off, s_mo, n_mo, n, bra_exc, kb, Cb, n_bra, ket_exc, kk, Ck, n_ket,
+                                    sigma, tier, k_begin, k_end, out, n_ket, st);
+    for (int j0 = 0; j0 < n_ket; j0 += MAX_KET_BLOCK) {
+        const int nb = n_ket - j0 < MAX_KET_BLOCK ? n_ket - j0 : MAX_KET_BLOCK;
+        WFO_TRY(state_overlaps_block(ctx, arena_off, s_mo, n_mo, n, bra_exc, kb, Cb, n_bra, ket_exc, kk,
+                                     Ck + (size_t)j0 * kk, nb, sigma, tier, k_begin, k_end, out + j0, n_ket, st));
+    }
     return WFO_OK;
 }
 
 int wfo_state_overlaps_dev(wfo_ctx *ctx, const double *s_mo, int n_mo, int n_occ, const int32_t *bra_exc, int kb,
                            const double *Cb, int n_bra, const int32_t *ket_exc, int kk, const double *Ck,
                            int n_ket, double sigma, int tier, int k_begin, int k_end, double *out, void *stream) {
-    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL%s");
+    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL");
     WFO_CUDA(cudaSetDevice(ctx->device));
     return state_overlaps_impl(ctx, 0, s_mo, n_mo, n_occ, bra_exc, kb, Cb, n_bra, ket_exc, kk, Ck, n_ket, sigma,
                                tier, k_begin, k_end, out, (cudaStream_t)stream);
@@ -775,9 +797,9 @@ static int host_front(wfo_ctx *ctx, const double *s_mo_host, const double *bra_m
                       const double *c_inv, int n_mo, int n, const int32_t *bra_exc, int kb, const double *Cb,
                       int n_bra, const int32_t *ket_exc, int kk, const double *Ck, int n_ket, double sigma,
                       int tier, int k_begin, int k_end, double *out) {
-    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL%s");
+    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL");
     if (kb < 0 || kk < 0 || n_bra < 1 || n_ket < 1 || n_mo < 1)
-        return set_err(WFO_ERR_ARG, "state_overlaps: negative or empty sizes%s");
+        return set_err(WFO_ERR_ARG, "state_overlaps: negative or empty sizes");
     WFO_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     size_t nsq = (size_t)n_mo * n_mo;
@@ -794,7 +816,7 @@ static int host_front(wfo_ctx *ctx, const double *s_mo_host, const double *bra_m
         bool want_t1 = false, may_t0 = false;
         if (n >= 1 && n <= n_mo && ksh > 0 && kk > 0 && k_begin >= 0 && k_end <= kb &&
             resolve_tier(ctx, n, tier, &want_t1, &may_t0) == WFO_OK) {
-            Part q = make_part(ctx, ksh, kk, n_ket, may_t0, want_t1);
+            Part q = make_part(ctx, ksh, kk, n_ket < MAX_KET_BLOCK ? n_ket : MAX_KET_BLOCK, may_t0, want_t1);
             Plan p;
             Sizer s2;
             s2.off = front;
@@ -831,7 +853,7 @@ static int host_front(wfo_ctx *ctx, const double *s_mo_host, const double *bra_m
     char *before = ctx->scratch;
     WFO_TRY(state_overlaps_impl(ctx, ar.off, d_smo, n_mo, n, d_be, kb, d_cb, n_bra, d_ke, kk, d_ck, n_ket, sigma,
                                 tier, k_begin, k_end, d_out, st));
-    if (ctx->scratch != before) return set_err(WFO_ERR_CUDA, "internal: arena moved during a host call%s");
+    if (ctx->scratch != before) return set_err(WFO_ERR_CUDA, "internal: arena moved during a host call");
     WFO_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n_bra * n_ket * 8, cudaMemcpyDeviceToHost, st));
     WFO_CUDA(cudaStreamSynchronize(st));
     return WFO_OK;
@@ -840,7 +862,7 @@ static int host_front(wfo_ctx *ctx, const double *s_mo_host, const double *bra_m
 int wfo_state_overlaps_host(wfo_ctx *ctx, const double *s_mo, int n_mo, int n_occ, const int32_t *bra_exc, int kb,
                             const double *Cb, int n_bra, const int32_t *ket_exc, int kk, const double *Ck,
                             int n_ket, double sigma, int tier, int k_begin, int k_end, double *out) {
-    if (!s_mo) return set_err(WFO_ERR_ARG, "state_overlaps_host: s_mo is NULL%s");
+    if (!s_mo) return set_err(WFO_ERR_ARG, "state_overlaps_host: s_mo is NULL");
     return host_front(ctx, s_mo, nullptr, nullptr, nullptr, n_mo, n_occ, bra_exc, kb, Cb, n_bra, ket_exc, kk, Ck,
                       n_ket, sigma, tier, k_begin, k_end, out);
 }
@@ -849,7 +871,7 @@ int wfo_overlaps_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos
                       int n_occ, const int32_t *bra_exc, int kb, const double *Cb, int n_bra,
                       const int32_t *ket_exc, int kk, const double *Ck, int n_ket, double sigma, int tier,
                       int k_begin, int k_end, double *out) {
-    if (!bra_mos || !ket_mos || !c_inv) return set_err(WFO_ERR_ARG, "overlaps_host: NULL MO pointer%s");
+    if (!bra_mos || !ket_mos || !c_inv) return set_err(WFO_ERR_ARG, "overlaps_host: NULL MO pointer");
     return host_front(ctx, nullptr, bra_mos, ket_mos, c_inv, n_mo, n_occ, bra_exc, kb, Cb, n_bra, ket_exc, kk, Ck,
                       n_ket, sigma, tier, k_begin, k_end, out);
 }
@@ -880,12 +902,12 @@ int wfo_overlaps_ci_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_
                          int n_occ, const double *bra_ci, int n_bra, const double *ket_ci, int n_ket,
                          double ci_thresh, int semantics, int tier, int rank, int world, double *out,
                          int32_t *info) {
-    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL%s");
+    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL");
     if (!bra_mos || !ket_mos || !c_inv || !bra_ci || !ket_ci || !out)
-        return set_err(WFO_ERR_ARG, "overlaps_ci_host: NULL pointer%s");
+        return set_err(WFO_ERR_ARG, "overlaps_ci_host: NULL pointer");
     if (n_mo < 1 || n_occ < 1 || n_occ > n_mo || n_bra < 1 || n_ket < 1 || world < 1 || rank < 0 || rank >= world)
-        return set_err(WFO_ERR_ARG, "overlaps_ci_host: bad sizes%s");
-    if (semantics != 0 && semantics != 1) return set_err(WFO_ERR_ARG, "overlaps_ci_host: semantics must be 0 or 1%s");
+        return set_err(WFO_ERR_ARG, "overlaps_ci_host: bad sizes");
+    if (semantics != 0 && semantics != 1) return set_err(WFO_ERR_ARG, "overlaps_ci_host: semantics must be 0 or 1");
     WFO_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int n = n_occ, v = n_mo - n_occ, count = n * v;
@@ -925,8 +947,8 @@ int wfo_overlaps_ci_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_
     WFO_TRY(wfo_sao_dev(ctx, d_inv, n_mo, d_sao, st));
     WFO_TRY(wfo_smo_dev(ctx, d_bra, d_sao, d_ket, n_mo, n_mo, n_mo, n_mo, d_smo, d_work, st));
     // ---- the table sizes (and per-state counts) come back: 2 small copies, one sync
-    int hb[1 + 64], hk[1 + 64];
-    if (n_bra > 64 || n_ket > 64) return set_err(WFO_ERR_ARG, "overlaps_ci_host: more than 64 states not supported%s");
+    std::vector<int> hb_v(1 + n_bra), hk_v(1 + n_ket);
+    int *hb = hb_v.data(), *hk = hk_v.data();
     WFO_CUDA(cudaMemcpyAsync(hb, tot_b, (1 + n_bra) * sizeof(int), cudaMemcpyDeviceToHost, st));
     WFO_CUDA(cudaMemcpyAsync(hk, tot_k, (1 + n_ket) * sizeof(int), cudaMemcpyDeviceToHost, st));
     WFO_CUDA(cudaStreamSynchronize(st));
@@ -935,7 +957,7 @@ int wfo_overlaps_ci_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_
     if (semantics == 1) {   // pywfo/main.py:186: a state without excitations cannot be unpacked
         for (int i = 0; i < n_bra; i++) if (hb[1 + i] == 0) { if (info) info[2] = 1; }
         for (int i = 0; i < n_ket; i++) if (hk[1 + i] == 0) { if (info) info[2] = 1; }
-        if (info && info[2]) return set_err(WFO_ERR_EMPTY_STATE, "overlaps: a state keeps no excitation above the threshold%s");
+        if (info && info[2]) return set_err(WFO_ERR_EMPTY_STATE, "overlaps: a state keeps no excitation above the threshold");
     }
     if (kb == 0 || kk == 0) {
         memset(out, 0, (size_t)n_bra * n_ket * sizeof(double));
@@ -951,7 +973,7 @@ int wfo_overlaps_ci_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_
         WFO_TRY(resolve_tier(ctx, n, tier, &want_t1, &may_t0));
         const int ksh = k_end - k_begin;
         if (ksh > 0) {
-            Part q = make_part(ctx, ksh, kk, n_ket, may_t0, want_t1);
+            Part q = make_part(ctx, ksh, kk, n_ket < MAX_KET_BLOCK ? n_ket : MAX_KET_BLOCK, may_t0, want_t1);
             Plan p;
             Sizer s2;
             s2.off = total;
@@ -983,7 +1005,7 @@ int wfo_overlaps_ci_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_
     char *before2 = ctx->scratch;
     WFO_TRY(state_overlaps_impl(ctx, ar2.off, d_smo, n_mo, n, exc_b, kb, d_cb, n_bra, exc_k, kk, d_ck, n_ket, sigma,
                                 tier, k_begin, k_end, d_out, st));
-    if (ctx->scratch != before2) return set_err(WFO_ERR_CUDA, "internal: arena moved during a host call%s");
+    if (ctx->scratch != before2) return set_err(WFO_ERR_CUDA, "internal: arena moved during a host call");
     if (info) info[3] = ctx->last_tier;
     WFO_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n_bra * n_ket * 8, cudaMemcpyDeviceToHost, st));
     WFO_CUDA(cudaStreamSynchronize(st));
@@ -1000,7 +1022,7 @@ int wfo_debug_phases(long long *out16, int reset) {
 
 /* ------------------------------------------------------------ measurement */
 int wfo_fp64_peak(wfo_ctx *ctx, int kind, int iters, double *tflops) {
-    if (!ctx || !tflops) return set_err(WFO_ERR_ARG, "fp64_peak: NULL argument%s");
+    if (!ctx || !tflops) return set_err(WFO_ERR_ARG, "fp64_peak: NULL argument");
     WFO_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     WFO_TRY(ensure_scratch(ctx, 256));
@@ -1013,7 +1035,7 @@ int wfo_fp64_peak(wfo_ctx *ctx, int kind, int iters, double *tflops) {
         if (kind == 0) dfma_peak_kernel<<<blocks, threads, 0, st>>>(iters, out);
         else if (kind == 1) dmma884_peak_kernel<<<blocks, threads, 0, st>>>(iters, out);
         else if (kind == 2) dmma1688_peak_kernel<<<blocks, threads, 0, st>>>(iters, out);
-        else return set_err(WFO_ERR_ARG, "fp64_peak: kind must be 0, 1 or 2%s");
+        else return set_err(WFO_ERR_ARG, "fp64_peak: kind must be 0, 1 or 2");
         WFO_LAUNCH_CHECK(ctx);
         WFO_CUDA(cudaEventRecord(ctx->ev1, st));
         WFO_CUDA(cudaEventSynchronize(ctx->ev1));

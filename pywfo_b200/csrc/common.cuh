@@ -15,8 +15,11 @@ namespace wfo {
 
 extern thread_local char g_err[512];
 
-inline int set_err(int code, const char *fmt, const char *a = "", long long b = 0, long long c = 0) {
-    snprintf(g_err, sizeof(g_err), fmt, a, b, c);
+// printf-style; integer arguments are passed as long long (use %lld)
+template <typename... Args>
+inline int set_err(int code, const char *fmt, Args... args) {
+    if constexpr (sizeof...(Args) == 0) snprintf(g_err, sizeof(g_err), "%s", fmt);
+    else snprintf(g_err, sizeof(g_err), fmt, static_cast<long long>(args)...);
     return code;
 }
 

@@ -115,7 +115,7 @@ ket_gs_dot_kernel(const double *__restrict__ Ck, int kk, int n_ket, const double
 // out[i][j] = d00 * sum_z P[z][i][j] + sigma * (sum_z P[z][i][n_ket]) * sum_z wpart[z][j]
 __global__ void finalize_kernel(const double *__restrict__ P, int n_slabs, int n_bra, int ldg, int n_ket,
                                 const double *__restrict__ wpart, const double *__restrict__ d00,
-                                double sigma, double *__restrict__ out) {
+                                double sigma, double *__restrict__ out, int ld_out) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_bra * n_ket) return;
     int i = idx / n_ket, j = idx - i * n_ket;
@@ -127,7 +127,7 @@ __global__ void finalize_kernel(const double *__restrict__ P, int n_slabs, int n
         a += P[z * slab + (size_t)i * ldg + j];
         u += P[z * slab + (size_t)i * ldg + n_ket];
     }
-    out[idx] = (*d00) * a + sigma * u * wj;
+    out[(size_t)i * ld_out + j] = (*d00) * a + sigma * u * wj;
 }
 
 // ---- closed-form tier (T2) helpers ---------------------------------------------------------
@@ -165,14 +165,15 @@ rowdot_kernel(const double *__restrict__ M, long long len, const double *__restr
 // out[i][j] = det^2 * ( (1+sigma) bx[i] ky[j] + sum_z P[z][i][j] )
 __global__ void closed_finalize_kernel(const double *__restrict__ P, int n_slabs, int n_bra, int n_ket,
                                        const double *__restrict__ bx, const double *__restrict__ ky,
-                                       const BaseInfo *__restrict__ info, double sigma, double *__restrict__ out) {
+                                       const BaseInfo *__restrict__ info, double sigma, double *__restrict__ out,
+                                       int ld_out) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_bra * n_ket) return;
     const int i = idx / n_ket, j = idx - i * n_ket;
     double a = 0.0;
     for (int z = 0; z < n_slabs; z++) a += P[(size_t)z * n_bra * n_ket + idx];
     const double d = info->det;
-    out[idx] = d * d * ((1.0 + sigma) * bx[i] * ky[j] + a);
+    out[(size_t)i * ld_out + j] = d * d * ((1.0 + sigma) * bx[i] * ky[j] + a);
 }
 
 // ---- FP64 peak microbenchmarks (roofline denominators, bench.py) -------------

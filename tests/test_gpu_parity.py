@@ -196,6 +196,18 @@ def test_kernel_form_tiers_agree_with_oracle(ctx, occ, n_mo, kb, kk, sigma):
         assert_parity(got, want, rtol=1e-9)
 
 
+@pytest.mark.parametrize("tier", ["lu", "update", "closed"])
+def test_many_states(ctx, tier):
+    """More ket states than one pass of the fused kernels holds (62): passes over state blocks."""
+    from pywfo_b200 import helpers, main
+    bra_mos, ket_mos, bci, kci = helpers.synthetic_case(31, 20, 6, 70, 131)
+    S = orc.mo_overlap(bra_mos, ket_mos, orc.get_S_AO(bra_mos, ket_mos, "ket"))
+    want = orc.state_overlaps_factored(S, 6, orc.signed_ci(bci, 6), orc.signed_ci(kci, 6), 1.0)
+    got = main.overlaps_cache(bra_mos, ket_mos, bci, kci, 6, ci_thresh=0.0, tier=tier)
+    assert got.shape == (70, 131)
+    assert_parity(got, want, rtol=1e-9)
+
+
 def test_closed_form_tier(ctx):
     """T2: GEMM-only closed form == brute force; refuses ground-state entries; shards add up."""
     from pywfo_b200._lib import WfoError
@@ -375,3 +387,17 @@ def test_config_sweep_n64(ctx, k):
     want = orc.state_overlaps_closed_form(S, occ, [tuple(e) for e in bra], Cb, [tuple(e) for e in ket], Ck, 1.0)
     for tier in ("lu", "update"):
         assert_parity(ctx.state_overlaps_host(S, occ, bra, Cb, ket, Ck, tier=tier), want, rtol=1e-9)
+
+
+def test_error_messages_are_formatted(ctx):
+    """Every error path formats its message (regression: a mis-ordered printf argument crashed)."""
+    from pywfo_b200._lib import WfoError
+    S = np.eye(140)
+    rows = np.arange(130, dtype=np.int32)[None, :]
+    with pytest.raises(WfoError, match="n_occ=130"):
+        ctx.det_table_host(S, rows, rows)
+    bra = np.zeros((1, 2), dtype=np.int32)
+    with pytest.raises(WfoError, match=r"bad shard \[0,5\)"):
+        ctx.state_overlaps_host(np.eye(4), 2, bra, np.ones((1, 1)), bra, np.ones((1, 1)), k_begin=0, k_end=5)
+    with pytest.raises(WfoError, match="n_occ=9 must be in 1..n_mo=4"):
+        ctx.state_overlaps_host(np.eye(4), 9, bra, np.ones((1, 1)), bra, np.ones((1, 1)))
