@@ -8,6 +8,7 @@
 #include "det_lu_blocked.cuh"
 #include "det_lu_v1.cuh"
 #include "det_lu_warp.cuh"
+#include "det_lu_wpm.cuh"
 #include "gemm_f64.cuh"
 #include "lu_base.cuh"
 #include "misc_kernels.cuh"
@@ -106,6 +107,10 @@ static int gemm(wfo_ctx *ctx, bool ta, bool tb, int m, int n, int k, double alph
 static size_t t0_smem_bytes(int n) { return (size_t)n * (n | 1) * sizeof(double) + 2 * (size_t)n * sizeof(int); }
 static int t0_threads(int n) { return n > 64 ? 256 : 128; }
 
+#ifndef WFO_T0_WPM_DEFAULT
+#define WFO_T0_WPM_DEFAULT 0
+#endif
+
 static bool use_v1() {
     static int v = -1;
     if (v < 0) { const char *e = getenv("WFO_T0_V1"); v = (e && e[0] == '1') ? 1 : 0; }
@@ -152,6 +157,20 @@ static int ensure_gscratch(wfo_ctx *ctx, size_t bytes) {
     return WFO_OK;
 }
 
+// warp-per-matrix kernels with an L2-resident scratch for 32 < n <= 128 (WFO_T0_WPM=0 selects the
+// shared-memory CTA-per-matrix kernels instead)
+static bool use_wpm_kernels(int n) {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("WFO_T0_WPM"); v = e ? atoi(e) : WFO_T0_WPM_DEFAULT; }
+    return v == 1 && n > 32 && n <= 128;
+}
+#define WFO_WPM_DISPATCH(n, CALL)            \
+    do {                                     \
+        if ((n) <= 64) { CALL(2); }          \
+        else if ((n) <= 96) { CALL(3); }     \
+        else { CALL(4); }                    \
+    } while (0)
+
 static bool use_warp_kernels(int n) {
     static int v = -1;
     if (v < 0) { const char *e = getenv("WFO_T0_NOWARP"); v = (e && e[0] == '1') ? 0 : 1; }
@@ -190,6 +209,13 @@ static int det_table(wfo_ctx *ctx, const double *S, int ld_s, int n, const int32
         int threads = t0_threads(n);
         WFO_TRY(persistent_grid(ctx, det_table_kernel, threads, smem, npairs, &grid));
         det_table_kernel<<<grid, threads, smem, st>>>(S, ld_s, n, rows, kb, cols, kk, D);
+    } else if (use_wpm_kernels(n)) {
+#define CALL_DP(SL_)                                                                                          \
+    WFO_TRY(persistent_grid(ctx, det_table_wpm_kernel<SL_>, WPM_WARPS * 32, 0, (npairs + WPM_WARPS - 1) / WPM_WARPS, &grid)); \
+    WFO_TRY(ensure_gscratch(ctx, (size_t)grid * WPM_WARPS * wpm_mat_bytes(n)));                                \
+    det_table_wpm_kernel<SL_><<<grid, WPM_WARPS * 32, 0, st>>>(S, ld_s, n, rows, kb, cols, kk, D, ctx->gscratch)
+        WFO_WPM_DISPATCH(n, CALL_DP);
+#undef CALL_DP
     } else if (use_warp_kernels(n)) {
 #define CALL_DW(NC_, SEG_)                                                                                 \
     WFO_TRY(persistent_grid(ctx, det_table_warp_kernel<NC_, SEG_>, 128, 0, (npairs + 3) / 4, &grid));      \
@@ -717,6 +743,15 @@ static int state_overlaps_block(wfo_ctx *ctx, size_t arena_off, const double *s_
             if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev0, st));
             t0_fused_kernel<<<grid, threads, smem, st>>>(s_mo, n_mo, n, p.bra_lists, ksh, p.ket_lists, kk, p.ckt,
                                                          ldg, chunk_len, t0_chunks, p.gpart);
+        } else if (use_wpm_kernels(n)) {
+#define CALL_FP(SL_)                                                                                              \
+    WFO_TRY(persistent_grid(ctx, t0_fused_wpm_kernel<SL_>, WPM_WARPS * 32, 0, (items + WPM_WARPS - 1) / WPM_WARPS, &grid)); \
+    WFO_TRY(ensure_gscratch(ctx, (size_t)grid * WPM_WARPS * wpm_mat_bytes(n)));                                    \
+    if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev0, st));                                                      \
+    t0_fused_wpm_kernel<SL_><<<grid, WPM_WARPS * 32, 0, st>>>(s_mo, n_mo, n, p.bra_lists, ksh, p.ket_lists, kk,    \
+                                                              p.ckt, ldg, chunk_len, t0_chunks, p.gpart, ctx->gscratch)
+            WFO_WPM_DISPATCH(n, CALL_FP);
+#undef CALL_FP
         } else if (use_warp_kernels(n)) {
 #define CALL_FW(NC_, SEG_)                                                                                      \
     WFO_TRY(persistent_grid(ctx, t0_fused_warp_kernel<NC_, SEG_>, 128, 0, (items + 3) / 4, &grid));             \
