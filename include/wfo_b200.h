@@ -135,6 +135,10 @@ int wfo_last_tier(const wfo_ctx *ctx);
  * determinant kernel of the last wfo_state_overlaps_* call made with timing on */
 int wfo_set_timing(wfo_ctx *ctx, int on);
 double wfo_last_kernel_ms(const wfo_ctx *ctx);
+/* timing level 2: CUDA events at the phase boundaries of the last wfo_state_overlaps_* call.
+ * Fills ms[i] (up to 23 entries) with the device time of phase i and `names` with the
+ * comma-separated phase labels; returns the number of phases (0 if timing < 2). */
+int wfo_last_phases(wfo_ctx *ctx, double *ms, char *names, int names_cap);
 
 /* ---- measurement helpers (bench.py roofline denominators) ------------------
  * MEASURED_PEAKS.json has no FP64 entry, so the harness measures it in-run:

@@ -50,6 +50,7 @@ SIGNATURES = {
     "wfo_last_tier": (C.c_int, [c_vp]),
     "wfo_set_timing": (C.c_int, [c_vp, C.c_int]),
     "wfo_last_kernel_ms": (C.c_double, [c_vp]),
+    "wfo_last_phases": (C.c_int, [c_vp, c_dp, C.c_char_p, C.c_int]),
     "wfo_fp64_peak": (C.c_int, [c_vp, C.c_int, C.c_int, c_dp]),
 }
 
@@ -245,8 +246,17 @@ class Context:
     def last_tier(self) -> int:
         return int(self.lib.wfo_last_tier(self.handle))
 
-    def set_timing(self, on: bool):
+    def set_timing(self, on):
+        """0 = off, 1 = dominant kernel only, 2 = phase breakdown (``last_phases``)."""
         check(self.lib.wfo_set_timing(self.handle, int(on)))
+
+    def last_phases(self):
+        """[(label, ms), ...] of the last state-overlap call (timing level 2)."""
+        ms = (C.c_double * 24)()
+        names = C.create_string_buffer(1024)
+        k = int(self.lib.wfo_last_phases(self.handle, ms, names, 1024))
+        labels = names.value.decode().split(",") if k else []
+        return [(labels[i], ms[i]) for i in range(k)]
 
     def last_kernel_ms(self) -> float:
         return float(self.lib.wfo_last_kernel_ms(self.handle))

@@ -243,29 +243,29 @@ static int det_table(wfo_ctx *ctx, const double *S, int ld_s, int n, const int32
     return WFO_OK;
 }
 
-template <int NT>
-static int launch_t1(wfo_ctx *ctx, int ktiles, int splits, cudaStream_t st, const double *Ai, const double *W,
-                     const BraMeta *bra, const double *bscale, int ksh, const KetMeta *ket, const double *ckts,
-                     int kk, int lps, int *counter, double *gpart) {
-    int per_sm = 1;
-    WFO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, t1_fused_kernel<NT>, T1_WARPS * 32, 0));
-    if (per_sm < 1) per_sm = 1;
-    const int items = ktiles * splits;
-    int grid = ctx->sm_count * per_sm;
-    if (grid > items) grid = items;
-    WFO_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
-    t1_fused_kernel<NT><<<grid, T1_WARPS * 32, 0, st>>>(Ai, W, bra, bscale, ksh, ket, ckts, kk, lps, ktiles, items,
-                                                        counter, gpart);
+// the rank-update kernel runs one persistent CTA per SM; opt in to its dynamic shared memory once
+static int t1_prepare(int ldg) {
+    static bool done[8] = {false, false, false, false, false, false, false, false};
+    const int nt = ldg / 8;
+    if (nt < 1 || nt > 7 || !(nt & 1)) return set_err(WFO_ERR_ARG, "state_overlaps: unsupported ldg %lld", ldg);
+    if (!done[nt]) {
+        switch (nt) {
+#define T1_ATTR(NT_) case NT_: WFO_CUDA(cudaFuncSetAttribute(t1_fused_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t1_smem_bytes<NT_>())); break;
+            T1_ATTR(1) T1_ATTR(3) T1_ATTR(5) T1_ATTR(7)
+#undef T1_ATTR
+        }
+        done[nt] = true;
+    }
     return WFO_OK;
 }
 
 struct Plan {   // everything wfo_state_overlaps needs from the arena
     // common
-    double *ckt, *gpart, *G, *P, *w, *dk0, *d0l, *d00, *out_dev;
+    double *ckt, *gpart, *P, *wvec, *dk0, *d0l, *d00, *out_dev;
     // T0
     int32_t *bra_lists, *ket_lists, *gs_list;
     // T1
-    double *Abuf, *Ai, *X, *Y, *Wb, *bscale, *ksgn;
+    double *Abuf, *Ai, *X, *Y, *Wb, *bscale;
     BraMeta *bmeta;
     KetMeta *kmeta;
     BaseInfo *info;
@@ -274,12 +274,13 @@ struct Plan {   // everything wfo_state_overlaps needs from the arena
 template <typename AR>
 static void carve(AR &ar, Plan &p, int n, int v, int ksh, int kk, int n_bra, int ldg, int n_parts, int n_slabs,
                   bool t0, bool t1) {
-    p.ckt = ar.template take<double>((size_t)kk * ldg);
-    p.gpart = ar.template take<double>((size_t)n_parts * ksh * ldg);
-    p.G = ar.template take<double>((size_t)ksh * ldg);
+    const size_t kk_pad = align_up((size_t)(kk > 0 ? kk : 1), T1_LT);   // whole ket tiles for the TMA ring
+    p.ckt = ar.template take<double>(kk_pad * ldg);
+    const size_t ksh_g = (size_t)ksh + 1;   // + the virtual ground-state row of the rank-update tier
+    p.gpart = ar.template take<double>((size_t)n_parts * ksh_g * ldg);
+    p.wvec = ar.template take<double>((size_t)KGS_SLABS * ldg);
     p.P = ar.template take<double>((size_t)n_slabs * n_bra * ldg);
-    p.w = ar.template take<double>((size_t)KGS_SLABS * ldg);
-    p.dk0 = ar.template take<double>(ksh > 0 ? ksh : 1);
+    p.dk0 = ar.template take<double>(ksh_g);
     p.d0l = ar.template take<double>(kk > 0 ? kk : 1);
     p.d00 = ar.template take<double>(1);
     if (t0) {
@@ -292,10 +293,9 @@ static void carve(AR &ar, Plan &p, int n, int v, int ksh, int kk, int n_bra, int
         p.X = ar.template take<double>((size_t)(v > 0 ? v : 1) * n);
         p.Y = ar.template take<double>((size_t)n * (v > 0 ? v : 1));
         p.Wb = ar.template take<double>((size_t)(v + 1) * (v + 1));
-        p.bscale = ar.template take<double>(ksh > 0 ? ksh : 1);
-        p.ksgn = ar.template take<double>(kk > 0 ? kk : 1);
-        p.bmeta = ar.template take<BraMeta>(ksh > 0 ? ksh : 1);
-        p.kmeta = ar.template take<KetMeta>(kk > 0 ? kk : 1);
+        p.bscale = ar.template take<double>(ksh_g);
+        p.bmeta = ar.template take<BraMeta>(ksh_g);
+        p.kmeta = ar.template take<KetMeta>(kk_pad);
         p.info = ar.template take<BaseInfo>(1);
     }
 }
@@ -308,7 +308,8 @@ static int pick_ldg(int n_ket) {
 
 
 struct Part {   // how the pair space of one call is cut up
-    int ldg, ktiles, t1_splits, lps, t0_chunks, chunk_len, n_parts, kslab, n_slabs;
+    int ldg, t0_chunks, chunk_len, n_parts, n_slabs;
+    PartMap t1;   // stream-K decomposition of the rank-update kernel
     bool may_t0, want_t1;
 };
 
@@ -342,32 +343,42 @@ static int resolve_tier(const wfo_ctx *ctx, int n, int tier, bool *want_t1, bool
     return WFO_OK;
 }
 
-static Part make_part(const wfo_ctx *ctx, int ksh, int kk, int n_ket, bool may_t0, bool want_t1) {
+static int make_part(wfo_ctx *ctx, int ksh, int kk, int n_ket, bool may_t0, bool want_t1, Part *out) {
     Part q;
     q.may_t0 = may_t0;
     q.want_t1 = want_t1;
     q.ldg = pick_ldg(n_ket);
-    const int target_ctas = ctx->sm_count * 48;
-    // T1: work items (k tile, l split), fetched dynamically by persistent CTAs
-    q.ktiles = cdiv(ksh, T1_KTILE);
-    int splits = cdiv(target_ctas, q.ktiles);
-    int max_splits = cdiv(kk, 16 * T1_LT);   // at least 16 ket tiles per work item
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
-    q.lps = (int)align_up((size_t)cdiv(kk, splits), T1_LT);
-    q.t1_splits = cdiv(kk, q.lps);
+    q.n_parts = 1;
+    memset(&q.t1, 0, sizeof(q.t1));
+    if (want_t1) {
+        // T1: iterations (bra tile, ket tile) in equal contiguous ranges over the resident CTAs
+        WFO_TRY(t1_prepare(q.ldg));
+        const int slots = ctx->sm_count;
+        const int ktiles = cdiv(ksh + 1, T1_KTILE), n_ltiles = cdiv(kk, T1_LT);
+        const long long I = (long long)ktiles * n_ltiles;
+        long long G = slots;
+        if (G > I / 4) G = I / 4;   // at least 4 ket tiles per CTA
+        if (G < 1) G = 1;
+        q.t1.I = I;
+        q.t1.G = (int)G;
+        q.t1.n_ltiles = n_ltiles;
+        q.t1.ktile_rows = T1_KTILE;
+        q.t1.uniform_parts = 0;
+        const long long per = I / G;   // >= 1
+        const int parts = (int)((n_ltiles + per - 1) / per) + 1;
+        if (parts > q.n_parts) q.n_parts = parts;
+    }
     // T0: items (k, chunk of l)
+    const int target_ctas = ctx->sm_count * 48;
     int chunks = cdiv(target_ctas, ksh);
     if (chunks > kk) chunks = kk;
     if (chunks < 1) chunks = 1;
     q.chunk_len = cdiv(kk, chunks);
     q.t0_chunks = cdiv(kk, q.chunk_len);
-    q.n_parts = 1;
-    if (want_t1 && q.t1_splits > q.n_parts) q.n_parts = q.t1_splits;
     if (may_t0 && q.t0_chunks > q.n_parts) q.n_parts = q.t0_chunks;
-    q.kslab = 1024;
-    q.n_slabs = cdiv(ksh, q.kslab);
-    return q;
+    q.n_slabs = cdiv(ksh + 1, RC_ROWS);
+    *out = q;
+    return WFO_OK;
 }
 
 __global__ void iota_kernel(int32_t *p, int n) {
@@ -409,8 +420,12 @@ int wfo_create(int device, wfo_ctx **out) {
     c->smem_optin = prop.sharedMemPerBlockOptin;
     c->last_tier = -1;
     WFO_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    WFO_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    WFO_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    WFO_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     WFO_CUDA(cudaEventCreate(&c->ev0));
     WFO_CUDA(cudaEventCreate(&c->ev1));
+    for (int i = 0; i < 24; i++) WFO_CUDA(cudaEventCreate(&c->pev[i]));
     *out = c;
     return WFO_OK;
 }
@@ -423,6 +438,10 @@ int wfo_destroy(wfo_ctx *ctx) {
     if (ctx->gscratch) cudaFree(ctx->gscratch);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
+    for (int i = 0; i < 24; i++) cudaEventDestroy(ctx->pev[i]);
+    cudaEventDestroy(ctx->ev_fork);
+    cudaEventDestroy(ctx->ev_join);
+    cudaStreamDestroy(ctx->stream2);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return WFO_OK;
@@ -435,6 +454,25 @@ int wfo_set_timing(wfo_ctx *ctx, int on) {
     ctx->timing = on;
     return WFO_OK;
 }
+int wfo_last_phases(wfo_ctx *ctx, double *ms, char *names, int names_cap) {
+    if (!ctx) return 0;
+    if (names && names_cap > 0) names[0] = 0;
+    if (ctx->timing < 2 || ctx->n_phase < 2) return 0;
+    if (cudaEventSynchronize(ctx->pev[ctx->n_phase - 1]) != cudaSuccess) return 0;
+    size_t used = 0;
+    for (int i = 1; i < ctx->n_phase; i++) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, ctx->pev[i - 1], ctx->pev[i]) != cudaSuccess) return 0;
+        if (ms) ms[i - 1] = t;
+        if (names) {
+            int w = snprintf(names + used, used < (size_t)names_cap ? names_cap - used : 0, "%s%s", i > 1 ? "," : "",
+                             ctx->pname[i]);
+            if (w > 0) used += (size_t)w;
+        }
+    }
+    return ctx->n_phase - 1;
+}
+
 double wfo_last_kernel_ms(const wfo_ctx *ctx) {
     if (!ctx || !ctx->timing) return -1.0;
     float ms = -1.f;
@@ -656,9 +694,9 @@ static int state_overlaps_block(wfo_ctx *ctx, size_t arena_off, const double *s_
     if (tier == WFO_TIER_CLOSED)
         return closed_form_impl(ctx, arena_off, s_mo, n_mo, n, bra_exc, kb, Cb, n_bra, ket_exc, kk, Ck, n_ket, sigma,
                                 k_begin, k_end, out, ld_out, st);
-    const Part q = make_part(ctx, ksh, kk, n_ket, may_t0, want_t1);
-    const int ldg = q.ldg, ktiles = q.ktiles, t1_splits = q.t1_splits, lps = q.lps, t0_chunks = q.t0_chunks,
-              chunk_len = q.chunk_len, kslab = q.kslab, n_slabs = q.n_slabs;
+    Part q;
+    WFO_TRY(make_part(ctx, ksh, kk, n_ket, may_t0, want_t1, &q));
+    const int ldg = q.ldg, t0_chunks = q.t0_chunks, chunk_len = q.chunk_len, n_slabs = q.n_slabs;
 
     Plan p;
     memset(&p, 0, sizeof(p));
@@ -671,49 +709,66 @@ static int state_overlaps_block(wfo_ctx *ctx, size_t arena_off, const double *s_
 
     const int32_t *bra_sh = bra_exc + 2 * (size_t)k_begin;
     const double *d00_ptr = nullptr;
-    int used = -1, parts_used = 0;
+    int used = -1;
+    PartMap pmap;
+    memset(&pmap, 0, sizeof(pmap));
+    ctx->n_phase = 0;
+    WFO_PHASE(ctx, st, "start");
+    const size_t ckt_smem = (size_t)CKT_TL * (ldg + 1) * sizeof(double);
 
     if (want_t1) {
+        // ---- side stream: what does not depend on the base factorisation (signed, transposed ket
+        // coefficients; the Dv block of W) runs next to the single-CTA base inverse
+        cudaStream_t s2 = ctx->stream2;
+        WFO_CUDA(cudaEventRecord(ctx->ev_fork, st));
+        WFO_CUDA(cudaStreamWaitEvent(s2, ctx->ev_fork, 0));
+        const int kk_pad = (int)align_up((size_t)kk, T1_LT);
+        ckt_kernel<<<cdiv(kk_pad, CKT_TL), 256, ckt_smem, s2>>>(Ck, kk, kk_pad, n_ket, ket_exc, n, ldg, p.ckt);
+        WFO_LAUNCH_CHECK(ctx);
+        {
+            long long wtot = (long long)(v + 1) * (v + 1);
+            w_init_kernel<<<(unsigned)((wtot + 255) / 256), 256, 0, s2>>>(s_mo, n_mo, n, v, p.Wb);
+            WFO_LAUNCH_CHECK(ctx);
+        }
+        WFO_CUDA(cudaEventRecord(ctx->ev_join, s2));
         // ---- one base factorisation, then the three block products
         base_inverse_kernel<<<1, LUB_THREADS, 0, st>>>(s_mo, n_mo, n, p.Ai, p.info);
         WFO_LAUNCH_CHECK(ctx);
         // the conditioning of the base block decides whether the rank-update tier is usable:
         // one 32-byte read-back (the only host synchronisation of the call)
         BaseInfo hinfo;
+        WFO_PHASE(ctx, st, "base_inverse");
         WFO_CUDA(cudaMemcpyAsync(&hinfo, p.info, sizeof(hinfo), cudaMemcpyDeviceToHost, st));
         WFO_CUDA(cudaStreamSynchronize(st));
+        WFO_PHASE(ctx, st, "info_sync");
         const bool ok = !hinfo.singular && hinfo.min_piv > 1e-6 * hinfo.max_piv;
+        WFO_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
         if (ok) {
             const double *Bblk = s_mo + n;                    // occ  x virt
             const double *Cblk = s_mo + (size_t)n * n_mo;     // virt x occ
             if (v > 0) {
                 WFO_TRY(gemm(ctx, false, false, v, n, n, 1.0, Cblk, n_mo, p.Ai, n, 0.0, p.X, n, 0, 0, st));
                 WFO_TRY(gemm(ctx, false, false, n, v, n, 1.0, p.Ai, n, Bblk, n_mo, 0.0, p.Y, v, 0, 0, st));
+                WFO_TRY(gemm(ctx, false, false, v, v, n, -1.0, Cblk, n_mo, p.Y, v, 1.0, p.Wb, v + 1, 0, 0, st));
             }
-            long long wtot = (long long)(v + 1) * (v + 1);
-            w_init_kernel<<<(unsigned)((wtot + 255) / 256), 256, 0, st>>>(s_mo, n_mo, n, v, p.Wb);
+            WFO_PHASE(ctx, st, "xyw_gemms");
+            t1_prep_kernel<<<cdiv(ksh + 1, 256) + cdiv(kk_pad, 256), 256, 0, st>>>(bra_sh, ksh, ket_exc, kk, kk_pad, n, v, p.X, p.Y, p.info,
+                                                                          p.bmeta, p.bscale, p.dk0, p.kmeta, p.d0l);
             WFO_LAUNCH_CHECK(ctx);
-            if (v > 0) WFO_TRY(gemm(ctx, false, false, v, v, n, -1.0, Cblk, n_mo, p.Y, v, 1.0, p.Wb, v + 1, 0, 0, st));
-            t1_prep_bra_kernel<<<cdiv(ksh, 256), 256, 0, st>>>(bra_sh, ksh, n, v, p.X, p.info, p.bmeta, p.bscale, p.dk0);
-            WFO_LAUNCH_CHECK(ctx);
-            t1_prep_ket_kernel<<<cdiv(kk, 256), 256, 0, st>>>(ket_exc, kk, n, v, p.Y, p.info, p.kmeta, p.ksgn, p.d0l);
-            WFO_LAUNCH_CHECK(ctx);
-            long long ctot = (long long)kk * ldg;
-            ckt_kernel<<<(unsigned)((ctot + 255) / 256), 256, 0, st>>>(Ck, kk, n_ket, p.ksgn, ldg, p.ckt);
-            WFO_LAUNCH_CHECK(ctx);
+            WFO_PHASE(ctx, st, "prep");
             if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev0, st));
-            int *counter = reinterpret_cast<int *>(p.w);   // w is written later in the stream
+            pmap = q.t1;
             switch (ldg / 8) {
-#define T1_CASE(NT_) case NT_: WFO_TRY(launch_t1<NT_>(ctx, ktiles, t1_splits, st, p.Ai, p.Wb, p.bmeta, p.bscale, ksh, p.kmeta, p.ckt, kk, lps, counter, p.gpart)); break;
+#define T1_CASE(NT_) case NT_: t1_fused_kernel<NT_><<<pmap.G, T1_WARPS * 32, t1_smem_bytes<NT_>(), st>>>(p.Ai, p.Wb, p.bmeta, p.bscale, ksh + 1, p.kmeta, p.ckt, kk, pmap, p.gpart); break;
                 T1_CASE(1) T1_CASE(3) T1_CASE(5) T1_CASE(7)
 #undef T1_CASE
                 default: return set_err(WFO_ERR_ARG, "state_overlaps: unsupported ldg %lld", ldg);
             }
             WFO_LAUNCH_CHECK(ctx);
             if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev1, st));
+            WFO_PHASE(ctx, st, "t1_fused");
             d00_ptr = &p.info->det;
             used = WFO_TIER_UPDATE;
-            parts_used = t1_splits;
         } else if (!may_t0) {
             return set_err(WFO_ERR_SINGULAR,
                            "state_overlaps: base block S_MO[:occ,:occ] is (numerically) singular, "
@@ -731,8 +786,7 @@ static int state_overlaps_block(wfo_ctx *ctx, size_t arena_off, const double *s_
         WFO_TRY(det_table(ctx, s_mo, n_mo, n, p.bra_lists, ksh, p.gs_list, 1, p.dk0, st));
         WFO_TRY(det_table(ctx, s_mo, n_mo, n, p.gs_list, 1, p.ket_lists, kk, p.d0l, st));
         WFO_TRY(det_table(ctx, s_mo, n_mo, n, p.gs_list, 1, p.gs_list, 1, p.d00, st));
-        long long ctot = (long long)kk * ldg;
-        ckt_kernel<<<(unsigned)((ctot + 255) / 256), 256, 0, st>>>(Ck, kk, n_ket, nullptr, ldg, p.ckt);
+        ckt_kernel<<<cdiv(kk, CKT_TL), 256, ckt_smem, st>>>(Ck, kk, kk, n_ket, nullptr, n, ldg, p.ckt);
         WFO_LAUNCH_CHECK(ctx);
         const long long items = (long long)ksh * t0_chunks;
         unsigned grid = 1;
@@ -781,22 +835,30 @@ static int state_overlaps_block(wfo_ctx *ctx, size_t arena_off, const double *s_
         }
         WFO_LAUNCH_CHECK(ctx);
         if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev1, st));
+        WFO_PHASE(ctx, st, "t0_path");
         d00_ptr = p.d00;
         used = WFO_TIER_LU;
-        parts_used = t0_chunks;
+        pmap.I = 0;
+        pmap.uniform_parts = t0_chunks;
     }
 
-    // ---- CI contraction: G = sum of partials (+ dk0 column), P = Cb[:, shard] G, finalize
-    long long gtot = (long long)ksh * ldg;
-    sum_parts_kernel<<<(unsigned)((gtot + 255) / 256), 256, 0, st>>>(p.gpart, parts_used, ksh, ldg, n_ket, p.dk0, p.G);
+    // ---- CI contraction: P[z] = Cb[:, slab z] (sum of partials of slab z), then the final sums
+    const int ksh_g = (used == WFO_TIER_UPDATE) ? ksh + 1 : ksh;
+    int n_wparts = 1;
+    if (used == WFO_TIER_LU) {   // the rank-update tier gets w from its virtual ground-state row
+        ket_gs_dot_kernel<<<dim3(n_ket, KGS_SLABS), 256, 0, st>>>(Ck, kk, n_ket, ldg, p.d0l, p.wvec);
+        WFO_LAUNCH_CHECK(ctx);
+        n_wparts = KGS_SLABS;
+    }
+    reduce_contract_kernel<<<dim3(cdiv(ksh_g, RC_ROWS), ldg / 8), 256, 0, st>>>(
+        p.gpart, pmap, ksh_g, ksh, ldg, n_ket, p.dk0, Cb + k_begin, kb, n_bra, p.P, p.wvec,
+        used == WFO_TIER_UPDATE ? ksh : -1);
     WFO_LAUNCH_CHECK(ctx);
-    WFO_TRY(gemm(ctx, false, false, n_bra, ldg, ksh, 1.0, Cb + k_begin, kb, p.G, ldg, 0.0, p.P, ldg, kslab,
-                 (long long)n_bra * ldg, st));
-    ket_gs_dot_kernel<<<dim3(n_ket, KGS_SLABS), 256, 0, st>>>(Ck, kk, n_ket, p.d0l, p.w);
+    WFO_PHASE(ctx, st, "reduce_contract");
+    finalize3_kernel<<<n_bra, 256, 0, st>>>(p.P, cdiv(ksh_g, RC_ROWS), n_bra, ldg, n_ket, p.wvec, n_wparts, d00_ptr, sigma,
+                                            out, ld_out);
     WFO_LAUNCH_CHECK(ctx);
-    finalize_kernel<<<cdiv(n_bra * n_ket, 128), 128, 0, st>>>(p.P, n_slabs, n_bra, ldg, n_ket, p.w, d00_ptr, sigma, out,
-                                                              ld_out);
-    WFO_LAUNCH_CHECK(ctx);
+    WFO_PHASE(ctx, st, "finalize");
     ctx->last_tier = used;
     return WFO_OK;
 }
@@ -851,7 +913,8 @@ static int host_front(wfo_ctx *ctx, const double *s_mo_host, const double *bra_m
         bool want_t1 = false, may_t0 = false;
         if (n >= 1 && n <= n_mo && ksh > 0 && kk > 0 && k_begin >= 0 && k_end <= kb &&
             resolve_tier(ctx, n, tier, &want_t1, &may_t0) == WFO_OK) {
-            Part q = make_part(ctx, ksh, kk, n_ket < MAX_KET_BLOCK ? n_ket : MAX_KET_BLOCK, may_t0, want_t1);
+            Part q;
+            WFO_TRY(make_part(ctx, ksh, kk, n_ket < MAX_KET_BLOCK ? n_ket : MAX_KET_BLOCK, may_t0, want_t1, &q));
             Plan p;
             Sizer s2;
             s2.off = front;
@@ -1008,7 +1071,8 @@ int wfo_overlaps_ci_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_
         WFO_TRY(resolve_tier(ctx, n, tier, &want_t1, &may_t0));
         const int ksh = k_end - k_begin;
         if (ksh > 0) {
-            Part q = make_part(ctx, ksh, kk, n_ket < MAX_KET_BLOCK ? n_ket : MAX_KET_BLOCK, may_t0, want_t1);
+            Part q;
+            WFO_TRY(make_part(ctx, ksh, kk, n_ket < MAX_KET_BLOCK ? n_ket : MAX_KET_BLOCK, may_t0, want_t1, &q));
             Plan p;
             Sizer s2;
             s2.off = total;
@@ -1046,6 +1110,12 @@ int wfo_overlaps_ci_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_
     WFO_CUDA(cudaStreamSynchronize(st));
     return WFO_OK;
 }
+
+#ifdef WFO_T1_CLOCKS
+int wfo_debug_t1_clocks(long long *out, int n_ctas) {
+    return (int)cudaMemcpyFromSymbol(out, g_t1_clk, sizeof(long long) * 4 * (size_t)n_ctas);
+}
+#endif
 
 #ifdef WFO_PHASE_TIMING
 int wfo_debug_phases(long long *out16, int reset) {

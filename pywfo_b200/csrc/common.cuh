@@ -74,6 +74,8 @@ struct wfo_ctx {
     int sm_count;
     size_t smem_optin;
     cudaStream_t stream;   // private stream of the *_host entry points
+    cudaStream_t stream2;  // side stream: work that overlaps the single-CTA base factorisation
+    cudaEvent_t ev_fork, ev_join;
     char *scratch;         // device arena, grown on demand
     size_t scratch_bytes;
     double *gscratch;      // per-CTA LU working matrices (global-scratch variant of the T0 kernel)
@@ -83,4 +85,17 @@ struct wfo_ctx {
     int timing;
     float last_ms;
     cudaEvent_t ev0, ev1;
+    // phase breakdown of the last state-overlap call (timing level 2): events at phase boundaries
+    cudaEvent_t pev[24];
+    const char *pname[24];
+    int n_phase;
 };
+
+// record a phase boundary on `st` (timing level 2 only); the name labels the phase that ENDS here
+#define WFO_PHASE(ctx, st, name)                                            \
+    do {                                                                    \
+        if ((ctx)->timing >= 2 && (ctx)->n_phase < 24) {                    \
+            WFO_CUDA(cudaEventRecord((ctx)->pev[(ctx)->n_phase], st));      \
+            (ctx)->pname[(ctx)->n_phase++] = name;                          \
+        }                                                                   \
+    } while (0)

@@ -65,7 +65,8 @@ base_inverse_kernel(const double *__restrict__ A_src, int ld_src, int n, double 
         for (int lj = 0; lj < nsteps; lj++) { // owning lane
             const int j = lj + 32 * cj;
             const int b = j & 1;
-            // ---- pivot search: per-warp candidate from lane lj, combined through shared memory
+            // ---- pivot search: per-warp candidate from the lane that owns column j; the owner
+            // publishes the column (the multipliers) and restarts its column slot from zero
             if (lane == lj) {
                 unsigned key = 0;
 #pragma unroll
@@ -73,6 +74,7 @@ base_inverse_kernel(const double *__restrict__ A_src, int ld_src, int n, double 
                     const unsigned k = (hi_abs(a[s][cj]) & 0xffffff00u) | 0x80u | (unsigned)(warp + LUB_WARPS * s);
                     key = max(key, done[s] ? 0u : k);
                     mcol[b][warp + LUB_WARPS * s] = a[s][cj];
+                    a[s][cj] = 0.0;
                 }
                 keys[b][warp] = key;
             }
@@ -106,18 +108,24 @@ base_inverse_kernel(const double *__restrict__ A_src, int ld_src, int n, double 
             double pr[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) pr[k] = prow[b][lane + 32 * k];
+            if (warp != wp) {                           // 15 of 16 warps: pure multiply-add
 #pragma unroll
-            for (int s = 0; s < LUB_RS; s++) {
-                const int r = warp + LUB_WARPS * s;
-                const bool is_p = (r == p);
-                done[s] = done[s] || is_p;
-                const double f = is_p ? 0.0 : mcol[b][r];
+                for (int s = 0; s < LUB_RS; s++) {
+                    const double f = mcol[b][warp + LUB_WARPS * s];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    // the eliminated column (static slot cj, lane lj) restarts from zero
-                    const double base = (k == cj && lane == lj) ? 0.0 : a[s][k];
-                    const double upd = fma(-f, pr[k], base);
-                    a[s][k] = is_p ? pr[k] : upd;
+                    for (int k = 0; k < 4; k++) a[s][k] = fma(-f, pr[k], a[s][k]);
+                }
+            } else {                                    // the warp that holds the pivot row
+#pragma unroll
+                for (int s = 0; s < LUB_RS; s++) {
+                    const bool is_p = (s == sp);
+                    done[s] = done[s] || is_p;
+                    const double f = is_p ? 0.0 : mcol[b][warp + LUB_WARPS * s];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const double upd = fma(-f, pr[k], a[s][k]);
+                        a[s][k] = is_p ? pr[k] : upd;
+                    }
                 }
             }
         }

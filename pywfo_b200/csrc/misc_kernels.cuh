@@ -19,15 +19,37 @@ __global__ void exc_lists_kernel(const int32_t *__restrict__ exc, int k, int n, 
     lists[idx] = v;
 }
 
-// CkT[l][j] = scale[l] * Ck[j][l] for j < n_ket, 0 for the padding columns.
-__global__ void ckt_kernel(const double *__restrict__ Ck, int kk, int n_ket, const double *__restrict__ scale,
-                           int ldg, double *__restrict__ ckt) {
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)kk * ldg) return;
-    int j = (int)(idx / kk), l = (int)(idx - (long long)j * kk);   // l fastest: coalesced reads
-    double v = 0.0;
-    if (j < n_ket) v = Ck[(size_t)j * kk + l] * (scale ? scale[l] : 1.0);
-    ckt[(size_t)l * ldg + j] = v;
+__device__ __forceinline__ double app_sign(int f, int n) { return ((n - 1 - f) & 1) ? -1.0 : 1.0; }
+
+// CkT[l][j] = s_l * Ck[j][l] for j < n_ket, 0 for the padding columns; s_l = (-1)^(n-1-f'_l) when an
+// excitation table is given (rank-update tier), 1 otherwise.  Tiled through shared memory: both
+// the reads (rows of Ck) and the writes (a contiguous block of CkT rows) are coalesced.
+constexpr int CKT_TL = 64;   // ket excitations per CTA
+__global__ void __launch_bounds__(256)
+ckt_kernel(const double *__restrict__ Ck, int kk, int kk_pad, int n_ket, const int32_t *__restrict__ exc, int n,
+           int ldg, double *__restrict__ ckt) {
+    extern __shared__ double ckt_sm[];   // CKT_TL x (ldg + 1)
+    const int l0 = blockIdx.x * CKT_TL;
+    const int rows = min(CKT_TL, kk_pad - l0);   // rows in [kk, kk_pad) are written as zeros
+    const int lds = ldg + 1;
+    for (int idx = threadIdx.x; idx < ldg * CKT_TL; idx += 256) {
+        const int j = idx / CKT_TL, r = idx - j * CKT_TL;
+        double v = 0.0;
+        if (j < n_ket && l0 + r < kk) {
+            v = Ck[(size_t)j * kk + l0 + r];
+            if (exc) {
+                const int f = exc[2 * (l0 + r)];
+                if (f >= 0) v *= app_sign(f, n);
+            }
+        }
+        ckt_sm[r * lds + j] = v;
+    }
+    __syncthreads();
+    double *dst = ckt + (size_t)l0 * ldg;
+    for (int idx = threadIdx.x; idx < rows * ldg; idx += 256) {
+        const int r = idx / ldg, j = idx - r * ldg;
+        dst[idx] = ckt_sm[r * lds + j];
+    }
 }
 
 // W buffer (v+1) x (v+1), ld = v+1: top-left = Dv block of S_MO, zero border
@@ -39,8 +61,6 @@ __global__ void w_init_kernel(const double *__restrict__ S, int ld_s, int n, int
     int r = (int)(idx / ldw), c = (int)(idx - (long long)r * ldw);
     Wb[idx] = (r < v && c < v) ? S[(size_t)(n + r) * ld_s + n + c] : 0.0;
 }
-
-__device__ __forceinline__ double app_sign(int f, int n) { return ((n - 1 - f) & 1) ? -1.0 : 1.0; }
 
 // bra side of the rank-update tier.  exc points at the first excitation of the shard.
 // X is v x n.  dk0[k] = D(k, GS) = s_k det(A) X[t,f].
@@ -79,6 +99,124 @@ __global__ void t1_prep_ket_kernel(const int32_t *__restrict__ exc, int kk, int 
     d0l[l] = s * detA * m.y;
 }
 
+// both sides in one launch: the first cdiv(ksh+1,256) CTAs do the bra table, the rest the ket table.
+// Bra row ksh is a virtual ground-state row (x = 1, zero row of W): its pair values are y_l, so its
+// row of G is w_j = sum_l D(0,l) Ck[j][l], the ket-side factor of the cross term, for free.
+__global__ void __launch_bounds__(256)
+t1_prep_kernel(const int32_t *__restrict__ bra_exc, int ksh, const int32_t *__restrict__ ket_exc, int kk, int kk_pad,
+               int n, int v,
+               const double *__restrict__ X, const double *__restrict__ Y, const BaseInfo *__restrict__ info,
+               BraMeta *__restrict__ bmeta, double *__restrict__ bscale, double *__restrict__ dk0,
+               KetMeta *__restrict__ kmeta, double *__restrict__ d0l) {
+    const int nb_bra = (ksh + 1 + 255) / 256;   // + the virtual ground-state row k = ksh
+    const double detA = info->det;
+    if ((int)blockIdx.x < nb_bra) {
+        const int k = blockIdx.x * 256 + threadIdx.x;
+        if (k > ksh) return;
+        const int f = (k < ksh) ? bra_exc[2 * k] : -1, t = (k < ksh) ? bra_exc[2 * k + 1] : -1;
+        BraMeta m;
+        double s;
+        if (f < 0) { m.f = 0; m.woff = v * (v + 1); m.x = 1.0; s = 1.0; }
+        else { m.f = f; m.woff = t * (v + 1); m.x = X[(size_t)t * n + f]; s = app_sign(f, n); }
+        bmeta[k] = m;
+        bscale[k] = s * detA;
+        dk0[k] = s * detA * m.x;
+    } else {
+        const int l = (blockIdx.x - nb_bra) * 256 + threadIdx.x;
+        if (l >= kk_pad) return;
+        if (l >= kk) {   // padding of the last ket tile: a finite pair value times zero coefficients
+            KetMeta z;
+            z.aoff = 0; z.tp = 0; z.y = 0.0;
+            kmeta[l] = z;
+            return;
+        }
+        const int f = ket_exc[2 * l], t = ket_exc[2 * l + 1];
+        KetMeta m;
+        double s;
+        if (f < 0) { m.aoff = 0; m.tp = v; m.y = 1.0; s = 1.0; }
+        else { m.aoff = f * n; m.tp = t; m.y = Y[(size_t)f * v + t]; s = app_sign(f, n); }
+        kmeta[l] = m;
+        d0l[l] = s * detA * m.y;
+    }
+}
+
+// ---- epilogue, two launches ----------------------------------------------------------------------
+// (1) reduce_contract: CTA (z, nt) owns RC_ROWS rows of G and one 8-column tile.  It adds the
+//     partial sums of those elements (fixed order; column n_ket is replaced by D(k,0)) into a shared
+//     slab and contracts it with the bra coefficients on the FP64 tensor cores:
+//     P[z][:, tile] = Cb[:, rows of z] . G_slab (every coefficient is used exactly once per CTA, so
+//     the A fragments come straight from global memory).  Row `gs_row` of G (rank-update tier: the
+//     virtual ground-state bra row, whose G is w_j = sum_l D(0,l) Ck[j][l]) is copied to wvec instead.
+// (2) finalize: CTA i adds the slabs (fixed order) and writes
+//     out[i][j] = D00 * sum_z P[z][i][j] + sigma * (sum_z P[z][i][n_ket]) * w_j.
+constexpr int RC_ROWS = 128;
+
+__global__ void __launch_bounds__(256)
+reduce_contract_kernel(const double *__restrict__ gpart, PartMap pm, int ksh_g, int ksh, int ldg, int n_ket,
+                       const double *__restrict__ dk0, const double *__restrict__ Cb, int ld_cb, int n_bra,
+                       double *__restrict__ P, double *__restrict__ wvec, int gs_row) {
+    __shared__ double Gs[RC_ROWS * 8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int k0 = blockIdx.x * RC_ROWS, j0 = blockIdx.y * 8;
+    const size_t part_stride = (size_t)ksh_g * ldg;
+#pragma unroll
+    for (int e = 0; e < RC_ROWS * 8 / 256; e++) {
+        const int idx = tid + e * 256;
+        const int r = idx >> 3, j = j0 + (idx & 7);
+        const int k = k0 + r;
+        double v = 0.0;
+        if (k < ksh_g) {
+            if (j == n_ket) {
+                v = (k < ksh) ? dk0[k] : 0.0;
+            } else {
+                const int np = parts_of_row(pm, k);
+                const double *src = gpart + (size_t)k * ldg + j;
+                for (int p = 0; p < np; p++) v += src[p * part_stride];
+                if (k == gs_row && j < n_ket) wvec[j] = v;
+            }
+        }
+        Gs[idx] = v;
+    }
+    __syncthreads();
+    double *Pz = P + (size_t)blockIdx.x * n_bra * ldg;
+    const int kmax = ksh - k0;   // rows r >= kmax carry no bra coefficient (padding / the ground-state row)
+    for (int mt = warp; mt * 8 < n_bra; mt += 8) {
+        const int i = 8 * mt + g;
+        const double *arow = Cb + (size_t)(i < n_bra ? i : 0) * ld_cb + k0 + t;
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll 8
+        for (int ks = 0; ks < RC_ROWS / 4; ks++) {
+            const double a = (i < n_bra && 4 * ks + t < kmax) ? __ldg(arow + 4 * ks) : 0.0;
+            dmma884(c0, c1, a, Gs[(4 * ks + t) * 8 + g]);
+        }
+        if (i < n_bra) *reinterpret_cast<double2 *>(Pz + (size_t)i * ldg + j0 + 2 * t) = make_double2(c0, c1);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+finalize3_kernel(const double *__restrict__ P, int n_slabs, int n_bra, int ldg, int n_ket,
+                 const double *__restrict__ wparts, int n_wparts, const double *__restrict__ d00,
+                 double sigma, double *__restrict__ out, int ld_out) {
+    __shared__ double ra[4][64];
+    __shared__ double tot[64];
+    const int i = blockIdx.x, tid = threadIdx.x;
+    const int j = tid & 63, q = tid >> 6;
+    const size_t slab = (size_t)n_bra * ldg;
+    double a = 0.0;
+    if (j < ldg)
+        for (int z = q; z < n_slabs; z += 4) a += P[z * slab + (size_t)i * ldg + j];
+    ra[q][j] = a;
+    __syncthreads();
+    if (q == 0) tot[j] = (ra[0][j] + ra[1][j]) + (ra[2][j] + ra[3][j]);
+    __syncthreads();
+    if (q == 0 && j < n_ket) {
+        double w = 0.0;
+        for (int p = 0; p < n_wparts; p++) w += wparts[p * ldg + j];
+        out[(size_t)i * ld_out + j] = (*d00) * tot[j] + sigma * tot[n_ket] * w;
+    }
+}
+
 // G[k][j] = sum_p gpart[p][k][j]  (fixed order);  column n_ket carries dk0[k].
 __global__ void sum_parts_kernel(const double *__restrict__ gpart, int n_parts, int ksh, int ldg,
                                  int n_ket, const double *__restrict__ dk0, double *__restrict__ G) {
@@ -95,7 +233,7 @@ __global__ void sum_parts_kernel(const double *__restrict__ gpart, int n_parts, 
 // wpart[z][j] = sum over slab z of Ck[j][l] * d0l[l]  (grid (n_ket, KGS_SLABS), fixed-shape tree)
 constexpr int KGS_SLABS = 8;
 __global__ void __launch_bounds__(256)
-ket_gs_dot_kernel(const double *__restrict__ Ck, int kk, int n_ket, const double *__restrict__ d0l,
+ket_gs_dot_kernel(const double *__restrict__ Ck, int kk, int n_ket, int ldw, const double *__restrict__ d0l,
                   double *__restrict__ wpart) {
     __shared__ double red[256];
     const int j = blockIdx.x, z = blockIdx.y;
@@ -109,7 +247,7 @@ ket_gs_dot_kernel(const double *__restrict__ Ck, int kk, int n_ket, const double
         if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) wpart[z * n_ket + j] = red[0];
+    if (threadIdx.x == 0) wpart[z * ldw + j] = red[0];
 }
 
 // out[i][j] = d00 * sum_z P[z][i][j] + sigma * (sum_z P[z][i][n_ket]) * sum_z wpart[z][j]

@@ -16,11 +16,19 @@
 // (CkTs = s_l * Ck^T, zero padded to ldg columns).  Pair values never reach HBM
 // (pywfo/main.py:613-626 is the loop this replaces).
 //
-// CTA = 4 warps, 96 bra excitations (3 m-tiles of 8 per warp, 168 registers, 3 CTAs/SM);
-// persistent CTAs fetch (k tile, l split) work items from an atomic counter; the ket
+// ONE persistent CTA per SM: 12 warps x 24 bra excitations (3 m-tiles of 8 per warp, 168
+// registers) = 288 bra excitations per bra tile.  Work decomposition is "stream-K": the iteration
+// space (bra tile, ket tile of 32) is cut into gridDim.x equal contiguous ranges, one per CTA, so
+// every SM executes the same number of inner iterations (+-1) whatever the shard size -- no wave
+// quantisation, no atomic work counter, a static and therefore run-to-run deterministic summation
+// order.  (Several CTAs per SM with equal static shares do NOT work: the warp schedulers favour
+// the older CTA and the younger ones finish ~15 % later, measured.)  A CTA whose range crosses a bra-tile boundary flushes its accumulators into
+// the partial-sum slot gpart[part] of that bra tile (part = rank of the CTA among the CTAs that
+// touch the tile, see t1_part_range); the epilogue kernel adds the few parts of each tile.  The ket
 // coefficient tiles (32 excitations x ldg, one contiguous block of CkTs) are staged in shared
-// memory by TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP), double buffered, and
-// shared by the 4 warps.  Ai and W are gathered
+// memory by TMA bulk copies (cp.async.bulk, SASS UBLKCP) through a 4-stage ring with full/empty
+// mbarriers -- no block barrier in the main loop; the 12 warps share every tile and may drift by
+// up to three tiles.  Ai and W are gathered
 // through L1 (the host orders the ket excitations so that a CTA's working set
 // of W is a few KB at a time, see pywfo_b200/excitations.py).
 #pragma once
@@ -29,21 +37,22 @@
 namespace wfo {
 
 #ifndef WFO_T1_WARPS
-#define WFO_T1_WARPS 4
+#define WFO_T1_WARPS 12
+#endif
+#ifndef WFO_T1_STAGES
+#define WFO_T1_STAGES 4
 #endif
 #ifndef WFO_T1_MT
 #define WFO_T1_MT 3
 #endif
-#ifndef WFO_T1_MINB
-#define WFO_T1_MINB 3
-#endif
 constexpr int T1_WARPS = WFO_T1_WARPS;
 constexpr int T1_MT = WFO_T1_MT;                 // m-tiles (8 bra excitations) per warp
-constexpr int T1_KTILE = T1_WARPS * T1_MT * 8;   // 128 bra excitations per CTA
+constexpr int T1_KTILE = T1_WARPS * T1_MT * 8;   // 288 bra excitations per CTA
 #ifndef WFO_T1_LT
 #define WFO_T1_LT 32
 #endif
 constexpr int T1_LT = WFO_T1_LT;                 // ket excitations per shared tile
+constexpr int T1_STAGES = WFO_T1_STAGES;         // depth of the TMA ring
 
 struct KetMeta {   // one per ket excitation (16 bytes)
     int aoff;      // f' * n      (row offset into Ai)
@@ -84,103 +93,157 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
         : "memory");
 }
 
-// NT = ldg / 8 column tiles of G.  Work item = (k tile, l split), fetched dynamically.
-// gpart[(split*ksh + k)*ldg + j]
+__device__ __forceinline__ bool mbar_test(unsigned long long *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// How the partial sums of the fused kernels are laid out: gpart[(part*ksh + k)*ldg + j].
+//   uniform (T0 kernels): every bra row has `uniform_parts` parts;
+//   stream-K (T1): iteration x = ktile*n_ltiles + ltile, CTA c of G owns [c*I/G, (c+1)*I/G);
+//   the CTA that contains x is ((x+1)*G - 1) / I, so bra tile `ktile` is touched by the CTAs
+//   c_first..c_last of its first and last iteration and CTA c writes part c - c_first.
+struct PartMap {
+    long long I;         // total iterations (0 = uniform mode)
+    int G;               // CTAs
+    int n_ltiles;        // ket tiles per bra tile
+    int ktile_rows;      // bra rows per tile
+    int uniform_parts;
+};
+__host__ __device__ inline int t1_cta_of_iter(const PartMap &pm, long long x) {
+    return (int)(((x + 1) * pm.G - 1) / pm.I);
+}
+__host__ __device__ inline void t1_part_range(const PartMap &pm, int ktile, int &c_first, int &n_parts) {
+    const long long x0 = (long long)ktile * pm.n_ltiles;
+    c_first = t1_cta_of_iter(pm, x0);
+    n_parts = t1_cta_of_iter(pm, x0 + pm.n_ltiles - 1) - c_first + 1;
+}
+__host__ __device__ inline int parts_of_row(const PartMap &pm, int k) {
+    if (pm.I == 0) return pm.uniform_parts;
+    int c_first, n_parts;
+    t1_part_range(pm, k / pm.ktile_rows, c_first, n_parts);
+    return n_parts;
+}
+
+#ifdef WFO_T1_CLOCKS
+__device__ long long g_t1_clk[2048][4];   // per CTA: elapsed clocks, SM id, start (globaltimer ns), end
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
+
+// NT = ldg / 8 column tiles of G.  One persistent CTA per SM; ckts and ket are padded with zero
+// rows to a multiple of T1_LT excitations, so every tile is a full tile.
 template <int NT>
-__global__ void __launch_bounds__(T1_WARPS * 32, WFO_T1_MINB)
+constexpr size_t t1_smem_bytes() { return (size_t)T1_STAGES * (T1_LT * NT * 8 * sizeof(double) + T1_LT * sizeof(KetMeta)); }
+
+template <int NT>
+__global__ void __launch_bounds__(T1_WARPS * 32, 1)
 t1_fused_kernel(const double *__restrict__ Ai, const double *__restrict__ W,
                 const BraMeta *__restrict__ bra, const double *__restrict__ bra_scale, int ksh,
                 const KetMeta *__restrict__ ket, const double *__restrict__ ckts, int kk,
-                int l_per_split, int n_ktiles, int n_items, int *__restrict__ counter,
-                double *__restrict__ gpart) {
+                PartMap pm, double *__restrict__ gpart) {
     constexpr int LDG = NT * 8;
-    __shared__ __align__(128) double Bs[2][T1_LT * LDG];
-    __shared__ __align__(16) KetMeta Ms[2][T1_LT];
-    __shared__ __align__(8) unsigned long long full_bar[2];   // "tile landed" barriers of the two stages
-    __shared__ int s_item;
+    constexpr unsigned TILE_BYTES = T1_LT * LDG * sizeof(double), META_BYTES = T1_LT * sizeof(KetMeta);
+    extern __shared__ __align__(128) unsigned char t1_sm[];
+    double *Bs = reinterpret_cast<double *>(t1_sm);                                       // [stage][T1_LT * LDG]
+    KetMeta *Ms = reinterpret_cast<KetMeta *>(t1_sm + (size_t)T1_STAGES * TILE_BYTES);   // [stage][T1_LT]
+    __shared__ __align__(8) unsigned long long full_bar[T1_STAGES];    // "tile landed" (TMA transaction count)
+    __shared__ __align__(8) unsigned long long empty_bar[T1_STAGES];   // "all warps are done with the tile"
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     if (tid == 0) {
-        mbar_init(&full_bar[0], 1);
-        mbar_init(&full_bar[1], 1);
+#pragma unroll
+        for (int s = 0; s < T1_STAGES; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], T1_WARPS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    unsigned phase0 = 0, phase1 = 0;   // parity of the next completion of each stage barrier
     __syncthreads();
-  for (;;) {
-    if (tid == 0) s_item = atomicAdd(counter, 1);
-    __syncthreads();
-    const int item = s_item;
-    __syncthreads();
-    if (item >= n_items) break;
-    const int split = item / n_ktiles, ktile = item - split * n_ktiles;
-    const int k0 = ktile * T1_KTILE + warp * (T1_MT * 8);
-    const int l_begin = split * l_per_split;
-    const int l_end = min(kk, l_begin + l_per_split);
+#ifdef WFO_T1_CLOCKS
+    const long long dbg_c0 = clock64();
+    const unsigned long long dbg_g0 = gtimer();
+#endif
+    const long long it0 = ((long long)blockIdx.x * pm.I) / pm.G;
+    const int Q = (int)(((long long)(blockIdx.x + 1) * pm.I) / pm.G - it0);   // ket tiles this CTA consumes
 
-    // per-thread bra data for its 4 rows (one per m-tile)
-    int bf[T1_MT], bw[T1_MT];
-    double bx[T1_MT];
-#pragma unroll
-    for (int mi = 0; mi < T1_MT; mi++) {
-        int k = k0 + 8 * mi + g;
-        if (k < ksh) {
-            BraMeta m = bra[k];
-            bf[mi] = m.f; bw[mi] = m.woff; bx[mi] = m.x;
-        } else {
-            bf[mi] = 0; bw[mi] = 0; bx[mi] = 0.0;   // harmless duplicates, never stored
-        }
-    }
-    double acc[T1_MT][NT][2];
-#pragma unroll
-    for (int mi = 0; mi < T1_MT; mi++)
-#pragma unroll
-        for (int ni = 0; ni < NT; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-
-    // stage one tile of ket data with TMA: the coefficient rows of T1_LT consecutive ket
-    // excitations are one contiguous block of CkTs (T1_LT * LDG * 8 bytes), their metadata another;
-    // one thread issues two bulk copies that complete on the stage's mbarrier.  Rows beyond the
-    // end of the split are zero-filled by the other threads (different addresses).
-    auto stage = [&](int buf, int l0) {
-        const int rows = min(T1_LT, l_end - l0);
-        if (tid == 0) {
-            mbar_expect_tx(&full_bar[buf], (unsigned)(rows * (LDG * 8 + 16)));
-            tma_bulk_g2s(&Bs[buf][0], ckts + (size_t)l0 * LDG, (unsigned)(rows * LDG * 8), &full_bar[buf]);
-            tma_bulk_g2s(&Ms[buf][0], ket + l0, (unsigned)(rows * 16), &full_bar[buf]);
-        }
-        if (rows < T1_LT) {
-            for (int c = rows * LDG + tid; c < T1_LT * LDG; c += T1_WARPS * 32) Bs[buf][c] = 0.0;
-            for (int r = rows + tid; r < T1_LT; r += T1_WARPS * 32) { Ms[buf][r].aoff = 0; Ms[buf][r].tp = 0; Ms[buf][r].y = 0.0; }
+    // ---- producer (warp 0; lane 0 issues): tile i of this CTA goes to stage i % T1_STAGES once every
+    // warp has released the tile that used the stage before.  Non-blocking except when the tile is
+    // needed right now, so the warp never waits for slower warps longer than the ring allows.
+    int issued = 0;
+    auto produce_upto = [&](int target, bool blocking) {
+        if (target > Q) target = Q;
+        while (issued < target) {
+            const int s = issued % T1_STAGES;
+            if (issued >= T1_STAGES) {
+                const unsigned par = (unsigned)((issued / T1_STAGES) - 1) & 1u;
+                if (blocking) mbar_wait(&empty_bar[s], par);
+                else if (!mbar_test(&empty_bar[s], par)) break;
+            }
+            if (lane == 0) {
+                const int l0 = (int)((it0 + issued) % pm.n_ltiles) * T1_LT;
+                mbar_expect_tx(&full_bar[s], TILE_BYTES + META_BYTES);
+                tma_bulk_g2s(Bs + (size_t)s * T1_LT * LDG, ckts + (size_t)l0 * LDG, TILE_BYTES, &full_bar[s]);
+                tma_bulk_g2s(Ms + (size_t)s * T1_LT, ket + l0, META_BYTES, &full_bar[s]);
+            }
+            issued++;
         }
     };
+    if (warp == 0) produce_upto(T1_STAGES, false);
 
-    int buf = 0;
-    if (l_begin < l_end) stage(0, l_begin);
-    for (int l0 = l_begin; l0 < l_end; l0 += T1_LT) {
-        if (l0 + T1_LT < l_end) stage(buf ^ 1, l0 + T1_LT);
-        if (buf == 0) { mbar_wait(&full_bar[0], phase0); phase0 ^= 1; }
-        else { mbar_wait(&full_bar[1], phase1); phase1 ^= 1; }
-        __syncthreads();   // also publishes the zero fill of a partial tile
-        const double *bs = &Bs[buf][0];
-        const KetMeta *ms = &Ms[buf][0];
-        // software pipeline over the 8 k-steps (4 ket excitations each): gather one step ahead
-        double a_cur[T1_MT], ai_n[T1_MT], w_n[T1_MT], y_n;
-        {
-            KetMeta m = ms[t];
-            y_n = m.y;
+    int q = 0;
+    while (q < Q) {
+        const long long it = it0 + q;
+        const int ktile = (int)(it / pm.n_ltiles);
+        const int lt0 = (int)(it - (long long)ktile * pm.n_ltiles);
+        const int cnt = min(pm.n_ltiles - lt0, Q - q);
+        const int split = (int)blockIdx.x - t1_cta_of_iter(pm, (long long)ktile * pm.n_ltiles);
+        const int k0 = ktile * T1_KTILE + warp * (T1_MT * 8);
+
+        // per-thread bra data for its rows (one per m-tile)
+        int bf[T1_MT], bw[T1_MT];
+        double bx[T1_MT];
 #pragma unroll
-            for (int mi = 0; mi < T1_MT; mi++) {
-                ai_n[mi] = __ldg(Ai + m.aoff + bf[mi]);
-                w_n[mi] = __ldg(W + bw[mi] + m.tp);
+        for (int mi = 0; mi < T1_MT; mi++) {
+            const int k = k0 + 8 * mi + g;
+            if (k < ksh) {
+                const BraMeta m = bra[k];
+                bf[mi] = m.f; bw[mi] = m.woff; bx[mi] = m.x;
+            } else {
+                bf[mi] = 0; bw[mi] = 0; bx[mi] = 0.0;   // harmless duplicates, never stored
             }
         }
+        double acc[T1_MT][NT][2];
 #pragma unroll
-        for (int ks = 0; ks < T1_LT / 4; ks++) {
+        for (int mi = 0; mi < T1_MT; mi++)
 #pragma unroll
-            for (int mi = 0; mi < T1_MT; mi++) a_cur[mi] = fma(bx[mi], y_n, ai_n[mi] * w_n[mi]);
-            if (ks + 1 < T1_LT / 4) {
-                KetMeta m = ms[4 * (ks + 1) + t];
+            for (int ni = 0; ni < NT; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+        for (int j = 0; j < cnt; j++, q++) {
+            const int s = q % T1_STAGES;
+            if (warp == 0) {
+                produce_upto(q + 1, true);
+                produce_upto(q + T1_STAGES, false);
+            }
+            mbar_wait(&full_bar[s], (unsigned)(q / T1_STAGES) & 1u);
+            const double *bs = Bs + (size_t)s * T1_LT * LDG;
+            const KetMeta *ms = Ms + (size_t)s * T1_LT;
+            // software pipeline over the 8 k-steps (4 ket excitations each): gather one step ahead
+            double a_cur[T1_MT], ai_n[T1_MT], w_n[T1_MT], y_n;
+            {
+                const KetMeta m = ms[t];
                 y_n = m.y;
 #pragma unroll
                 for (int mi = 0; mi < T1_MT; mi++) {
@@ -188,32 +251,56 @@ t1_fused_kernel(const double *__restrict__ Ai, const double *__restrict__ W,
                     w_n[mi] = __ldg(W + bw[mi] + m.tp);
                 }
             }
-            double b[NT];
 #pragma unroll
-            for (int ni = 0; ni < NT; ni++) b[ni] = bs[(4 * ks + t) * LDG + 8 * ni + g];
+            for (int ks = 0; ks < T1_LT / 4; ks++) {
 #pragma unroll
-            for (int mi = 0; mi < T1_MT; mi++)
+                for (int mi = 0; mi < T1_MT; mi++) a_cur[mi] = fma(bx[mi], y_n, ai_n[mi] * w_n[mi]);
+                if (ks + 1 < T1_LT / 4) {
+                    const KetMeta m = ms[4 * (ks + 1) + t];
+                    y_n = m.y;
 #pragma unroll
-                for (int ni = 0; ni < NT; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a_cur[mi], b[ni]);
+                    for (int mi = 0; mi < T1_MT; mi++) {
+                        ai_n[mi] = __ldg(Ai + m.aoff + bf[mi]);
+                        w_n[mi] = __ldg(W + bw[mi] + m.tp);
+                    }
+                }
+                double b[NT];
+#pragma unroll
+                for (int ni = 0; ni < NT; ni++) b[ni] = bs[(4 * ks + t) * LDG + 8 * ni + g];
+#pragma unroll
+                for (int mi = 0; mi < T1_MT; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < NT; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a_cur[mi], b[ni]);
+                if (ks == T1_LT / 8 - 1 && warp == 0) produce_upto(q + T1_STAGES, false);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);   // this warp is done with the stage
         }
-        __syncthreads();
-        buf ^= 1;
-    }
 
-    // epilogue: row scale s_k * det(A) and store this split's partial
+        // flush: row scale s_k * det(A), store into this CTA's partial-sum slot of the bra tile
 #pragma unroll
-    for (int mi = 0; mi < T1_MT; mi++) {
-        int k = k0 + 8 * mi + g;
-        if (k >= ksh) continue;
-        double sc = bra_scale[k];
-        double *dst = gpart + ((size_t)split * ksh + k) * LDG + 2 * t;
+        for (int mi = 0; mi < T1_MT; mi++) {
+            const int k = k0 + 8 * mi + g;
+            if (k >= ksh) continue;
+            const double sc = bra_scale[k];
+            double *dst = gpart + ((size_t)split * ksh + k) * LDG + 2 * t;
 #pragma unroll
-        for (int ni = 0; ni < NT; ni++) {
-            double2 v = make_double2(sc * acc[mi][ni][0], sc * acc[mi][ni][1]);
-            *reinterpret_cast<double2 *>(dst + 8 * ni) = v;
+            for (int ni = 0; ni < NT; ni++) {
+                const double2 v = make_double2(sc * acc[mi][ni][0], sc * acc[mi][ni][1]);
+                *reinterpret_cast<double2 *>(dst + 8 * ni) = v;
+            }
         }
     }
-  }
+#ifdef WFO_T1_CLOCKS
+    if (tid == 0 && blockIdx.x < 2048) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_t1_clk[blockIdx.x][0] = clock64() - dbg_c0;
+        g_t1_clk[blockIdx.x][1] = smid;
+        g_t1_clk[blockIdx.x][2] = (long long)dbg_g0;
+        g_t1_clk[blockIdx.x][3] = (long long)gtimer();
+    }
+#endif
 }
 
 }  // namespace wfo
