@@ -38,6 +38,12 @@ extern "C" {
 #define WFO_ERR_ARG 2
 #define WFO_ERR_SINGULAR 3 /* base block S_MO[:occ,:occ] singular: tier 1/2 not applicable */
 #define WFO_ERR_EMPTY_STATE 4 /* pywfo.main.overlaps semantics: a state keeps no excitation (ValueError upstream) */
+#define WFO_ERR_NOCONV 5 /* device inverse did not converge (singular / extremely ill-conditioned MO matrix) */
+
+/* where the inverse of the MO matrix in S_AO = C^-1 C^-T (pywfo/main.py:301-311) comes from */
+#define WFO_AO_GIVEN 0 /* the caller supplies c_inv (e.g. np.linalg.inv, exactly as upstream) */
+#define WFO_AO_BRA 1   /* ao_ovlps="bra": bra_mos is inverted on the device */
+#define WFO_AO_KET 2   /* ao_ovlps="ket": ket_mos is inverted on the device */
 
 /* algorithm tiers (identical results to ~1e-13) */
 #define WFO_TIER_LU 0      /* T0: one partially pivoted LU per determinant pair          */
@@ -70,6 +76,14 @@ int wfo_smo_host(wfo_ctx *ctx, const double *bra_mos, const double *s_ao, const 
 /* S_AO = Cinv Cinv^T, replaces the product in pywfo/main.py:304 (the inverse
  * itself stays numpy/LAPACK on the host, as in the reference). */
 int wfo_sao_dev(wfo_ctx *ctx, const double *c_inv, int n, double *s_ao, void *stream);
+/* a_inv = a^-1 (n x n), replaces np.linalg.inv in pywfo/main.py:303 (98, 212): Newton-Schulz
+ * iteration X <- X (2I - A X) from X0 = A^T / (|A|_1 |A|_inf), i.e. nothing but FP64 tensor-core
+ * GEMMs; quadratically convergent for every non-singular A, about 2 log2(cond) + 10 iterations.
+ * `work` = 2 n*n doubles of device scratch (NULL: from the context).  Synchronises the stream
+ * every few iterations to read the residual max|A X - I|.  WFO_ERR_NOCONV if it does not
+ * converge within 100 iterations (the Python layer then falls back to LAPACK). */
+int wfo_inverse_dev(wfo_ctx *ctx, const double *a, int n, double *a_inv, double *work, void *stream);
+int wfo_inverse_host(wfo_ctx *ctx, const double *a, int n, double *a_inv);
 /* generic C = alpha*op(A) op(B) + beta*C (row-major; ta/tb: 0 = N, 1 = T) */
 int wfo_gemm_dev(wfo_ctx *ctx, int ta, int tb, int m, int n, int k, double alpha, const double *A,
                  int lda, const double *B, int ldb, double beta, double *C, int ldc, void *stream);
@@ -121,12 +135,13 @@ int wfo_overlaps_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos
  * sigma=+1: overlaps_cache / overlaps_naive / overlaps_most_naive) or main.py:112,122-123
  * (|c| > thr, semantics 1, sigma=-1 and the sign^occ factor of main.py:154,176: overlaps)
  * -- runs on the device too, so the host only supplies bra_ci (n_bra, n_occ, n_virt),
- * ket_ci (n_ket, n_occ, n_virt) and the MO matrices.  The bra excitations are sharded
+ * ket_ci (n_ket, n_occ, n_virt) and the MO matrices.  ao_side (WFO_AO_*) says whether c_inv is
+ * supplied (WFO_AO_GIVEN) or computed on the device from bra_mos / ket_mos (c_inv may be NULL).  The bra excitations are sharded
  * over `world` ranks ([rank] gets a contiguous, balanced slice); `out` is this rank's
  * partial matrix.  info (may be NULL) receives {K_bra, K_ket, empty_state, tier_used}.
  * Returns WFO_ERR_EMPTY_STATE for semantics 1 when a state keeps no excitation. */
 int wfo_overlaps_ci_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos,
-                         const double *c_inv, int n_mo, int n_occ, const double *bra_ci, int n_bra,
+                         const double *c_inv, int ao_side, int n_mo, int n_occ, const double *bra_ci, int n_bra,
                          const double *ket_ci, int n_ket, double ci_thresh, int semantics, int tier,
                          int rank, int world, double *out, int32_t *info);
 /* tier actually used by the last wfo_state_overlaps_* call of this context */

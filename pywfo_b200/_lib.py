@@ -45,7 +45,9 @@ SIGNATURES = {
                                           c_vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, c_vp]),
     "wfo_overlaps_host": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, C.c_int, c_vp, C.c_int, c_vp,
                                     C.c_int, c_vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, c_vp]),
-    "wfo_overlaps_ci_host": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, C.c_int, c_vp, C.c_int,
+    "wfo_inverse_dev": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp]),
+    "wfo_inverse_host": (C.c_int, [c_vp, c_vp, C.c_int, c_vp]),
+    "wfo_overlaps_ci_host": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, c_vp, C.c_int,
                                        C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
     "wfo_last_tier": (C.c_int, [c_vp]),
     "wfo_set_timing": (C.c_int, [c_vp, C.c_int]),
@@ -55,8 +57,14 @@ SIGNATURES = {
 }
 
 
+AO_GIVEN, AO_BRA, AO_KET = 0, 1, 2
+ERR_NOCONV = 5
+
+
 class WfoError(RuntimeError):
-    pass
+    def __init__(self, msg, code=None):
+        super().__init__(msg)
+        self.code = code
 
 
 _lib = None
@@ -85,7 +93,7 @@ def load():
 def check(rc: int):
     if rc != 0:
         msg = load().wfo_last_error().decode("utf-8", "replace")
-        raise WfoError(f"wfo_b200 error {rc}: {msg}")
+        raise WfoError(f"wfo_b200 error {rc}: {msg}", code=rc)
 
 
 def _hptr(a: np.ndarray):
@@ -173,20 +181,37 @@ class Context:
                                          _hptr(out)))
         return out
 
+    def inverse_host(self, a):
+        """a^-1 on the device (Newton-Schulz on the DMMA GEMM); raises WfoError(code=ERR_NOCONV)
+        when the iteration does not converge."""
+        a = as_f64(a)
+        n = a.shape[0]
+        if a.shape != (n, n):
+            raise ValueError("inverse needs a square matrix")
+        out = np.empty((n, n))
+        check(self.lib.wfo_inverse_host(self.handle, _hptr(a), n, _hptr(out)))
+        return out
+
     def overlaps_ci_host(self, bra_mos, ket_mos, c_inv, n_occ, bra_ci, ket_ci, ci_thresh, semantics=0,
-                         tier="auto", rank=0, world=1):
-        """Whole path from raw CI tensors; excitation selection on the device.
+                         tier="auto", rank=0, world=1, ao_side=AO_GIVEN):
+        """Whole path from raw CI tensors; excitation selection on the device.  ``c_inv`` is the
+        inverse of the MO matrix behind S_AO (``ao_side=AO_GIVEN``) or None with ``ao_side`` =
+        AO_BRA / AO_KET: the inverse is then computed on the device.
         Returns (partial matrix, info = [K_bra, K_ket, empty_state, tier_used])."""
-        bra, ket, inv = as_f64(bra_mos), as_f64(ket_mos), as_f64(c_inv)
+        bra, ket = as_f64(bra_mos), as_f64(ket_mos)
+        inv = as_f64(c_inv) if c_inv is not None else None
+        if inv is None and ao_side == AO_GIVEN:
+            raise ValueError("c_inv is None: pass ao_side=AO_BRA or AO_KET")
         bci, kci = as_f64(bra_ci), as_f64(ket_ci)
         n_mo = bra.shape[0]
-        if bra.shape != (n_mo, n_mo) or ket.shape != (n_mo, n_mo) or inv.shape != (n_mo, n_mo):
+        if bra.shape != (n_mo, n_mo) or ket.shape != (n_mo, n_mo) or (inv is not None and inv.shape != (n_mo, n_mo)):
             raise ValueError("MO matrices must be square and of equal shape")
         if bci.ndim != 3 or kci.ndim != 3 or bci.shape[1:] != (n_occ, n_mo - n_occ) or kci.shape[1:] != bci.shape[1:]:
             raise ValueError("CI coefficients must have shape (n_states, occ, n_mo - occ)")
         out = np.empty((bci.shape[0], kci.shape[0]))
         info = np.zeros(4, dtype=np.int32)
-        rc = self.lib.wfo_overlaps_ci_host(self.handle, _hptr(bra), _hptr(ket), _hptr(inv), n_mo, int(n_occ),
+        rc = self.lib.wfo_overlaps_ci_host(self.handle, _hptr(bra), _hptr(ket), _hptr(inv) if inv is not None else None,
+                                           int(ao_side if inv is None else AO_GIVEN), n_mo, int(n_occ),
                                            _hptr(bci), bci.shape[0], _hptr(kci), kci.shape[0], float(ci_thresh),
                                            int(semantics), TIERS[tier], int(rank), int(world), _hptr(out),
                                            _hptr(info))

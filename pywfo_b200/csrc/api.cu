@@ -80,26 +80,39 @@ static int gemm(wfo_ctx *ctx, bool ta, bool tb, int m, int n, int k, double alph
     const bool small = (long long)cdiv(n, GN) * cdiv(m, 64) * nz < ctx->sm_count;
     const int gm = small ? 32 : 64;
     dim3 grid(cdiv(n, GN), cdiv(m, gm), nz), block(128);
-#define GEMM_LAUNCH(TA_, TB_)                                                                                     \
+    // 16-byte async copies need even leading dimensions / slab starts / batch strides and aligned bases
+    const bool vec = !ta && !((lda | ldb) & 1) && !(((uintptr_t)A | (uintptr_t)B) & 15) &&
+                     !((batch_a | batch_b) & 1) && (nz == 1 || batch > 0 || !(kslab & 1));
+#define GEMM_LAUNCH2(TA_, TB_, GM_, VEC_)                                                                         \
     do {                                                                                                          \
         static bool attr_done_ = false;                                                                           \
         if (!attr_done_) {                                                                                        \
-            WFO_CUDA(cudaFuncSetAttribute(gemm_f64_kernel<TA_, TB_, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          (int)gemm_smem_bytes<32>()));                                           \
-            WFO_CUDA(cudaFuncSetAttribute(gemm_f64_kernel<TA_, TB_, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          (int)gemm_smem_bytes<64>()));                                           \
+            WFO_CUDA(cudaFuncSetAttribute(gemm_f64_kernel<TA_, TB_, GM_, VEC_>,                                   \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<GM_>())); \
             attr_done_ = true;                                                                                    \
         }                                                                                                         \
-        if (small) gemm_f64_kernel<TA_, TB_, 32><<<grid, block, gemm_smem_bytes<32>(), st>>>(                     \
-            m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kslab, slab_stride, batch_a, batch_b);                  \
-        else gemm_f64_kernel<TA_, TB_, 64><<<grid, block, gemm_smem_bytes<64>(), st>>>(                           \
+        gemm_f64_kernel<TA_, TB_, GM_, VEC_><<<grid, block, gemm_smem_bytes<GM_>(), st>>>(                        \
             m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kslab, slab_stride, batch_a, batch_b);                  \
     } while (0)
-    if (!ta && !tb) GEMM_LAUNCH(false, false);
+#define GEMM_LAUNCH(TA_, TB_)                                             \
+    do {                                                                  \
+        if (small) { GEMM_LAUNCH2(TA_, TB_, 32, false); }                 \
+        else { GEMM_LAUNCH2(TA_, TB_, 64, false); }                       \
+    } while (0)
+#define GEMM_LAUNCH_V(TB_)                                                \
+    do {                                                                  \
+        if (small) { GEMM_LAUNCH2(false, TB_, 32, true); }                \
+        else { GEMM_LAUNCH2(false, TB_, 64, true); }                      \
+    } while (0)
+    if (vec && !tb) GEMM_LAUNCH_V(false);
+    else if (vec && tb) GEMM_LAUNCH_V(true);
+    else if (!ta && !tb) GEMM_LAUNCH(false, false);
     else if (!ta && tb) GEMM_LAUNCH(false, true);
     else if (ta && !tb) GEMM_LAUNCH(true, false);
     else GEMM_LAUNCH(true, true);
 #undef GEMM_LAUNCH
+#undef GEMM_LAUNCH_V
+#undef GEMM_LAUNCH2
     WFO_LAUNCH_CHECK(ctx);
     return WFO_OK;
 }
@@ -426,6 +439,8 @@ int wfo_create(int device, wfo_ctx **out) {
     WFO_CUDA(cudaEventCreate(&c->ev0));
     WFO_CUDA(cudaEventCreate(&c->ev1));
     for (int i = 0; i < 24; i++) WFO_CUDA(cudaEventCreate(&c->pev[i]));
+    WFO_CUDA(cudaMalloc(&c->ns_slots, 128 * sizeof(double)));
+    WFO_CUDA(cudaMallocHost(&c->h_slots, 128 * sizeof(double)));
     *out = c;
     return WFO_OK;
 }
@@ -436,6 +451,8 @@ int wfo_destroy(wfo_ctx *ctx) {
     cudaDeviceSynchronize();
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->gscratch) cudaFree(ctx->gscratch);
+    if (ctx->ns_slots) cudaFree(ctx->ns_slots);
+    if (ctx->h_slots) cudaFreeHost(ctx->h_slots);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     for (int i = 0; i < 24; i++) cudaEventDestroy(ctx->pev[i]);
@@ -508,6 +525,72 @@ int wfo_smo_dev(wfo_ctx *ctx, const double *bra_mos, const double *s_ao, const d
     // (bra S_AO) then (.) ket^T, the order of pywfo/main.py:532
     WFO_TRY(gemm(ctx, false, false, p, v, u, 1.0, bra_mos, u, s_ao, v, 0.0, work, v, 0, 0, st));
     WFO_TRY(gemm(ctx, false, true, p, q, v, 1.0, work, v, ket_mos, v, 0.0, s_mo, q, 0, 0, st));
+    return WFO_OK;
+}
+
+/* Newton-Schulz inverse on the DMMA GEMM (replaces np.linalg.inv, pywfo/main.py:303) */
+constexpr int NS_MAX_ITERS = 100;
+int wfo_inverse_dev(wfo_ctx *ctx, const double *a, int n, double *a_inv, double *work, void *stream) {
+    if (!ctx || !a || !a_inv) return set_err(WFO_ERR_ARG, "inverse: NULL argument");
+    if (n < 1) return set_err(WFO_ERR_ARG, "inverse: n=%lld", n);
+    WFO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nn = (size_t)n * n;
+    if (!work) {
+        WFO_TRY(ensure_scratch(ctx, 2 * align_up(nn * sizeof(double), 256)));
+        work = reinterpret_cast<double *>(ctx->scratch);
+    }
+    double *T = work, *Xb = work + align_up(nn * sizeof(double), 256) / sizeof(double);
+    double *X = a_inv, *Xn = Xb;   // ping-pong; the result must end in a_inv
+    double *slots = ctx->ns_slots;
+    WFO_CUDA(cudaMemsetAsync(slots, 0, 128 * sizeof(double), st));
+    ns_norms_kernel<<<n, 256, 0, st>>>(a, n, slots);
+    WFO_LAUNCH_CHECK(ctx);
+    ns_init_kernel<<<dim3(cdiv(n, 32), cdiv(n, 32)), dim3(32, 8), 0, st>>>(a, n, slots, X);
+    WFO_LAUNCH_CHECK(ctx);
+    const int rblocks = (int)((nn + 255) / 256 < (size_t)ctx->sm_count * 4 ? (nn + 255) / 256 : (size_t)ctx->sm_count * 4);
+    int it = 0, checked = 0;
+    bool converged = false;
+    ctx->last_inverse_iters = 0;
+    while (it < NS_MAX_ITERS && !converged) {
+        const int batch = (it == 0) ? 10 : 4;   // iterations between two looks at the residuals
+        for (int b = 0; b < batch && it < NS_MAX_ITERS; b++, it++) {
+            // T = A X; residual max|T - I| -> slots[2 + it], Xn = X; Xn = 2 Xn - X T
+            WFO_TRY(gemm(ctx, false, false, n, n, n, 1.0, a, n, X, n, 0.0, T, n, 0, 0, st));
+            ns_residual_kernel<<<rblocks, 256, 0, st>>>(T, X, n, slots + 2 + it, Xn);
+            WFO_LAUNCH_CHECK(ctx);
+            WFO_TRY(gemm(ctx, false, false, n, n, n, -1.0, X, n, T, n, 2.0, Xn, n, 0, 0, st));
+            double *tmp = X; X = Xn; Xn = tmp;
+        }
+        WFO_CUDA(cudaMemcpyAsync(ctx->h_slots, slots, 128 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        WFO_CUDA(cudaStreamSynchronize(st));
+        // the residual seen at iteration i is squared by the update that follows it
+        for (; checked < it; checked++) {
+            const double r = ctx->h_slots[2 + checked];
+            if (!(r < 1e250)) return set_err(WFO_ERR_NOCONV, "inverse: Newton-Schulz diverged (singular matrix?)");
+            if (r < 1e-8) { converged = true; }
+        }
+    }
+    ctx->last_inverse_iters = it;
+    if (!converged)
+        return set_err(WFO_ERR_NOCONV, "inverse: Newton-Schulz did not converge in %lld iterations", it);
+    if (X != a_inv) WFO_CUDA(cudaMemcpyAsync(a_inv, X, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return WFO_OK;
+}
+
+int wfo_inverse_host(wfo_ctx *ctx, const double *a, int n, double *a_inv) {
+    if (!ctx || !a || !a_inv) return set_err(WFO_ERR_ARG, "inverse: NULL argument");
+    if (n < 1) return set_err(WFO_ERR_ARG, "inverse: n=%lld", n);
+    WFO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t nn = (size_t)n * n, blk = align_up(nn * sizeof(double), 256);
+    WFO_TRY(ensure_scratch(ctx, 4 * blk));
+    double *d_a = reinterpret_cast<double *>(ctx->scratch), *d_x = reinterpret_cast<double *>(ctx->scratch + blk),
+           *d_w = reinterpret_cast<double *>(ctx->scratch + 2 * blk);
+    WFO_CUDA(cudaMemcpyAsync(d_a, a, nn * sizeof(double), cudaMemcpyHostToDevice, st));
+    WFO_TRY(wfo_inverse_dev(ctx, d_a, n, d_x, d_w, st));
+    WFO_CUDA(cudaMemcpyAsync(a_inv, d_x, nn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    WFO_CUDA(cudaStreamSynchronize(st));
     return WFO_OK;
 }
 
@@ -996,13 +1079,16 @@ static int build_tables_dev(wfo_ctx *ctx, const double *ci_dev, int n_states, in
     return WFO_OK;
 }
 
-int wfo_overlaps_ci_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos, const double *c_inv, int n_mo,
-                         int n_occ, const double *bra_ci, int n_bra, const double *ket_ci, int n_ket,
+int wfo_overlaps_ci_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos, const double *c_inv, int ao_side,
+                         int n_mo, int n_occ, const double *bra_ci, int n_bra, const double *ket_ci, int n_ket,
                          double ci_thresh, int semantics, int tier, int rank, int world, double *out,
                          int32_t *info) {
     if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL");
-    if (!bra_mos || !ket_mos || !c_inv || !bra_ci || !ket_ci || !out)
+    if (!bra_mos || !ket_mos || !bra_ci || !ket_ci || !out)
         return set_err(WFO_ERR_ARG, "overlaps_ci_host: NULL pointer");
+    if (ao_side != WFO_AO_GIVEN && ao_side != WFO_AO_BRA && ao_side != WFO_AO_KET)
+        return set_err(WFO_ERR_ARG, "overlaps_ci_host: ao_side must be WFO_AO_GIVEN, WFO_AO_BRA or WFO_AO_KET");
+    if (ao_side == WFO_AO_GIVEN && !c_inv) return set_err(WFO_ERR_ARG, "overlaps_ci_host: c_inv is NULL");
     if (n_mo < 1 || n_occ < 1 || n_occ > n_mo || n_bra < 1 || n_ket < 1 || world < 1 || rank < 0 || rank >= world)
         return set_err(WFO_ERR_ARG, "overlaps_ci_host: bad sizes");
     if (semantics != 0 && semantics != 1) return set_err(WFO_ERR_ARG, "overlaps_ci_host: semantics must be 0 or 1");
@@ -1020,6 +1106,7 @@ int wfo_overlaps_ci_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_
     // ---- phase 1: uploads, S_MO chain, flags + scans
     Sizer sz;
     sz.take<double>(nsq); sz.take<double>(nsq); sz.take<double>(nsq); sz.take<double>(nsq); sz.take<double>(nsq); sz.take<double>(nsq);
+    sz.take<double>(nsq);
     sz.take<double>((size_t)n_bra * count); sz.take<double>((size_t)n_ket * count);
     sz.take<int>(count); sz.take<int>(count); sz.take<int>(count); sz.take<int>(count);
     sz.take<int>(1 + n_bra); sz.take<int>(1 + n_ket);
@@ -1029,21 +1116,31 @@ int wfo_overlaps_ci_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_
     Arena ar{ctx->scratch, ctx->scratch_bytes, 0};
     double *d_smo = ar.take<double>(nsq), *d_bra = ar.take<double>(nsq), *d_ket = ar.take<double>(nsq),
            *d_inv = ar.take<double>(nsq), *d_sao = ar.take<double>(nsq), *d_work = ar.take<double>(nsq);
+    double *d_work2 = ar.take<double>(nsq);   // d_work, d_work2 contiguous: scratch of the device inverse
     double *d_bci = ar.take<double>((size_t)n_bra * count), *d_kci = ar.take<double>((size_t)n_ket * count);
     int *fl_b = ar.take<int>(count), *of_b = ar.take<int>(count), *fl_k = ar.take<int>(count), *of_k = ar.take<int>(count);
     int *tot_b = ar.take<int>(1 + n_bra), *tot_k = ar.take<int>(1 + n_ket);
     int32_t *exc_b = ar.take<int32_t>(2 * (size_t)count), *exc_k = ar.take<int32_t>(2 * (size_t)count);
     double *d_out = ar.take<double>((size_t)n_bra * n_ket);
     const size_t front1 = ar.off;
+    // main stream: raw CI tensors up, union flags + scans; side stream (concurrently): MO matrices up,
+    // the inverse behind S_AO (device Newton-Schulz unless the caller supplies it), S_AO, S_MO
     WFO_CUDA(cudaMemcpyAsync(d_bci, bra_ci, (size_t)n_bra * count * 8, cudaMemcpyHostToDevice, st));
     WFO_CUDA(cudaMemcpyAsync(d_kci, ket_ci, (size_t)n_ket * count * 8, cudaMemcpyHostToDevice, st));
     WFO_TRY(build_tables_dev(ctx, d_bci, n_bra, n, v, ci_thresh, strict, 0, fl_b, of_b, tot_b, st));
     WFO_TRY(build_tables_dev(ctx, d_kci, n_ket, n, v, ci_thresh, strict, 1, fl_k, of_k, tot_k, st));
-    WFO_CUDA(cudaMemcpyAsync(d_bra, bra_mos, nsq * 8, cudaMemcpyHostToDevice, st));
-    WFO_CUDA(cudaMemcpyAsync(d_ket, ket_mos, nsq * 8, cudaMemcpyHostToDevice, st));
-    WFO_CUDA(cudaMemcpyAsync(d_inv, c_inv, nsq * 8, cudaMemcpyHostToDevice, st));
-    WFO_TRY(wfo_sao_dev(ctx, d_inv, n_mo, d_sao, st));
-    WFO_TRY(wfo_smo_dev(ctx, d_bra, d_sao, d_ket, n_mo, n_mo, n_mo, n_mo, d_smo, d_work, st));
+    {
+        cudaStream_t s2 = ctx->stream2;
+        WFO_CUDA(cudaMemcpyAsync(d_bra, bra_mos, nsq * 8, cudaMemcpyHostToDevice, s2));
+        WFO_CUDA(cudaMemcpyAsync(d_ket, ket_mos, nsq * 8, cudaMemcpyHostToDevice, s2));
+        (void)d_work2;
+        if (ao_side == WFO_AO_GIVEN) WFO_CUDA(cudaMemcpyAsync(d_inv, c_inv, nsq * 8, cudaMemcpyHostToDevice, s2));
+        else WFO_TRY(wfo_inverse_dev(ctx, ao_side == WFO_AO_BRA ? d_bra : d_ket, n_mo, d_inv, d_work, s2));
+        WFO_TRY(wfo_sao_dev(ctx, d_inv, n_mo, d_sao, s2));
+        WFO_TRY(wfo_smo_dev(ctx, d_bra, d_sao, d_ket, n_mo, n_mo, n_mo, n_mo, d_smo, d_work, s2));
+        WFO_CUDA(cudaEventRecord(ctx->ev_join, s2));
+        WFO_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    }
     // ---- the table sizes (and per-state counts) come back: 2 small copies, one sync
     std::vector<int> hb_v(1 + n_bra), hk_v(1 + n_ket);
     int *hb = hb_v.data(), *hk = hk_v.data();

@@ -76,6 +76,9 @@ struct wfo_ctx {
     cudaStream_t stream;   // private stream of the *_host entry points
     cudaStream_t stream2;  // side stream: work that overlaps the single-CTA base factorisation
     cudaEvent_t ev_fork, ev_join;
+    double *ns_slots;      // device: norms + per-iteration residuals of the Newton-Schulz inverse (128 doubles)
+    double *h_slots;       // pinned host mirror
+    int last_inverse_iters;
     char *scratch;         // device arena, grown on demand
     size_t scratch_bytes;
     double *gscratch;      // per-CTA LU working matrices (global-scratch variant of the T0 kernel)

@@ -6,10 +6,10 @@
 //
 // CTA tile GM x 64 (GM = 64, or 32 when that is needed to fill the 148 SMs), 4 warps in a
 // 2x2 grid, warp tile (GM/2) x 32 = (GM/16) x 4 DMMA.8x8x4 tiles, K tile 16.  Operand tiles
-// are brought in with cp.async (8-byte elements, zero fill at the edges) through a 3-stage
-// shared-memory ring, so the L2 latency of tile t+2 hides behind the DMMAs of tile t with one
+// are brought in with cp.async (16-byte copies when the operands allow it, else 8-byte elements;
+// zero fill at the edges) through a 3-stage shared-memory ring, so the L2 latency of tile t+2 hides behind the DMMAs of tile t with one
 // block barrier per K tile.  Padded shared tiles make both fragment loads conflict-free
-// (A: stride 20 doubles, B: stride 72 doubles).  blockIdx.z selects a K slab (split-K): slab z
+// (k-contiguous tiles: stride 20 doubles, n-contiguous B tile: stride 72 doubles).  blockIdx.z selects a K slab (split-K): slab z
 // covers k in [z*kslab, min(k,(z+1)*kslab)) and writes C + z*slab_stride; deterministic,
 // summed by a later kernel in fixed order.  With batch strides blockIdx.z is a batch index.
 #pragma once
@@ -18,33 +18,38 @@
 namespace wfo {
 
 constexpr int GN = 64, GK = 16;   // GM (64 or 32 rows per CTA) is a template parameter
-constexpr int GLDA = GK + 4;      // 20
-constexpr int GLDB = GN + 8;      // 72
+constexpr int GLDA = GK + 4;      // 20: row stride of k-contiguous tiles (A, and B when it is stored transposed)
+constexpr int GLDB = GN + 8;      // 72: row stride of the n-contiguous B tile
 constexpr int GSTAGES = 3;
+constexpr int GBS = GN * GLDA;    // doubles reserved for the B tile of a stage (>= GK * GLDB)
 
 template <int GM>
-constexpr size_t gemm_smem_bytes() { return (size_t)GSTAGES * (GM * GLDA + GK * GLDB) * sizeof(double); }
+constexpr size_t gemm_smem_bytes() { return (size_t)GSTAGES * (GM * GLDA + GBS) * sizeof(double); }
 
-// 8-byte async copy global -> shared; bytes = 0 zero-fills (out-of-range elements)
+// async copies global -> shared; a source size below the copy size zero-fills the rest
 __device__ __forceinline__ void cp_async8(double *dst, const double *src, bool ok) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
     const int bytes = ok ? 8 : 0;
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(src), "r"(bytes));
 }
+__device__ __forceinline__ void cp_async16(double *dst, const double *src, int bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(src), "r"(bytes));
+}
 
-template <bool TA, bool TB, int GM>
+// VEC: 16-byte copies (needs !TA, even leading dimensions and K-slab starts, 16-byte aligned bases)
+template <bool TA, bool TB, int GM, bool VEC>
 __global__ void __launch_bounds__(128)
 gemm_f64_kernel(int m, int n, int k, double alpha, const double *__restrict__ A, int lda,
                 const double *__restrict__ B, int ldb, double beta, double *__restrict__ C, int ldc,
                 int kslab, long long slab_stride, long long batch_a, long long batch_b) {
     extern __shared__ __align__(16) double gsm[];
-    constexpr int STAGE = GM * GLDA + GK * GLDB;   // doubles per stage
+    constexpr int STAGE = GM * GLDA + GBS;   // doubles per stage
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     constexpr int MT = GM / 16;               // 8-row tiles per warp (warps are 2 x 2)
-    constexpr int EA = GM * GK / 128;         // A elements per thread and k tile
     const int wm = (warp >> 1) * (GM / 2), wn = (warp & 1) * 32;
     const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
     // blockIdx.z is either a K slab (batch strides 0) or a batch index (kslab >= k, batch strides set)
@@ -61,28 +66,56 @@ gemm_f64_kernel(int m, int n, int k, double alpha, const double *__restrict__ A,
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+    // shared layouts: As[mm][kk] (stride GLDA); Bs[kb][nn] (stride GLDB) for B as stored k x n,
+    // Bs[nn][kb] (stride GLDA) for B stored n x k (TB)
     auto issue_tile = [&](int stage, int k0) {
         double *As = gsm + stage * STAGE;
         double *Bs = As + GM * GLDA;
+        if (VEC) {
 #pragma unroll
-        for (int e = 0; e < EA; e++) {
-            const int idx = tid + e * 128;
-            int mm, kk;
-            if (TA) { kk = idx / GM; mm = idx % GM; } else { mm = idx / GK; kk = idx % GK; }
-            const int gm = m0 + mm, gk = k0 + kk;
-            const bool ok = gm < m && gk < kend;
-            const double *src = ok ? (TA ? A + (long long)gk * lda + gm : A + (long long)gm * lda + gk) : A;
-            cp_async8(As + mm * GLDA + kk, src, ok);
-        }
+            for (int e = 0; e < GM / 16; e++) {
+                const int idx = tid + e * 128;
+                const int mm = idx >> 3, kc = (idx & 7) * 2;
+                const int gm = m0 + mm, gk = k0 + kc;
+                const int bytes = (gm < m) ? max(0, min(16, (kend - gk) * 8)) : 0;
+                cp_async16(As + mm * GLDA + kc, bytes ? A + (long long)gm * lda + gk : A, bytes);
+            }
 #pragma unroll
-        for (int e = 0; e < 8; e++) {
-            const int idx = tid + e * 128;
-            int nn, kb;
-            if (TB) { nn = idx / GK; kb = idx % GK; } else { kb = idx / GN; nn = idx % GN; }
-            const int gn = n0 + nn, gkb = k0 + kb;
-            const bool ok = gn < n && gkb < kend;
-            const double *src = ok ? (TB ? B + (long long)gn * ldb + gkb : B + (long long)gkb * ldb + gn) : B;
-            cp_async8(Bs + kb * GLDB + nn, src, ok);
+            for (int e = 0; e < 4; e++) {
+                const int idx = tid + e * 128;
+                if (TB) {
+                    const int nn = idx >> 3, kc = (idx & 7) * 2;
+                    const int gn = n0 + nn, gk = k0 + kc;
+                    const int bytes = (gn < n) ? max(0, min(16, (kend - gk) * 8)) : 0;
+                    cp_async16(Bs + nn * GLDA + kc, bytes ? B + (long long)gn * ldb + gk : B, bytes);
+                } else {
+                    const int kb = idx >> 5, nc = (idx & 31) * 2;
+                    const int gkb = k0 + kb, gn = n0 + nc;
+                    const int bytes = (gkb < kend) ? max(0, min(16, (n - gn) * 8)) : 0;
+                    cp_async16(Bs + kb * GLDB + nc, bytes ? B + (long long)gkb * ldb + gn : B, bytes);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < GM * GK / 128; e++) {
+                const int idx = tid + e * 128;
+                int mm, kk;
+                if (TA) { kk = idx / GM; mm = idx % GM; } else { mm = idx / GK; kk = idx % GK; }
+                const int gm = m0 + mm, gk = k0 + kk;
+                const bool ok = gm < m && gk < kend;
+                const double *src = ok ? (TA ? A + (long long)gk * lda + gm : A + (long long)gm * lda + gk) : A;
+                cp_async8(As + mm * GLDA + kk, src, ok);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const int idx = tid + e * 128;
+                int nn, kb;
+                if (TB) { nn = idx / GK; kb = idx % GK; } else { kb = idx / GN; nn = idx % GN; }
+                const int gn = n0 + nn, gkb = k0 + kb;
+                const bool ok = gn < n && gkb < kend;
+                const double *src = ok ? (TB ? B + (long long)gn * ldb + gkb : B + (long long)gkb * ldb + gn) : B;
+                cp_async8(TB ? Bs + nn * GLDA + kb : Bs + kb * GLDB + nn, src, ok);
+            }
         }
     };
 
@@ -106,7 +139,8 @@ gemm_f64_kernel(int m, int n, int k, double alpha, const double *__restrict__ A,
 #pragma unroll
             for (int i = 0; i < MT; i++) a[i] = As[(wm + 8 * i + g) * GLDA + ks + t];
 #pragma unroll
-            for (int j = 0; j < 4; j++) b[j] = Bs[(ks + t) * GLDB + wn + 8 * j + g];
+            for (int j = 0; j < 4; j++)
+                b[j] = TB ? Bs[(wn + 8 * j + g) * GLDA + ks + t] : Bs[(ks + t) * GLDB + wn + 8 * j + g];
 #pragma unroll
             for (int i = 0; i < MT; i++)
 #pragma unroll

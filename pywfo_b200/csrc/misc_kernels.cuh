@@ -314,6 +314,70 @@ __global__ void closed_finalize_kernel(const double *__restrict__ P, int n_slabs
     out[(size_t)i * ld_out + j] = d * d * ((1.0 + sigma) * bx[i] * ky[j] + a);
 }
 
+// ---- Newton-Schulz inverse helpers (device-side replacement of np.linalg.inv, pywfo/main.py:303) ----
+__device__ __forceinline__ void atomic_max_nonneg(double *slot, double v) {   // v >= 0: IEEE order = integer order
+    atomicMax(reinterpret_cast<unsigned long long *>(slot), (unsigned long long)__double_as_longlong(v));
+}
+// slots[0] = max row sum of |A| (inf-norm), slots[1] = max column sum (1-norm); grid = n CTAs
+__global__ void __launch_bounds__(256) ns_norms_kernel(const double *__restrict__ A, int n, double *__restrict__ slots) {
+    __shared__ double red[2][256];
+    const int r = blockIdx.x;
+    double rs = 0.0, cs = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        rs += fabs(A[(size_t)r * n + i]);
+        cs += fabs(A[(size_t)i * n + r]);
+    }
+    red[0][threadIdx.x] = rs;
+    red[1][threadIdx.x] = cs;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+        if (threadIdx.x < o) {
+            red[0][threadIdx.x] += red[0][threadIdx.x + o];
+            red[1][threadIdx.x] += red[1][threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        atomic_max_nonneg(slots, red[0][0]);
+        atomic_max_nonneg(slots + 1, red[1][0]);
+    }
+}
+// X0 = A^T / (|A|_1 |A|_inf)
+__global__ void ns_init_kernel(const double *__restrict__ A, int n, const double *__restrict__ slots, double *__restrict__ X) {
+    __shared__ double tile[32][33];
+    const double sc = 1.0 / (slots[0] * slots[1]);
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+        const int r = by + dy, c = bx + threadIdx.x;
+        tile[dy][threadIdx.x] = (r < n && c < n) ? A[(size_t)r * n + c] : 0.0;
+    }
+    __syncthreads();
+    for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+        const int r = bx + dy, c = by + threadIdx.x;
+        if (r < n && c < n) X[(size_t)r * n + c] = tile[threadIdx.x][dy] * sc;
+    }
+}
+// slot = max |T - I|;  Xn = X  (the next iterate starts as a copy: Xn = 2 Xn - X T follows as a GEMM)
+__global__ void ns_residual_kernel(const double *__restrict__ T, const double *__restrict__ X, int n,
+                                   double *__restrict__ slot, double *__restrict__ Xn) {
+    const size_t tot = (size_t)n * n;
+    double m = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / n), c = (int)(i - (size_t)r * n);
+        const double d = fabs(T[i] - (r == c ? 1.0 : 0.0));
+        m = (d > m || d != d) ? d : m;   // NaN propagates
+        Xn[i] = X[i];
+    }
+    for (int o = 16; o; o >>= 1) {
+        const double x = __shfl_xor_sync(0xffffffffu, m, o);
+        m = (x > m || x != x) ? x : m;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (m != m) m = 1e300;
+        atomic_max_nonneg(slot, m);
+    }
+}
+
 // ---- FP64 peak microbenchmarks (roofline denominators, bench.py) -------------
 __global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double *out) {
     double a[16];

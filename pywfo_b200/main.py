@@ -5,13 +5,13 @@
     moovlp | moovlp_expl | moovlp_dots (mos1, mos2, S_AO)
     get_S_AO(bra_mos, ket_mos, ao_ovlps)
 
-The host does what the reference's host code does around the arithmetic --
-``np.linalg.inv`` of the MO matrix for ``ao_ovlps in {"bra","ket"}``
-(pywfo/main.py:303) and the thresholding of the CI vectors (main.py:539-540,
-112, 122-123; see excitations.py) -- and hands everything else to the CUDA
-library through ``include/wfo_b200.h``: S_AO = Cinv Cinv^T, S_MO, every
+The host only checks shapes; everything the reference computes goes to the CUDA
+library through ``include/wfo_b200.h``: the inverse of the MO matrix for
+``ao_ovlps in {"bra","ket"}`` (pywfo/main.py:303; Newton-Schulz on the FP64
+tensor-core GEMM, LAPACK only as a fallback), S_AO = Cinv Cinv^T, S_MO, the
+thresholding of the CI vectors (main.py:539-540, 112, 122-123), every
 determinant pair and the CI-weighted reduction.  Extra keyword arguments
-(``tier``, ``device``) are a superset of the reference signature.
+(``tier``, ``device``, ``host_inverse``) are a superset of the reference signature.
 
 When ``torch.distributed`` is initialised with more than one rank, each rank
 computes the partial matrix of its shard of the bra excitations and the
@@ -35,11 +35,21 @@ def log(message, level="info"):
     getattr(logger, level)(message)
 
 
+def _mo_inverse(mos):
+    """``np.linalg.inv(mos)`` of pywfo/main.py:303 on the device (Newton-Schulz on the FP64
+    tensor-core GEMM); LAPACK on the host only if that iteration does not converge."""
+    try:
+        return _lib.context().inverse_host(mos)
+    except _lib.WfoError as exc:
+        if exc.code != _lib.ERR_NOCONV:
+            raise
+        return np.linalg.inv(mos)
+
+
 def get_S_AO(bra_mos, ket_mos, ao_ovlps):
-    """pywfo/main.py:301-311.  The inverse is numpy/LAPACK on the host exactly as
-    upstream; the product ``inv inv^T`` runs on the GPU (wfo_sao_dev via smo)."""
+    """pywfo/main.py:301-311: inverse and the product ``inv inv^T`` both on the GPU."""
     if isinstance(ao_ovlps, str):
-        inv = np.linalg.inv({"bra": bra_mos, "ket": ket_mos}[ao_ovlps])
+        inv = _mo_inverse(np.asarray({"bra": bra_mos, "ket": ket_mos}[ao_ovlps], dtype=np.float64))
         # inv @ I @ inv^T through the DMMA GEMM chain
         return _lib.context().smo_host(inv, np.eye(inv.shape[1]), inv)
     if isinstance(ao_ovlps, np.ndarray):  # upstream's isinstance(.., np.array) raises TypeError
@@ -63,7 +73,7 @@ def moovlp_dots(mos1, mos2, S_AO):
 
 
 def _state_overlaps(semantics, sigma, bra_mos, ket_mos, bra_ci, ket_ci, occ, ci_thresh, ao_ovlps,
-                    tier="auto", device=None):
+                    tier="auto", device=None, host_inverse=False):
     bra_mos = np.asarray(bra_mos, dtype=np.float64)
     ket_mos = np.asarray(ket_mos, dtype=np.float64)
     bra_ci = np.asarray(bra_ci, dtype=np.float64)
@@ -76,13 +86,25 @@ def _state_overlaps(semantics, sigma, bra_mos, ket_mos, bra_ci, ket_ci, occ, ci_
     ctx = _lib.context(device)
     n_bra, n_ket = bra_ci.shape[0], ket_ci.shape[0]
     if isinstance(ao_ovlps, str):
-        # host: the one LAPACK call upstream makes here (main.py:303); device: everything else,
-        # including the selection of excitations above the threshold
-        c_inv = np.linalg.inv({"bra": bra_mos, "ket": ket_mos}[ao_ovlps])
+        # everything on the device: the inverse behind S_AO (main.py:303; ``host_inverse=True``
+        # keeps upstream's LAPACK call instead), S_AO, S_MO, the selection of excitations above
+        # the threshold, every determinant pair and the CI-weighted reduction
+        if ao_ovlps not in ("bra", "ket"):
+            raise KeyError(ao_ovlps)   # upstream: dict lookup, main.py:303
+        side = _lib.AO_BRA if ao_ovlps == "bra" else _lib.AO_KET
         rank, world = dist.world()
-        part, _ = ctx.overlaps_ci_host(bra_mos, ket_mos, c_inv, occ, bra_ci, ket_ci, ci_thresh,
-                                       semantics=0 if semantics == "cache" else 1, tier=tier,
-                                       rank=rank, world=world)
+        kw = dict(semantics=0 if semantics == "cache" else 1, tier=tier, rank=rank, world=world)
+        part = None
+        if not host_inverse:
+            try:
+                part, _ = ctx.overlaps_ci_host(bra_mos, ket_mos, None, occ, bra_ci, ket_ci, ci_thresh,
+                                               ao_side=side, **kw)
+            except _lib.WfoError as exc:
+                if exc.code != _lib.ERR_NOCONV:
+                    raise
+        if part is None:   # asked for, or the device iteration did not converge: LAPACK as upstream
+            c_inv = np.linalg.inv(bra_mos if ao_ovlps == "bra" else ket_mos)
+            part, _ = ctx.overlaps_ci_host(bra_mos, ket_mos, c_inv, occ, bra_ci, ket_ci, ci_thresh, **kw)
         return dist.sum_over_ranks(part, device=ctx.device)
     if not isinstance(ao_ovlps, np.ndarray):
         raise Exception("Invalid AO overlaps!")

@@ -401,3 +401,44 @@ def test_error_messages_are_formatted(ctx):
         ctx.state_overlaps_host(np.eye(4), 2, bra, np.ones((1, 1)), bra, np.ones((1, 1)), k_begin=0, k_end=5)
     with pytest.raises(WfoError, match="n_occ=9 must be in 1..n_mo=4"):
         ctx.state_overlaps_host(np.eye(4), 9, bra, np.ones((1, 1)), bra, np.ones((1, 1)))
+
+
+# ---------------------------------------------------------------- device inverse (np.linalg.inv, main.py:303)
+@pytest.mark.parametrize("n,cond", [(3, 1.0), (38, 30.0), (137, 1e3), (500, 1.0), (500, 1e5)])
+def test_device_inverse_matches_lapack(ctx, n, cond):
+    rng = np.random.default_rng(n)
+    u, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    v, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    sv = np.logspace(0, -np.log10(cond), n)
+    a = (u * sv) @ v.T
+    got = ctx.inverse_host(a)
+    want = np.linalg.inv(a)
+    # forward error of any backward-stable inverse is O(eps * cond)
+    assert np.abs(got - want).max() <= 1e-12 * cond * np.abs(want).max()
+    assert np.abs(a @ got - np.eye(n)).max() <= 1e-11 * max(cond ** 0.5, 1.0)
+
+
+def test_device_inverse_reports_singular(ctx):
+    from pywfo_b200 import _lib
+    a = np.ones((8, 8))
+    with pytest.raises(_lib.WfoError) as ei:
+        ctx.inverse_host(a)
+    assert ei.value.code == _lib.ERR_NOCONV
+
+
+@pytest.mark.parametrize("name", ["h2o2", "r_n17", "r_odd"])
+@pytest.mark.parametrize("ao", ["ket", "bra"])
+def test_device_inverse_path_equals_host_inverse_path(ctx, name, ao):
+    """ao_ovlps in {"bra","ket"}: inverse on the device (default) vs upstream's LAPACK call."""
+    from pywfo_b200 import main
+    g = load_golden(name)
+    occ = int(g["occ"])
+    args = (g["bra_mos"], g["ket_mos"], g["bra_ci"], g["ket_ci"], occ)
+    thr = float(g["ci_thresh"]) if "ci_thresh" in g else 1e-2
+    dev = main.overlaps_cache(*args, ci_thresh=thr, ao_ovlps=ao)
+    host = main.overlaps_cache(*args, ci_thresh=thr, ao_ovlps=ao, host_inverse=True)
+    assert_parity(dev, host)
+    want = {("h2o2", "ket"): "ref_cache_4x4_1e-2", ("r_n17", "ket"): "ref_overlaps_cache", ("r_odd", "ket"): "ref_overlaps_cache",
+            ("r_n17", "bra"): "ref_overlaps_cache_bra", ("r_odd", "bra"): "ref_overlaps_cache_bra"}.get((name, ao))
+    if want:
+        assert_parity(dev, g[want])
