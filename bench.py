@@ -96,7 +96,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.005)
 
     def start(self):
         if self.nv is not None:
@@ -321,8 +321,16 @@ def run_ours(args, w):
         kname = "t0_fused_kernel (pivoted LU per pair + CI contraction)"
     achieved = pairs_shard * flops_pair / (k_ms * 1e-3) / 1e12
     # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this
-    # exact configuration (profiles/r01_t1_fused_kernel_ncu_full_excerpt.csv); null for other configs
-    traffic = 22013952 + 270981376 if (args.workload == "c4" and world == 1 and used_tier == 1) else None
+    # exact configuration (profiles/traffic.json, written from the capture by scratch/make_profiles.py);
+    # null for configurations that were not captured
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        key = f"{args.workload}:n{world}:tier{used_tier}"
+        if key in tj:
+            traffic = int(tj[key]["dram_bytes_read"] + tj[key]["dram_bytes_write"])
+    except Exception:
+        traffic = None
     roofline = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "measured in this run: max of register-resident DFMA loop and DMMA.8x8x4 loop "
@@ -427,7 +435,7 @@ def main():
     sys.stdout = real_stdout
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))

@@ -439,6 +439,8 @@ int wfo_create(int device, wfo_ctx **out) {
     WFO_CUDA(cudaEventCreate(&c->ev0));
     WFO_CUDA(cudaEventCreate(&c->ev1));
     for (int i = 0; i < 24; i++) WFO_CUDA(cudaEventCreate(&c->pev[i]));
+    WFO_CUDA(cudaFuncSetAttribute(base_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)lub_smem_bytes(LUB_MAXN)));
     WFO_CUDA(cudaMalloc(&c->ns_slots, 128 * sizeof(double)));
     WFO_CUDA(cudaMallocHost(&c->h_slots, 128 * sizeof(double)));
     *out = c;
@@ -707,7 +709,7 @@ static int closed_form_impl(wfo_ctx *ctx, size_t arena_off, const double *s_mo, 
     Arena ar{ctx->scratch, ctx->scratch_bytes, arena_off};
     carve2(ar, Ai, Xt, Y, Wb, cb, ck, Z, T, P, bx, ky, info, flag);
 
-    base_inverse_kernel<<<1, LUB_THREADS, 0, st>>>(s_mo, n_mo, n, Ai, info);
+    base_inverse_kernel<<<1, LUB_THREADS, lub_smem_bytes(n), st>>>(s_mo, n_mo, n, Ai, info);
     WFO_LAUNCH_CHECK(ctx);
     WFO_CUDA(cudaMemsetAsync(cb, 0, (size_t)n_bra * nv * 8, st));
     WFO_CUDA(cudaMemsetAsync(ck, 0, (size_t)n_ket * nv * 8, st));
@@ -815,7 +817,7 @@ static int state_overlaps_block(wfo_ctx *ctx, size_t arena_off, const double *s_
         }
         WFO_CUDA(cudaEventRecord(ctx->ev_join, s2));
         // ---- one base factorisation, then the three block products
-        base_inverse_kernel<<<1, LUB_THREADS, 0, st>>>(s_mo, n_mo, n, p.Ai, p.info);
+        base_inverse_kernel<<<1, LUB_THREADS, lub_smem_bytes(n), st>>>(s_mo, n_mo, n, p.Ai, p.info);
         WFO_LAUNCH_CHECK(ctx);
         // the conditioning of the base block decides whether the rank-update tier is usable:
         // one 32-byte read-back (the only host synchronisation of the call)
@@ -1207,6 +1209,14 @@ int wfo_overlaps_ci_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_
     WFO_CUDA(cudaStreamSynchronize(st));
     return WFO_OK;
 }
+
+#ifdef WFO_LUB_CLOCKS
+int wfo_debug_lub_clocks(long long *out16, int reset) {
+    if (out16) cudaMemcpyFromSymbol(out16, g_lub_clk, sizeof(long long) * 16);
+    if (reset) { long long z[16] = {0}; cudaMemcpyToSymbol(g_lub_clk, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 #ifdef WFO_T1_CLOCKS
 int wfo_debug_t1_clocks(long long *out, int n_ctas) {

@@ -1,15 +1,12 @@
-// Base-block factorisation for the rank-update tiers: Gauss-Jordan inverse with
-// partial (row) pivoting of A = S_MO[:n,:n] (n <= 128) in ONE CTA of 512 threads,
-// REGISTER resident: warp w owns rows {w, w+16, ..., w+112}, lane l owns columns
-// {l, l+32, l+64, l+96} -> 32 matrix elements per thread.  Per elimination step only
-// the pivot row and the multiplier column travel through shared memory (2 block
-// barriers per step); pivoting is implicit (rows never move), the row/column
-// permutation is undone when the inverse is written out.
+// Base-block factorisation for the rank-update tiers: in-place Gauss-Jordan inverse with
+// partial (row) pivoting of A = S_MO[:n,:n] (n <= 128) in ONE CTA of 512 threads, REGISTER
+// resident (32 matrix elements per thread).  Pivoting is implicit (rows never move), the
+// row/column permutation is undone when the inverse is written out.
 // Produces Ai = A^-1, det(A) and min/max |pivot| as a conditioning indicator.
 //
-// This is the "one base LU" that north_star's rank-1 (Sherman-Morrison / cofactor)
-// updates reuse; upstream the same numbers would come from np.linalg.det /
-// np.linalg.inv of S_MO[:occ,:occ] (pywfo/main.py:548).
+// This is the "one base LU" that north_star's rank-1 (Sherman-Morrison / cofactor) updates
+// reuse; upstream the same numbers would come from np.linalg.det / np.linalg.inv of
+// S_MO[:occ,:occ] (pywfo/main.py:548).
 #pragma once
 #include "common.cuh"
 
@@ -23,139 +20,241 @@ struct BaseInfo {     // device-resident result block
     int pad;
 };
 
+#ifdef WFO_LUB_CLOCKS
+__device__ long long g_lub_clk[16];
+#define LUB_T(i) do { long long now_ = clock64(); t_acc[i] += now_ - t_prev; t_prev = now_; } while (0)
+#else
+#define LUB_T(i)
+#endif
 constexpr int LUB_MAXN = 128;
 constexpr int LUB_THREADS = 512;
 constexpr int LUB_WARPS = LUB_THREADS / 32;   // 16
-constexpr int LUB_RS = LUB_MAXN / LUB_WARPS;     // 8 row slots per thread
+constexpr int LUB_CS = LUB_MAXN / LUB_WARPS;  // 8 column slots per thread (columns warp + 16 c)
+constexpr int LUB_RS = 4;                     // 4 row slots per thread (rows 4 lane + s)
+constexpr int LUB_LDS = LUB_MAXN + 1;         // row stride of the staging tile
+inline size_t lub_smem_bytes(int n) { return (size_t)n * LUB_LDS * sizeof(double); }
 
 // A_src: n x n block with leading dimension ld_src.  Ai_out: n x n, ld = n.
+// Dynamic shared memory: lub_smem_bytes(n) (staging tile for coalesced load / store).
+//
+// Ownership: lane l holds rows 4l..4l+3, warp w holds columns w, w+16, ..., w+112, so
+//   * column j lives entirely in ONE warp (j mod 16): the pivot search is 4 compares per lane and
+//     one REDUX inside that warp -- no shared memory, no barrier;
+//   * row p lives in lane p/4 of EVERY warp: each warp passes its part of the pivot row through a
+//     warp-private shared buffer (one lane writes, the warp reads it back) -- no block barrier;
+//   * the update is branch- and select-free: the pivot row's own multiplier is published as d - 1,
+//     so that a_p - (d-1) (a_p / d) = a_p / d comes out of the same multiply-add as every other row;
+//   * only the multiplier column (and p, 1/pivot) goes through block-shared memory: ONE block barrier
+//     per elimination step, and the warp that owns the next column updates that column first,
+//     searches its pivot and publishes it while the other warps still work on the current step;
+//   * det / min / max pivot are accumulated by the owning warps and combined at the end.
 __global__ void __launch_bounds__(LUB_THREADS)
 base_inverse_kernel(const double *__restrict__ A_src, int ld_src, int n, double *__restrict__ Ai_out,
                     BaseInfo *__restrict__ info) {
-    // double buffered by step parity: a step's writes never race the previous step's reads
-    __shared__ unsigned keys[2][32];   // LUB_WARPS used, rest stays 0
-    __shared__ double prow[2][LUB_MAXN];   // scaled pivot row
-    __shared__ double mcol[2][LUB_MAXN];   // multiplier column
-    __shared__ int piv_of_col[LUB_MAXN];   // p_j: pivot row chosen for column j
-    __shared__ int col_of_piv[LUB_MAXN];   // inverse map
+    extern __shared__ __align__(16) double lub_tile[];    // n x LUB_LDS
+    __shared__ __align__(16) double mcol[2][LUB_MAXN];    // multiplier column, double buffered by step parity
+    __shared__ __align__(16) double prow[LUB_WARPS][LUB_CS];   // warp-private: this warp's part of the pivot row
+    __shared__ double prd[2];                             // reciprocal of the pivot
+    __shared__ int pp[2];                                 // pivot row (-1: no candidate left)
+    __shared__ int piv_of_col[LUB_MAXN];                  // p_j: pivot row chosen for column j
+    __shared__ int col_of_piv[LUB_MAXN];                  // inverse map
+    __shared__ double wdet[LUB_WARPS], wmin[LUB_WARPS], wmax[LUB_WARPS];
+    __shared__ int wsing[LUB_WARPS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned FULL = 0xffffffffu;
+#ifdef WFO_LUB_CLOCKS
+    long long t_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long t_prev = clock64();
+#endif
 
-    double a[LUB_RS][4];
-    bool done[LUB_RS];
-    if (tid < 64) keys[tid >> 5][tid & 31] = 0;
+    // coalesced load through the staging tile
+    for (int idx = tid; idx < n * n; idx += LUB_THREADS) {
+        const int r = idx / n, c = idx - r * n;
+        lub_tile[r * LUB_LDS + c] = A_src[(size_t)r * ld_src + c];
+    }
     __syncthreads();
+    double a[LUB_RS][LUB_CS];
+    unsigned donemask = 0;   // bit s: row 4 lane + s is a used pivot row or beyond n
 #pragma unroll
     for (int s = 0; s < LUB_RS; s++) {
-        const int r = warp + LUB_WARPS * s;
-        done[s] = !(r < n);
+        const int r = 4 * lane + s;
+        if (!(r < n)) donemask |= 1u << s;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int c = lane + 32 * k;
-            a[s][k] = (r < n && c < n) ? A_src[(size_t)r * ld_src + c] : 0.0;
+        for (int c = 0; c < LUB_CS; c++) {
+            const int col = warp + LUB_WARPS * c;
+            a[s][c] = (r < n && col < n) ? lub_tile[r * LUB_LDS + col] : 0.0;
         }
     }
-    double det = 1.0, minp = 1e300, maxp = 0.0;
+    double det = 1.0, minp = 1e300, maxp = 0.0;   // over the columns this warp owns
     int singular = 0;
 
-    // straight-line step body (no early exits, selects instead of branches): the compiler keeps
-    // the 32 matrix registers in place; a zero pivot only sets a sticky flag
+    // pivot search in column slot C of this warp + publication (multipliers, pivot row index,
+    // reciprocal) for step J; then the slot restarts as the unit column e_p (in-place Gauss-Jordan)
+#define LUB_PUBLISH(C, B, J)                                                                               \
+    do {                                                                                                   \
+        unsigned key = 0;                                                                                  \
+        _Pragma("unroll") for (int s = 0; s < LUB_RS; s++) {                                               \
+            const unsigned k = (hi_abs(a[s][C]) & 0xffffff00u) | 0x80u | (unsigned)(4 * lane + s);         \
+            key = max(key, ((donemask >> s) & 1u) ? 0u : k);                                               \
+        }                                                                                                  \
+        const unsigned kmax = __reduce_max_sync(FULL, key);                                                \
+        const int p_ = (kmax != 0u) ? (int)(kmax & 0x7fu) : -1;                                            \
+        const int ps_ = p_ & 3, pl_ = (p_ >> 2) & 31;                                                      \
+        double cand = a[0][C];                                                                             \
+        cand = (ps_ == 1) ? a[1][C] : cand;                                                                \
+        cand = (ps_ == 2) ? a[2][C] : cand;                                                                \
+        cand = (ps_ == 3) ? a[3][C] : cand;                                                                \
+        const double d_ = __shfl_sync(FULL, cand, pl_);                                                    \
+        /* multipliers; the pivot row's own entry is d - 1, so that a_p - (d-1) (a_p/d) = a_p/d */        \
+        double m_[LUB_RS];                                                                                 \
+        _Pragma("unroll") for (int s = 0; s < LUB_RS; s++) m_[s] = (4 * lane + s == p_) ? d_ - 1.0 : a[s][C]; \
+        *reinterpret_cast<double2 *>(&mcol[B][4 * lane]) = make_double2(m_[0], m_[1]);                     \
+        *reinterpret_cast<double2 *>(&mcol[B][4 * lane + 2]) = make_double2(m_[2], m_[3]);                 \
+        if (lane == 0) {                                                                                   \
+            prd[B] = fast_rcp(d_);                                                                         \
+            pp[B] = p_;                                                                                    \
+            piv_of_col[J] = p_;                                                                            \
+            col_of_piv[p_ & 127] = J;                                                                      \
+        }                                                                                                  \
+        const double ad_ = fabs(d_);                                                                       \
+        singular |= (p_ < 0 || !(ad_ > 0.0) || !(ad_ < 1e300)) ? 1 : 0;                                    \
+        det *= d_;                                                                                         \
+        minp = fmin(minp, ad_);                                                                            \
+        maxp = fmax(maxp, ad_);                                                                            \
+        _Pragma("unroll") for (int s = 0; s < LUB_RS; s++) a[s][C] = (4 * lane + s == p_) ? 1.0 : 0.0;    \
+    } while (0)
+
+    LUB_T(0);
+    if (warp == 0 && n > 0) LUB_PUBLISH(0, 0, 0);
+    __syncthreads();
+    LUB_T(1);
+
 #pragma unroll
-    for (int cj = 0; cj < 4; cj++) {          // column slot (static register index)
-        const int nsteps = min(32, n - 32 * cj);
-        for (int lj = 0; lj < nsteps; lj++) { // owning lane
-            const int j = lj + 32 * cj;
+    for (int cj = 0; cj < LUB_CS; cj++) {           // column slot of the current step (static register index)
+        const int nsteps = min(LUB_WARPS, n - LUB_WARPS * cj);
+        for (int wj = 0; wj < nsteps; wj++) {       // owning warp
+            const int j = wj + LUB_WARPS * cj;
             const int b = j & 1;
-            // ---- pivot search: per-warp candidate from the lane that owns column j; the owner
-            // publishes the column (the multipliers) and restarts its column slot from zero
-            if (lane == lj) {
-                unsigned key = 0;
-#pragma unroll
-                for (int s = 0; s < LUB_RS; s++) {
-                    const unsigned k = (hi_abs(a[s][cj]) & 0xffffff00u) | 0x80u | (unsigned)(warp + LUB_WARPS * s);
-                    key = max(key, done[s] ? 0u : k);
-                    mcol[b][warp + LUB_WARPS * s] = a[s][cj];
-                    a[s][cj] = 0.0;
+            LUB_T(2);
+            const int p = pp[b];
+            const double rd = prd[b];
+            const int ps = p & 3, pl = (p >> 2) & 31;
+            // this warp's part of the pivot row: lane pl writes it (slot ps), everybody reads it back
+            if (lane == pl) {
+                switch (ps) {   // static register indices
+#define LUB_ROW(S_)                                                                              \
+    _Pragma("unroll") for (int c = 0; c < LUB_CS; c += 2)                                        \
+        *reinterpret_cast<double2 *>(&prow[warp][c]) = make_double2(a[S_][c], a[S_][c + 1]);
+                    case 0: LUB_ROW(0) break;
+                    case 1: LUB_ROW(1) break;
+                    case 2: LUB_ROW(2) break;
+                    default: LUB_ROW(3) break;
+#undef LUB_ROW
                 }
-                keys[b][warp] = key;
             }
-            __syncthreads();
-            const unsigned kmax = __reduce_max_sync(0xffffffffu, keys[b][lane]);
-            const int p = (int)(kmax & 0x7fu);          // pivot row
-            const int wp = p % LUB_WARPS, sp = p / LUB_WARPS;
-            const double d = mcol[b][p];
-            const double ad = fabs(d);
-            singular |= (kmax == 0u || !(ad > 0.0) || !(ad < 1e300)) ? 1 : 0;
-            det *= d;
-            minp = fmin(minp, ad);
-            maxp = fmax(maxp, ad);
-            const double rd = fast_rcp(d);
-            if (warp == wp) {                           // publish the scaled pivot row
-                double row[4];
+            __syncwarp();
+            double pr[LUB_CS];
 #pragma unroll
-                for (int k = 0; k < 4; k++) row[k] = a[0][k];
-#pragma unroll
-                for (int s = 1; s < LUB_RS; s++)
-#pragma unroll
-                    for (int k = 0; k < 4; k++) row[k] = (s == sp) ? a[s][k] : row[k];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int c = lane + 32 * k;
-                    prow[b][c] = ((c == j) ? 1.0 : row[k]) * rd;
-                }
-                if (lane == 0) { piv_of_col[j] = p; col_of_piv[p] = j; }
+            for (int c = 0; c < LUB_CS; c += 2) {
+                const double2 v = *reinterpret_cast<const double2 *>(&prow[warp][c]);
+                pr[c] = v.x * rd;
+                pr[c + 1] = v.y * rd;
             }
-            __syncthreads();
-            double pr[4];
+            LUB_T(3);
+            // multipliers of this lane's rows
+            const double2 f01 = *reinterpret_cast<const double2 *>(&mcol[b][4 * lane]);
+            const double2 f23 = *reinterpret_cast<const double2 *>(&mcol[b][4 * lane + 2]);
+            const double f[LUB_RS] = {f01.x, f01.y, f23.x, f23.y};
+            donemask |= (lane == pl) ? (1u << ps) : 0u;
+            LUB_T(4);
+            // look-ahead: the owner of the next column updates it first and publishes its pivot
+            const int jn = j + 1;
+            const bool own_next = (jn < n) && (warp == (jn & (LUB_WARPS - 1)));
+            if (jn < n) {
+                if (wj + 1 < LUB_WARPS) {           // next column is in the same slot cj
+                    if (own_next) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) pr[k] = prow[b][lane + 32 * k];
-            if (warp != wp) {                           // 15 of 16 warps: pure multiply-add
+                        for (int s = 0; s < LUB_RS; s++) a[s][cj] = fma(-f[s], pr[cj], a[s][cj]);
+                        LUB_PUBLISH(cj, b ^ 1, jn);
+                    }
+                } else if (cj + 1 < LUB_CS) {       // next column is slot cj + 1 of warp 0
+                    if (own_next) {
 #pragma unroll
-                for (int s = 0; s < LUB_RS; s++) {
-                    const double f = mcol[b][warp + LUB_WARPS * s];
-#pragma unroll
-                    for (int k = 0; k < 4; k++) a[s][k] = fma(-f, pr[k], a[s][k]);
-                }
-            } else {                                    // the warp that holds the pivot row
-#pragma unroll
-                for (int s = 0; s < LUB_RS; s++) {
-                    const bool is_p = (s == sp);
-                    done[s] = done[s] || is_p;
-                    const double f = is_p ? 0.0 : mcol[b][warp + LUB_WARPS * s];
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const double upd = fma(-f, pr[k], a[s][k]);
-                        a[s][k] = is_p ? pr[k] : upd;
+                        for (int s = 0; s < LUB_RS; s++)
+                            a[s][(cj + 1) % LUB_CS] = fma(-f[s], pr[(cj + 1) % LUB_CS], a[s][(cj + 1) % LUB_CS]);
+                        LUB_PUBLISH((cj + 1) % LUB_CS, b ^ 1, jn);
                     }
                 }
             }
+            LUB_T(5);
+            // the rest of the update (the column handled by the look-ahead is skipped by its owner)
+            const int skip = !own_next ? -1 : ((wj + 1 < LUB_WARPS) ? cj : cj + 1);
+#pragma unroll
+            for (int c = 0; c < LUB_CS; c++) {
+                if (c == skip) continue;
+#pragma unroll
+                for (int s = 0; s < LUB_RS; s++) a[s][c] = fma(-f[s], pr[c], a[s][c]);
+            }
+            // keep the bulk update on this side of the barrier: sunk into the next step it would sit in
+            // front of that step's critical path (pivot row exchange -> look-ahead publish)
+#pragma unroll
+            for (int c = 0; c < LUB_CS; c++)
+#pragma unroll
+                for (int s = 0; s < LUB_RS; s++) asm volatile("" : "+d"(a[s][c]));
+            LUB_T(6);
+            __syncthreads();
+            LUB_T(7);
         }
     }
+#undef LUB_PUBLISH
+    LUB_T(8);
+    // ---- combine the per-warp pivot statistics
+    if (lane == 0) { wdet[warp] = det; wmin[warp] = minp; wmax[warp] = maxp; wsing[warp] = singular; }
+    __syncthreads();
+    double tdet = 1.0, tmin = 1e300, tmax = 0.0;
+    int tsing = 0;
+#pragma unroll
+    for (int w = 0; w < LUB_WARPS; w++) {
+        tdet *= wdet[w];
+        tmin = fmin(tmin, wmin[w]);
+        tmax = fmax(tmax, wmax[w]);
+        tsing |= wsing[w];
+    }
     // ---- write out: stored[r][j'] = M[r][p_j'],  Ai[j][c] = M[p_j][c]  =>  Ai[col_of_piv[r]][piv_of_col[j']] = stored[r][j']
-    if (!singular) {
+    // (permuted into the staging tile, then a coalesced copy)
+    if (!tsing) {
 #pragma unroll
         for (int s = 0; s < LUB_RS; s++) {
-            const int r = warp + LUB_WARPS * s;
+            const int r = 4 * lane + s;
             if (r < n) {
                 const int orow = col_of_piv[r];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int c = lane + 32 * k;
-                    if (c < n) Ai_out[(size_t)orow * n + piv_of_col[c]] = a[s][k];
+                for (int c = 0; c < LUB_CS; c++) {
+                    const int col = warp + LUB_WARPS * c;
+                    if (col < n) lub_tile[orow * LUB_LDS + piv_of_col[col]] = a[s][c];
                 }
             }
         }
     }
     // sign of the permutation j -> piv_of_col[j]: parallel inversion count
-    __syncthreads();
     int inv = 0;
-    if (!singular && tid < n)
+    if (!tsing && tid < n)
         for (int k = tid + 1; k < n; k++) inv += piv_of_col[k] < piv_of_col[tid];
     const int par = __syncthreads_count(inv & 1) & 1;
+    if (!tsing)
+        for (int idx = tid; idx < n * n; idx += LUB_THREADS) {
+            const int r = idx / n, c = idx - r * n;
+            Ai_out[idx] = lub_tile[r * LUB_LDS + c];
+        }
+    LUB_T(9);
+#ifdef WFO_LUB_CLOCKS
+    if (tid == 32) for (int i = 0; i < 10; i++) g_lub_clk[i] = t_acc[i];
+#endif
     if (tid == 0) {
-        info->det = singular ? 0.0 : (par ? -det : det);
-        info->min_piv = minp;
-        info->max_piv = maxp;
-        info->singular = singular;
+        info->det = tsing ? 0.0 : (par ? -tdet : tdet);
+        info->min_piv = tmin;
+        info->max_piv = tmax;
+        info->singular = tsing;
     }
 }
 

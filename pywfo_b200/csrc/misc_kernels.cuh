@@ -62,43 +62,6 @@ __global__ void w_init_kernel(const double *__restrict__ S, int ld_s, int n, int
     Wb[idx] = (r < v && c < v) ? S[(size_t)(n + r) * ld_s + n + c] : 0.0;
 }
 
-// bra side of the rank-update tier.  exc points at the first excitation of the shard.
-// X is v x n.  dk0[k] = D(k, GS) = s_k det(A) X[t,f].
-__global__ void t1_prep_bra_kernel(const int32_t *__restrict__ exc, int ksh, int n, int v,
-                                   const double *__restrict__ X, const BaseInfo *__restrict__ info,
-                                   BraMeta *__restrict__ meta, double *__restrict__ scale,
-                                   double *__restrict__ dk0) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= ksh) return;
-    int f = exc[2 * k], t = exc[2 * k + 1];
-    const double detA = info->det;
-    BraMeta m;
-    double s;
-    if (f < 0) { m.f = 0; m.woff = v * (v + 1); m.x = 1.0; s = 1.0; }
-    else { m.f = f; m.woff = t * (v + 1); m.x = X[(size_t)t * n + f]; s = app_sign(f, n); }
-    meta[k] = m;
-    scale[k] = s * detA;
-    dk0[k] = s * detA * m.x;
-}
-
-// ket side: Y is n x v.  d0l[l] = D(GS, l) = s_l det(A) Y[f',t'];  sgn[l] = s_l.
-__global__ void t1_prep_ket_kernel(const int32_t *__restrict__ exc, int kk, int n, int v,
-                                   const double *__restrict__ Y, const BaseInfo *__restrict__ info,
-                                   KetMeta *__restrict__ meta, double *__restrict__ sgn,
-                                   double *__restrict__ d0l) {
-    int l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= kk) return;
-    int f = exc[2 * l], t = exc[2 * l + 1];
-    const double detA = info->det;
-    KetMeta m;
-    double s;
-    if (f < 0) { m.aoff = 0; m.tp = v; m.y = 1.0; s = 1.0; }
-    else { m.aoff = f * n; m.tp = t; m.y = Y[(size_t)f * v + t]; s = app_sign(f, n); }
-    meta[l] = m;
-    sgn[l] = s;
-    d0l[l] = s * detA * m.y;
-}
-
 // both sides in one launch: the first cdiv(ksh+1,256) CTAs do the bra table, the rest the ket table.
 // Bra row ksh is a virtual ground-state row (x = 1, zero row of W): its pair values are y_l, so its
 // row of G is w_j = sum_l D(0,l) Ck[j][l], the ket-side factor of the cross term, for free.
@@ -217,19 +180,6 @@ finalize3_kernel(const double *__restrict__ P, int n_slabs, int n_bra, int ldg, 
     }
 }
 
-// G[k][j] = sum_p gpart[p][k][j]  (fixed order);  column n_ket carries dk0[k].
-__global__ void sum_parts_kernel(const double *__restrict__ gpart, int n_parts, int ksh, int ldg,
-                                 int n_ket, const double *__restrict__ dk0, double *__restrict__ G) {
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long tot = (long long)ksh * ldg;
-    if (idx >= tot) return;
-    int j = (int)(idx % ldg);
-    double s = 0.0;
-    for (int p = 0; p < n_parts; p++) s += gpart[(size_t)p * tot + idx];
-    if (j == n_ket) s = dk0[idx / ldg];
-    G[idx] = s;
-}
-
 // wpart[z][j] = sum over slab z of Ck[j][l] * d0l[l]  (grid (n_ket, KGS_SLABS), fixed-shape tree)
 constexpr int KGS_SLABS = 8;
 __global__ void __launch_bounds__(256)
@@ -248,24 +198,6 @@ ket_gs_dot_kernel(const double *__restrict__ Ck, int kk, int n_ket, int ldw, con
         __syncthreads();
     }
     if (threadIdx.x == 0) wpart[z * ldw + j] = red[0];
-}
-
-// out[i][j] = d00 * sum_z P[z][i][j] + sigma * (sum_z P[z][i][n_ket]) * sum_z wpart[z][j]
-__global__ void finalize_kernel(const double *__restrict__ P, int n_slabs, int n_bra, int ldg, int n_ket,
-                                const double *__restrict__ wpart, const double *__restrict__ d00,
-                                double sigma, double *__restrict__ out, int ld_out) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_bra * n_ket) return;
-    int i = idx / n_ket, j = idx - i * n_ket;
-    double a = 0.0, u = 0.0, wj = 0.0;
-#pragma unroll
-    for (int z = 0; z < KGS_SLABS; z++) wj += wpart[z * n_ket + j];
-    size_t slab = (size_t)n_bra * ldg;
-    for (int z = 0; z < n_slabs; z++) {
-        a += P[z * slab + (size_t)i * ldg + j];
-        u += P[z * slab + (size_t)i * ldg + n_ket];
-    }
-    out[(size_t)i * ld_out + j] = (*d00) * a + sigma * u * wj;
 }
 
 // ---- closed-form tier (T2) helpers ---------------------------------------------------------
