@@ -121,7 +121,7 @@ static size_t t0_smem_bytes(int n) { return (size_t)n * (n | 1) * sizeof(double)
 static int t0_threads(int n) { return n > 64 ? 256 : 128; }
 
 #ifndef WFO_T0_WPM_DEFAULT
-#define WFO_T0_WPM_DEFAULT 0
+#define WFO_T0_WPM_DEFAULT 1
 #endif
 
 static bool use_v1() {
@@ -443,6 +443,8 @@ int wfo_create(int device, wfo_ctx **out) {
                                   (int)lub_smem_bytes(LUB_MAXN)));
     WFO_CUDA(cudaMalloc(&c->ns_slots, 128 * sizeof(double)));
     WFO_CUDA(cudaMallocHost(&c->h_slots, 128 * sizeof(double)));
+    WFO_CUDA(cudaMallocHost(&c->h_info, sizeof(BaseInfo)));
+    WFO_CUDA(cudaEventCreateWithFlags(&c->ev_info, cudaEventDisableTiming));
     *out = c;
     return WFO_OK;
 }
@@ -455,6 +457,8 @@ int wfo_destroy(wfo_ctx *ctx) {
     if (ctx->gscratch) cudaFree(ctx->gscratch);
     if (ctx->ns_slots) cudaFree(ctx->ns_slots);
     if (ctx->h_slots) cudaFreeHost(ctx->h_slots);
+    if (ctx->h_info) cudaFreeHost(ctx->h_info);
+    cudaEventDestroy(ctx->ev_info);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     for (int i = 0; i < 24; i++) cudaEventDestroy(ctx->pev[i]);
@@ -819,15 +823,17 @@ static int state_overlaps_block(wfo_ctx *ctx, size_t arena_off, const double *s_
         // ---- one base factorisation, then the three block products
         base_inverse_kernel<<<1, LUB_THREADS, lub_smem_bytes(n), st>>>(s_mo, n_mo, n, p.Ai, p.info);
         WFO_LAUNCH_CHECK(ctx);
-        // the conditioning of the base block decides whether the rank-update tier is usable:
-        // one 32-byte read-back (the only host synchronisation of the call)
-        BaseInfo hinfo;
+        // the conditioning of the base block decides whether the rank-update tier is usable.  The
+        // 32-byte verdict travels to pinned host memory behind the kernel; the rank-update kernels
+        // are queued right away (speculatively) and the host looks at the verdict after queueing
+        // them: no bubble on the GPU, and the brute-force tier simply overwrites `out` if needed.
         WFO_PHASE(ctx, st, "base_inverse");
-        WFO_CUDA(cudaMemcpyAsync(&hinfo, p.info, sizeof(hinfo), cudaMemcpyDeviceToHost, st));
-        WFO_CUDA(cudaStreamSynchronize(st));
-        WFO_PHASE(ctx, st, "info_sync");
-        const bool ok = !hinfo.singular && hinfo.min_piv > 1e-6 * hinfo.max_piv;
         WFO_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+        WFO_CUDA(cudaEventRecord(ctx->ev_fork, st));            // base inverse done ...
+        WFO_CUDA(cudaStreamWaitEvent(s2, ctx->ev_fork, 0));     // ... the copy rides on the side stream
+        WFO_CUDA(cudaMemcpyAsync(ctx->h_info, p.info, sizeof(BaseInfo), cudaMemcpyDeviceToHost, s2));
+        WFO_CUDA(cudaEventRecord(ctx->ev_info, s2));
+        const bool ok = true;   // speculation; checked below
         if (ok) {
             const double *Bblk = s_mo + n;                    // occ  x virt
             const double *Cblk = s_mo + (size_t)n * n_mo;     // virt x occ
@@ -854,10 +860,15 @@ static int state_overlaps_block(wfo_ctx *ctx, size_t arena_off, const double *s_
             WFO_PHASE(ctx, st, "t1_fused");
             d00_ptr = &p.info->det;
             used = WFO_TIER_UPDATE;
-        } else if (!may_t0) {
-            return set_err(WFO_ERR_SINGULAR,
-                           "state_overlaps: base block S_MO[:occ,:occ] is (numerically) singular, "
-                           "tier UPDATE not applicable");
+        }
+        WFO_CUDA(cudaEventSynchronize(ctx->ev_info));
+        const BaseInfo &hinfo = *ctx->h_info;
+        if (hinfo.singular || !(hinfo.min_piv > 1e-6 * hinfo.max_piv)) {
+            used = -1;   // what was queued computes garbage into buffers the brute-force tier rewrites
+            if (!may_t0)
+                return set_err(WFO_ERR_SINGULAR,
+                               "state_overlaps: base block S_MO[:occ,:occ] is (numerically) singular, "
+                               "tier UPDATE not applicable");
         }
     }
     if (used < 0) {

@@ -69,6 +69,8 @@ __device__ __forceinline__ unsigned hi_abs(double x) {
 
 }  // namespace wfo
 
+namespace wfo { struct BaseInfo; }
+
 struct wfo_ctx {
     int device;
     int sm_count;
@@ -79,6 +81,8 @@ struct wfo_ctx {
     double *ns_slots;      // device: norms + per-iteration residuals of the Newton-Schulz inverse (128 doubles)
     double *h_slots;       // pinned host mirror
     int last_inverse_iters;
+    wfo::BaseInfo *h_info;  // pinned host copy of the base-block verdict
+    cudaEvent_t ev_info;
     char *scratch;         // device arena, grown on demand
     size_t scratch_bytes;
     double *gscratch;      // per-CTA LU working matrices (global-scratch variant of the T0 kernel)
