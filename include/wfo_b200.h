@@ -38,7 +38,7 @@ extern "C" {
 #define WFO_ERR_ARG 2
 #define WFO_ERR_SINGULAR 3 /* base block S_MO[:occ,:occ] singular: tier 1/2 not applicable */
 #define WFO_ERR_EMPTY_STATE 4 /* pywfo.main.overlaps semantics: a state keeps no excitation (ValueError upstream) */
-#define WFO_ERR_NOCONV 5 /* device inverse did not converge (singular / extremely ill-conditioned MO matrix) */
+#define WFO_ERR_NOCONV 5 /* device inverse did not converge (singular / extremely ill-conditioned MO matrix; LinAlgError in Python) */
 
 /* where the inverse of the MO matrix in S_AO = C^-1 C^-T (pywfo/main.py:301-311) comes from */
 #define WFO_AO_GIVEN 0 /* the caller supplies c_inv (e.g. np.linalg.inv, exactly as upstream) */
@@ -81,7 +81,7 @@ int wfo_sao_dev(wfo_ctx *ctx, const double *c_inv, int n, double *s_ao, void *st
  * GEMMs; quadratically convergent for every non-singular A, about 2 log2(cond) + 10 iterations.
  * `work` = 2 n*n doubles of device scratch (NULL: from the context).  Synchronises the stream
  * every few iterations to read the residual max|A X - I|.  WFO_ERR_NOCONV if it does not
- * converge within 100 iterations (the Python layer then falls back to LAPACK). */
+ * converge within 100 iterations (singular or extremely ill-conditioned input). */
 int wfo_inverse_dev(wfo_ctx *ctx, const double *a, int n, double *a_inv, double *work, void *stream);
 int wfo_inverse_host(wfo_ctx *ctx, const double *a, int n, double *a_inv);
 /* generic C = alpha*op(A) op(B) + beta*C (row-major; ta/tb: 0 = N, 1 = T) */

@@ -8,10 +8,10 @@
 The host only checks shapes; everything the reference computes goes to the CUDA
 library through ``include/wfo_b200.h``: the inverse of the MO matrix for
 ``ao_ovlps in {"bra","ket"}`` (pywfo/main.py:303; Newton-Schulz on the FP64
-tensor-core GEMM, LAPACK only as a fallback), S_AO = Cinv Cinv^T, S_MO, the
+tensor-core GEMM), S_AO = Cinv Cinv^T, S_MO, the
 thresholding of the CI vectors (main.py:539-540, 112, 122-123), every
 determinant pair and the CI-weighted reduction.  Extra keyword arguments
-(``tier``, ``device``, ``host_inverse``) are a superset of the reference signature.
+(``tier``, ``device``, ``c_inv``) are a superset of the reference signature.
 
 When ``torch.distributed`` is initialised with more than one rank, each rank
 computes the partial matrix of its shard of the bra excitations and the
@@ -37,13 +37,14 @@ def log(message, level="info"):
 
 def _mo_inverse(mos):
     """``np.linalg.inv(mos)`` of pywfo/main.py:303 on the device (Newton-Schulz on the FP64
-    tensor-core GEMM); LAPACK on the host only if that iteration does not converge."""
+    tensor-core GEMM).  A matrix the iteration cannot invert raises ``LinAlgError`` like numpy
+    does for a singular one; there is no host fallback."""
     try:
         return _lib.context().inverse_host(mos)
     except _lib.WfoError as exc:
         if exc.code != _lib.ERR_NOCONV:
             raise
-        return np.linalg.inv(mos)
+        raise np.linalg.LinAlgError("Singular matrix") from exc
 
 
 def get_S_AO(bra_mos, ket_mos, ao_ovlps):
@@ -73,7 +74,7 @@ def moovlp_dots(mos1, mos2, S_AO):
 
 
 def _state_overlaps(semantics, sigma, bra_mos, ket_mos, bra_ci, ket_ci, occ, ci_thresh, ao_ovlps,
-                    tier="auto", device=None, host_inverse=False):
+                    tier="auto", device=None, c_inv=None):
     bra_mos = np.asarray(bra_mos, dtype=np.float64)
     ket_mos = np.asarray(ket_mos, dtype=np.float64)
     bra_ci = np.asarray(bra_ci, dtype=np.float64)
@@ -86,25 +87,21 @@ def _state_overlaps(semantics, sigma, bra_mos, ket_mos, bra_ci, ket_ci, occ, ci_
     ctx = _lib.context(device)
     n_bra, n_ket = bra_ci.shape[0], ket_ci.shape[0]
     if isinstance(ao_ovlps, str):
-        # everything on the device: the inverse behind S_AO (main.py:303; ``host_inverse=True``
-        # keeps upstream's LAPACK call instead), S_AO, S_MO, the selection of excitations above
-        # the threshold, every determinant pair and the CI-weighted reduction
+        # everything on the device: the inverse behind S_AO (main.py:303), S_AO, S_MO, the selection
+        # of excitations above the threshold, every determinant pair and the CI-weighted reduction.
+        # ``c_inv`` (optional input): an inverse of the chosen MO matrix the caller already has.
         if ao_ovlps not in ("bra", "ket"):
             raise KeyError(ao_ovlps)   # upstream: dict lookup, main.py:303
         side = _lib.AO_BRA if ao_ovlps == "bra" else _lib.AO_KET
         rank, world = dist.world()
-        kw = dict(semantics=0 if semantics == "cache" else 1, tier=tier, rank=rank, world=world)
-        part = None
-        if not host_inverse:
-            try:
-                part, _ = ctx.overlaps_ci_host(bra_mos, ket_mos, None, occ, bra_ci, ket_ci, ci_thresh,
-                                               ao_side=side, **kw)
-            except _lib.WfoError as exc:
-                if exc.code != _lib.ERR_NOCONV:
-                    raise
-        if part is None:   # asked for, or the device iteration did not converge: LAPACK as upstream
-            c_inv = np.linalg.inv(bra_mos if ao_ovlps == "bra" else ket_mos)
-            part, _ = ctx.overlaps_ci_host(bra_mos, ket_mos, c_inv, occ, bra_ci, ket_ci, ci_thresh, **kw)
+        try:
+            part, _ = ctx.overlaps_ci_host(bra_mos, ket_mos, c_inv, occ, bra_ci, ket_ci, ci_thresh,
+                                           ao_side=side, semantics=0 if semantics == "cache" else 1,
+                                           tier=tier, rank=rank, world=world)
+        except _lib.WfoError as exc:
+            if exc.code != _lib.ERR_NOCONV:
+                raise
+            raise np.linalg.LinAlgError("Singular matrix") from exc   # what np.linalg.inv raises upstream
         return dist.sum_over_ranks(part, device=ctx.device)
     if not isinstance(ao_ovlps, np.ndarray):
         raise Exception("Invalid AO overlaps!")

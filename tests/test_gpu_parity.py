@@ -429,16 +429,26 @@ def test_device_inverse_reports_singular(ctx):
 @pytest.mark.parametrize("name", ["h2o2", "r_n17", "r_odd"])
 @pytest.mark.parametrize("ao", ["ket", "bra"])
 def test_device_inverse_path_equals_host_inverse_path(ctx, name, ao):
-    """ao_ovlps in {"bra","ket"}: inverse on the device (default) vs upstream's LAPACK call."""
+    """ao_ovlps in {"bra","ket"}: inverse formed on the device (default) vs an inverse supplied by the
+    caller (here numpy's, i.e. the number upstream's LAPACK call produces)."""
     from pywfo_b200 import main
     g = load_golden(name)
     occ = int(g["occ"])
     args = (g["bra_mos"], g["ket_mos"], g["bra_ci"], g["ket_ci"], occ)
     thr = float(g["ci_thresh"]) if "ci_thresh" in g else 1e-2
     dev = main.overlaps_cache(*args, ci_thresh=thr, ao_ovlps=ao)
-    host = main.overlaps_cache(*args, ci_thresh=thr, ao_ovlps=ao, host_inverse=True)
+    host = main.overlaps_cache(*args, ci_thresh=thr, ao_ovlps=ao,
+                               c_inv=np.linalg.inv(g["bra_mos"] if ao == "bra" else g["ket_mos"]))
     assert_parity(dev, host)
     want = {("h2o2", "ket"): "ref_cache_4x4_1e-2", ("r_n17", "ket"): "ref_overlaps_cache", ("r_odd", "ket"): "ref_overlaps_cache",
             ("r_n17", "bra"): "ref_overlaps_cache_bra", ("r_odd", "bra"): "ref_overlaps_cache_bra"}.get((name, ao))
     if want:
         assert_parity(dev, g[want])
+
+
+def test_singular_mo_matrix_raises_like_numpy(ctx):
+    from pywfo_b200 import main
+    mos = np.ones((6, 6))
+    ci = np.full((1, 2, 4), 0.3)
+    with pytest.raises(np.linalg.LinAlgError):
+        main.overlaps_cache(mos, mos, ci, ci, 2)
