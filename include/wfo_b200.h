@@ -144,6 +144,17 @@ int wfo_overlaps_ci_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_
                          const double *c_inv, int ao_side, int n_mo, int n_occ, const double *bra_ci, int n_bra,
                          const double *ket_ci, int n_ket, double ci_thresh, int semantics, int tier,
                          int rank, int world, double *out, int32_t *info);
+/* Trajectory driver: n_cycles geometries (mos: n_cycles x n_mo x n_mo, ci: n_cycles x n_states x n_occ x
+ * n_virt, host), the state-overlap matrices of n_pairs (bra cycle, ket cycle) index pairs -> out
+ * (n_pairs x n_states x n_states).  Replaces a loop of pywfo.main.overlaps_cache / overlaps calls over
+ * the steps of a trajectory (how pysisyphus drives pywfo; pywfo/tests/ref_cytosin holds a 9-cycle
+ * example): every cycle is uploaded once and stays resident, the inverse behind S_AO (ao_side =
+ * WFO_AO_BRA or WFO_AO_KET) is formed once per cycle, per pair only S_AO, S_MO, the tables and the
+ * fused stages run.  info: {max K_bra, max K_ket, empty_state, tier of the last pair}. */
+int wfo_trajectory_ci_host(wfo_ctx *ctx, const double *mos, const double *ci, int n_cycles, int n_mo,
+                           int n_occ, int n_states, double ci_thresh, int semantics, int tier,
+                           int ao_side, const int32_t *pairs, int n_pairs, int rank, int world,
+                           double *out, int32_t *info);
 /* tier actually used by the last wfo_state_overlaps_* call of this context */
 int wfo_last_tier(const wfo_ctx *ctx);
 /* device time (ms, CUDA events on the launching stream) of the dominant

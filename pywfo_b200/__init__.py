@@ -7,5 +7,5 @@ arithmetic runs in hand-written sm_100a CUDA kernels behind the C ABI of
 """
 from . import excitations  # noqa: F401
 
-__all__ = ["main", "dets", "helpers", "excitations", "dist"]
+__all__ = ["main", "dets", "helpers", "excitations", "dist", "trajectory", "formats"]
 __version__ = "0.1.0"

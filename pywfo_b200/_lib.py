@@ -49,6 +49,8 @@ SIGNATURES = {
     "wfo_inverse_host": (C.c_int, [c_vp, c_vp, C.c_int, c_vp]),
     "wfo_overlaps_ci_host": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, c_vp, C.c_int,
                                        C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
+    "wfo_trajectory_ci_host": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
+                                         C.c_int, c_vp, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
     "wfo_last_tier": (C.c_int, [c_vp]),
     "wfo_set_timing": (C.c_int, [c_vp, C.c_int]),
     "wfo_last_kernel_ms": (C.c_double, [c_vp]),
@@ -215,6 +217,29 @@ class Context:
                                            _hptr(bci), bci.shape[0], _hptr(kci), kci.shape[0], float(ci_thresh),
                                            int(semantics), TIERS[tier], int(rank), int(world), _hptr(out),
                                            _hptr(info))
+        if rc == 4:
+            raise ValueError("not enough values to unpack (expected 2, got 0)")   # pywfo/main.py:186
+        check(rc)
+        return out, info
+
+    def trajectory_ci_host(self, mos, ci, n_occ, pairs, ci_thresh, semantics=0, tier="auto", ao_side=AO_KET,
+                           rank=0, world=1):
+        """State overlaps of (bra cycle, ket cycle) pairs of a trajectory; every cycle is uploaded once.
+        mos (n_cycles, n_mo, n_mo), ci (n_cycles, n_states, n_occ, n_virt), pairs (n_pairs, 2).
+        Returns (n_pairs, n_states, n_states) and info."""
+        mos, ci = as_f64(mos), as_f64(ci)
+        pr = as_i32(pairs).reshape(-1, 2)
+        n_cycles, n_mo = mos.shape[0], mos.shape[1]
+        if mos.ndim != 3 or mos.shape[2] != n_mo:
+            raise ValueError("mos must have shape (n_cycles, n_mo, n_mo)")
+        if ci.ndim != 4 or ci.shape[0] != n_cycles or ci.shape[2:] != (n_occ, n_mo - n_occ):
+            raise ValueError("ci must have shape (n_cycles, n_states, occ, n_mo - occ)")
+        ns = ci.shape[1]
+        out = np.empty((pr.shape[0], ns, ns))
+        info = np.zeros(4, dtype=np.int32)
+        rc = self.lib.wfo_trajectory_ci_host(self.handle, _hptr(mos), _hptr(ci), n_cycles, n_mo, int(n_occ), ns,
+                                             float(ci_thresh), int(semantics), TIERS[tier], int(ao_side), _hptr(pr),
+                                             pr.shape[0], int(rank), int(world), _hptr(out), _hptr(info))
         if rc == 4:
             raise ValueError("not enough values to unpack (expected 2, got 0)")   # pywfo/main.py:186
         check(rc)

@@ -455,6 +455,7 @@ int wfo_destroy(wfo_ctx *ctx) {
     cudaDeviceSynchronize();
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->gscratch) cudaFree(ctx->gscratch);
+    if (ctx->resident) cudaFree(ctx->resident);
     if (ctx->ns_slots) cudaFree(ctx->ns_slots);
     if (ctx->h_slots) cudaFreeHost(ctx->h_slots);
     if (ctx->h_info) cudaFreeHost(ctx->h_info);
@@ -1092,90 +1093,100 @@ static int build_tables_dev(wfo_ctx *ctx, const double *ci_dev, int n_states, in
     return WFO_OK;
 }
 
-int wfo_overlaps_ci_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos, const double *c_inv, int ao_side,
-                         int n_mo, int n_occ, const double *bra_ci, int n_bra, const double *ket_ci, int n_ket,
-                         double ci_thresh, int semantics, int tier, int rank, int world, double *out,
-                         int32_t *info) {
-    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL");
-    if (!bra_mos || !ket_mos || !bra_ci || !ket_ci || !out)
-        return set_err(WFO_ERR_ARG, "overlaps_ci_host: NULL pointer");
-    if (ao_side != WFO_AO_GIVEN && ao_side != WFO_AO_BRA && ao_side != WFO_AO_KET)
-        return set_err(WFO_ERR_ARG, "overlaps_ci_host: ao_side must be WFO_AO_GIVEN, WFO_AO_BRA or WFO_AO_KET");
-    if (ao_side == WFO_AO_GIVEN && !c_inv) return set_err(WFO_ERR_ARG, "overlaps_ci_host: c_inv is NULL");
-    if (n_mo < 1 || n_occ < 1 || n_occ > n_mo || n_bra < 1 || n_ket < 1 || world < 1 || rank < 0 || rank >= world)
-        return set_err(WFO_ERR_ARG, "overlaps_ci_host: bad sizes");
-    if (semantics != 0 && semantics != 1) return set_err(WFO_ERR_ARG, "overlaps_ci_host: semantics must be 0 or 1");
-    WFO_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
+}  // extern "C"
+
+// ---- raw-CI path: phase-1 workspace (sizes depend on n_mo, n_occ and the state counts only) lives in
+// the context's RESIDENT buffer next to the inputs; the arena holds what is sized by the number of
+// surviving excitations.  Neither moves during a call.
+struct CiWork {
+    double *smo, *sao, *work, *work2, *inv;   // n_mo^2 each; work and work2 are contiguous (device inverse)
+    int *fl_b, *of_b, *fl_k, *of_k, *tot_b, *tot_k;
+    int32_t *exc_b, *exc_k;
+    double *out;
+};
+template <typename AR>
+static void carve_ciwork(AR &ar, CiWork &w, size_t nsq, int count, int n_bra, int n_ket) {
+    w.smo = ar.template take<double>(nsq);
+    w.sao = ar.template take<double>(nsq);
+    w.work = ar.template take<double>(nsq);
+    w.work2 = ar.template take<double>(nsq);
+    w.inv = ar.template take<double>(nsq);
+    w.fl_b = ar.template take<int>(count);
+    w.of_b = ar.template take<int>(count);
+    w.fl_k = ar.template take<int>(count);
+    w.of_k = ar.template take<int>(count);
+    w.tot_b = ar.template take<int>(1 + n_bra);
+    w.tot_k = ar.template take<int>(1 + n_ket);
+    w.exc_b = ar.template take<int32_t>(2 * (size_t)count);
+    w.exc_k = ar.template take<int32_t>(2 * (size_t)count);
+    w.out = ar.template take<double>((size_t)n_bra * n_ket);
+}
+
+static int ensure_resident(wfo_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->resident_bytes) return WFO_OK;
+    WFO_CUDA(cudaDeviceSynchronize());
+    if (ctx->resident) WFO_CUDA(cudaFree(ctx->resident));
+    ctx->resident = nullptr;
+    ctx->resident_bytes = 0;
+    const size_t want = bytes + bytes / 8 + (1 << 20);
+    WFO_CUDA(cudaMalloc(&ctx->resident, want));
+    ctx->resident_bytes = want;
+    return WFO_OK;
+}
+
+// One (bra, ket) pair from DEVICE inputs: S_AO, S_MO on the side stream (from d_inv if given, else the
+// inverse of the chosen MO matrix is formed first), excitation tables on the main stream, then the
+// fused stages on this rank's shard.  Result in w.out (device).  `zero` is set when the result is
+// identically zero (no excitation survives) and w.out was not written.
+static int overlaps_ci_core(wfo_ctx *ctx, const CiWork &w, const double *d_bra, const double *d_ket,
+                            const double *d_inv, int ao_side, int n_mo, int n_occ, const double *d_bci, int n_bra,
+                            const double *d_kci, int n_ket, double ci_thresh, int semantics, int tier, int rank,
+                            int world, bool side_after_main, int32_t *info, bool *zero, cudaStream_t st) {
     const int n = n_occ, v = n_mo - n_occ, count = n * v;
     const int strict = semantics == 1;
     const double sigma = semantics == 1 ? -1.0 : 1.0;
-    const size_t nsq = (size_t)n_mo * n_mo;
-    if (info) { info[0] = info[1] = 0; info[2] = 0; info[3] = -1; }
-    if (count == 0) {   // no virtual orbitals: no excitations, all sums are empty
-        memset(out, 0, (size_t)n_bra * n_ket * sizeof(double));
-        return WFO_OK;
+    *zero = false;
+    cudaStream_t s2 = ctx->stream2;
+    if (side_after_main) {   // the side stream may not overwrite S_MO / the scratch while earlier main-stream work reads them
+        WFO_CUDA(cudaEventRecord(ctx->ev_fork, st));
+        WFO_CUDA(cudaStreamWaitEvent(s2, ctx->ev_fork, 0));
     }
-    // ---- phase 1: uploads, S_MO chain, flags + scans
-    Sizer sz;
-    sz.take<double>(nsq); sz.take<double>(nsq); sz.take<double>(nsq); sz.take<double>(nsq); sz.take<double>(nsq); sz.take<double>(nsq);
-    sz.take<double>(nsq);
-    sz.take<double>((size_t)n_bra * count); sz.take<double>((size_t)n_ket * count);
-    sz.take<int>(count); sz.take<int>(count); sz.take<int>(count); sz.take<int>(count);
-    sz.take<int>(1 + n_bra); sz.take<int>(1 + n_ket);
-    sz.take<int32_t>(2 * (size_t)count); sz.take<int32_t>(2 * (size_t)count);
-    sz.take<double>((size_t)n_bra * n_ket);
-    WFO_TRY(ensure_scratch(ctx, sz.off));
-    Arena ar{ctx->scratch, ctx->scratch_bytes, 0};
-    double *d_smo = ar.take<double>(nsq), *d_bra = ar.take<double>(nsq), *d_ket = ar.take<double>(nsq),
-           *d_inv = ar.take<double>(nsq), *d_sao = ar.take<double>(nsq), *d_work = ar.take<double>(nsq);
-    double *d_work2 = ar.take<double>(nsq);   // d_work, d_work2 contiguous: scratch of the device inverse
-    double *d_bci = ar.take<double>((size_t)n_bra * count), *d_kci = ar.take<double>((size_t)n_ket * count);
-    int *fl_b = ar.take<int>(count), *of_b = ar.take<int>(count), *fl_k = ar.take<int>(count), *of_k = ar.take<int>(count);
-    int *tot_b = ar.take<int>(1 + n_bra), *tot_k = ar.take<int>(1 + n_ket);
-    int32_t *exc_b = ar.take<int32_t>(2 * (size_t)count), *exc_k = ar.take<int32_t>(2 * (size_t)count);
-    double *d_out = ar.take<double>((size_t)n_bra * n_ket);
-    const size_t front1 = ar.off;
-    // main stream: raw CI tensors up, union flags + scans; side stream (concurrently): MO matrices up,
-    // the inverse behind S_AO (device Newton-Schulz unless the caller supplies it), S_AO, S_MO
-    WFO_CUDA(cudaMemcpyAsync(d_bci, bra_ci, (size_t)n_bra * count * 8, cudaMemcpyHostToDevice, st));
-    WFO_CUDA(cudaMemcpyAsync(d_kci, ket_ci, (size_t)n_ket * count * 8, cudaMemcpyHostToDevice, st));
-    WFO_TRY(build_tables_dev(ctx, d_bci, n_bra, n, v, ci_thresh, strict, 0, fl_b, of_b, tot_b, st));
-    WFO_TRY(build_tables_dev(ctx, d_kci, n_ket, n, v, ci_thresh, strict, 1, fl_k, of_k, tot_k, st));
-    {
-        cudaStream_t s2 = ctx->stream2;
-        WFO_CUDA(cudaMemcpyAsync(d_bra, bra_mos, nsq * 8, cudaMemcpyHostToDevice, s2));
-        WFO_CUDA(cudaMemcpyAsync(d_ket, ket_mos, nsq * 8, cudaMemcpyHostToDevice, s2));
-        (void)d_work2;
-        if (ao_side == WFO_AO_GIVEN) WFO_CUDA(cudaMemcpyAsync(d_inv, c_inv, nsq * 8, cudaMemcpyHostToDevice, s2));
-        else WFO_TRY(wfo_inverse_dev(ctx, ao_side == WFO_AO_BRA ? d_bra : d_ket, n_mo, d_inv, d_work, s2));
-        WFO_TRY(wfo_sao_dev(ctx, d_inv, n_mo, d_sao, s2));
-        WFO_TRY(wfo_smo_dev(ctx, d_bra, d_sao, d_ket, n_mo, n_mo, n_mo, n_mo, d_smo, d_work, s2));
-        WFO_CUDA(cudaEventRecord(ctx->ev_join, s2));
-        WFO_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    WFO_TRY(build_tables_dev(ctx, d_bci, n_bra, n, v, ci_thresh, strict, 0, w.fl_b, w.of_b, w.tot_b, st));
+    WFO_TRY(build_tables_dev(ctx, d_kci, n_ket, n, v, ci_thresh, strict, 1, w.fl_k, w.of_k, w.tot_k, st));
+    if (!d_inv) {
+        WFO_TRY(wfo_inverse_dev(ctx, ao_side == WFO_AO_BRA ? d_bra : d_ket, n_mo, w.inv, w.work, s2));
+        d_inv = w.inv;
     }
+    WFO_TRY(wfo_sao_dev(ctx, d_inv, n_mo, w.sao, s2));
+    WFO_TRY(wfo_smo_dev(ctx, d_bra, w.sao, d_ket, n_mo, n_mo, n_mo, n_mo, w.smo, w.work, s2));
+    WFO_CUDA(cudaEventRecord(ctx->ev_join, s2));
+    WFO_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     // ---- the table sizes (and per-state counts) come back: 2 small copies, one sync
     std::vector<int> hb_v(1 + n_bra), hk_v(1 + n_ket);
     int *hb = hb_v.data(), *hk = hk_v.data();
-    WFO_CUDA(cudaMemcpyAsync(hb, tot_b, (1 + n_bra) * sizeof(int), cudaMemcpyDeviceToHost, st));
-    WFO_CUDA(cudaMemcpyAsync(hk, tot_k, (1 + n_ket) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    WFO_CUDA(cudaMemcpyAsync(hb, w.tot_b, (1 + n_bra) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    WFO_CUDA(cudaMemcpyAsync(hk, w.tot_k, (1 + n_ket) * sizeof(int), cudaMemcpyDeviceToHost, st));
     WFO_CUDA(cudaStreamSynchronize(st));
     const int kb = hb[0], kk = hk[0];
-    if (info) { info[0] = kb; info[1] = kk; }
+    if (info) { info[0] = kb; info[1] = kk; info[2] = 0; info[3] = -1; }
     if (semantics == 1) {   // pywfo/main.py:186: a state without excitations cannot be unpacked
-        for (int i = 0; i < n_bra; i++) if (hb[1 + i] == 0) { if (info) info[2] = 1; }
-        for (int i = 0; i < n_ket; i++) if (hk[1 + i] == 0) { if (info) info[2] = 1; }
-        if (info && info[2]) return set_err(WFO_ERR_EMPTY_STATE, "overlaps: a state keeps no excitation above the threshold");
+        bool empty = false;
+        for (int i = 0; i < n_bra; i++) empty = empty || hb[1 + i] == 0;
+        for (int i = 0; i < n_ket; i++) empty = empty || hk[1 + i] == 0;
+        if (empty) {
+            if (info) info[2] = 1;
+            return set_err(WFO_ERR_EMPTY_STATE, "overlaps: a state keeps no excitation above the threshold");
+        }
     }
     if (kb == 0 || kk == 0) {
-        memset(out, 0, (size_t)n_bra * n_ket * sizeof(double));
+        *zero = true;
         return WFO_OK;
     }
     // ---- phase 2: coefficient matrices, then the fused stages on this rank's shard
     const int base = kb / world, rem = kb % world;
     const int k_begin = rank * base + (rank < rem ? rank : rem);
     const int k_end = k_begin + base + (rank < rem ? 1 : 0);
-    size_t total = front1 + align_up((size_t)n_bra * kb * 8, 256) + align_up((size_t)n_ket * kk * 8, 256);
+    size_t total = align_up((size_t)n_bra * kb * 8, 256) + align_up((size_t)n_ket * kk * 8, 256);
     {
         bool want_t1 = false, may_t0 = false;
         WFO_TRY(resolve_tier(ctx, n, tier, &want_t1, &may_t0));
@@ -1184,39 +1195,151 @@ int wfo_overlaps_ci_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_
             Part q;
             WFO_TRY(make_part(ctx, ksh, kk, n_ket < MAX_KET_BLOCK ? n_ket : MAX_KET_BLOCK, may_t0, want_t1, &q));
             Plan p;
-            Sizer s2;
-            s2.off = total;
-            carve(s2, p, n, v, ksh, kk, n_bra, q.ldg, q.n_parts, q.n_slabs, may_t0, want_t1);
-            if (tier == WFO_TIER_CLOSED) s2.off = total + closed_form_bytes(n, v, n_bra, n_ket);
-            total = s2.off;
+            Sizer s2z;
+            s2z.off = total;
+            carve(s2z, p, n, v, ksh, kk, n_bra, q.ldg, q.n_parts, q.n_slabs, may_t0, want_t1);
+            if (tier == WFO_TIER_CLOSED) s2z.off = total + closed_form_bytes(n, v, n_bra, n_ket);
+            total = s2z.off;
         }
     }
-    char *before = ctx->scratch;
-    WFO_TRY(ensure_scratch_keep(ctx, total, front1));
-    const ptrdiff_t shift = ctx->scratch - before;   // arena may have moved: rebase the pointers
-    d_smo = (double *)((char *)d_smo + shift); d_bci = (double *)((char *)d_bci + shift); d_kci = (double *)((char *)d_kci + shift);
-    fl_b = (int *)((char *)fl_b + shift); of_b = (int *)((char *)of_b + shift);
-    fl_k = (int *)((char *)fl_k + shift); of_k = (int *)((char *)of_k + shift);
-    exc_b = (int32_t *)((char *)exc_b + shift); exc_k = (int32_t *)((char *)exc_k + shift);
-    d_out = (double *)((char *)d_out + shift);
-    Arena ar2{ctx->scratch, ctx->scratch_bytes, front1};
+    WFO_TRY(ensure_scratch(ctx, total));   // nothing of this call lives in the arena yet
+    Arena ar2{ctx->scratch, ctx->scratch_bytes, 0};
     double *d_cb = ar2.take<double>((size_t)n_bra * kb), *d_ck = ar2.take<double>((size_t)n_ket * kk);
-    emit_exc_kernel<<<cdiv(count, 256), 256, 0, st>>>(fl_b, of_b, n, v, 0, exc_b);
+    emit_exc_kernel<<<cdiv(count, 256), 256, 0, st>>>(w.fl_b, w.of_b, n, v, 0, w.exc_b);
     WFO_LAUNCH_CHECK(ctx);
-    emit_exc_kernel<<<cdiv(count, 256), 256, 0, st>>>(fl_k, of_k, n, v, 1, exc_k);
+    emit_exc_kernel<<<cdiv(count, 256), 256, 0, st>>>(w.fl_k, w.of_k, n, v, 1, w.exc_k);
     WFO_LAUNCH_CHECK(ctx);
-    emit_coeff_kernel<<<dim3(cdiv(count, 256), n_bra), 256, 0, st>>>(d_bci, fl_b, of_b, n, v, ci_thresh, strict, 0,
+    emit_coeff_kernel<<<dim3(cdiv(count, 256), n_bra), 256, 0, st>>>(d_bci, w.fl_b, w.of_b, n, v, ci_thresh, strict, 0,
                                                                     semantics == 1, kb, d_cb);
     WFO_LAUNCH_CHECK(ctx);
-    emit_coeff_kernel<<<dim3(cdiv(count, 256), n_ket), 256, 0, st>>>(d_kci, fl_k, of_k, n, v, ci_thresh, strict, 1,
+    emit_coeff_kernel<<<dim3(cdiv(count, 256), n_ket), 256, 0, st>>>(d_kci, w.fl_k, w.of_k, n, v, ci_thresh, strict, 1,
                                                                     semantics == 1, kk, d_ck);
     WFO_LAUNCH_CHECK(ctx);
-    char *before2 = ctx->scratch;
-    WFO_TRY(state_overlaps_impl(ctx, ar2.off, d_smo, n_mo, n, exc_b, kb, d_cb, n_bra, exc_k, kk, d_ck, n_ket, sigma,
-                                tier, k_begin, k_end, d_out, st));
-    if (ctx->scratch != before2) return set_err(WFO_ERR_CUDA, "internal: arena moved during a host call");
+    char *before = ctx->scratch;
+    WFO_TRY(state_overlaps_impl(ctx, ar2.off, w.smo, n_mo, n, w.exc_b, kb, d_cb, n_bra, w.exc_k, kk, d_ck, n_ket, sigma,
+                                tier, k_begin, k_end, w.out, st));
+    if (ctx->scratch != before) return set_err(WFO_ERR_CUDA, "internal: arena moved during a host call");
     if (info) info[3] = ctx->last_tier;
-    WFO_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n_bra * n_ket * 8, cudaMemcpyDeviceToHost, st));
+    return WFO_OK;
+}
+
+static int check_ci_args(const char *who, int ao_side, int n_mo, int n_occ, int n_bra, int n_ket, int semantics,
+                         int rank, int world) {
+    if (ao_side != WFO_AO_GIVEN && ao_side != WFO_AO_BRA && ao_side != WFO_AO_KET)
+        return set_err(WFO_ERR_ARG, "ao_side must be WFO_AO_GIVEN, WFO_AO_BRA or WFO_AO_KET");
+    if (n_mo < 1 || n_occ < 1 || n_occ > n_mo || n_bra < 1 || n_ket < 1 || world < 1 || rank < 0 || rank >= world)
+        return set_err(WFO_ERR_ARG, "bad sizes");
+    if (semantics != 0 && semantics != 1) return set_err(WFO_ERR_ARG, "semantics must be 0 or 1");
+    (void)who;
+    return WFO_OK;
+}
+
+extern "C" {
+
+int wfo_overlaps_ci_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos, const double *c_inv, int ao_side,
+                         int n_mo, int n_occ, const double *bra_ci, int n_bra, const double *ket_ci, int n_ket,
+                         double ci_thresh, int semantics, int tier, int rank, int world, double *out,
+                         int32_t *info) {
+    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL");
+    if (!bra_mos || !ket_mos || !bra_ci || !ket_ci || !out)
+        return set_err(WFO_ERR_ARG, "overlaps_ci_host: NULL pointer");
+    WFO_TRY(check_ci_args("overlaps_ci_host", ao_side, n_mo, n_occ, n_bra, n_ket, semantics, rank, world));
+    if (ao_side == WFO_AO_GIVEN && !c_inv) return set_err(WFO_ERR_ARG, "overlaps_ci_host: c_inv is NULL");
+    WFO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream, s2 = ctx->stream2;
+    const int n = n_occ, v = n_mo - n_occ, count = n * v;
+    const size_t nsq = (size_t)n_mo * n_mo;
+    if (info) { info[0] = info[1] = 0; info[2] = 0; info[3] = -1; }
+    if (count == 0) {   // no virtual orbitals: no excitations, all sums are empty
+        memset(out, 0, (size_t)n_bra * n_ket * sizeof(double));
+        return WFO_OK;
+    }
+    CiWork w;
+    Sizer sz;
+    sz.take<double>(nsq); sz.take<double>(nsq); sz.take<double>(nsq);
+    sz.take<double>((size_t)n_bra * count); sz.take<double>((size_t)n_ket * count);
+    carve_ciwork(sz, w, nsq, count, n_bra, n_ket);
+    WFO_TRY(ensure_resident(ctx, sz.off));
+    Arena ar{ctx->resident, ctx->resident_bytes, 0};
+    double *d_bra = ar.take<double>(nsq), *d_ket = ar.take<double>(nsq), *d_inv = ar.take<double>(nsq);
+    double *d_bci = ar.take<double>((size_t)n_bra * count), *d_kci = ar.take<double>((size_t)n_ket * count);
+    carve_ciwork(ar, w, nsq, count, n_bra, n_ket);
+    // main stream: raw CI tensors up (then the tables); side stream, concurrently: MO matrices up (then the
+    // inverse behind S_AO, S_AO, S_MO)
+    WFO_CUDA(cudaMemcpyAsync(d_bci, bra_ci, (size_t)n_bra * count * 8, cudaMemcpyHostToDevice, st));
+    WFO_CUDA(cudaMemcpyAsync(d_kci, ket_ci, (size_t)n_ket * count * 8, cudaMemcpyHostToDevice, st));
+    WFO_CUDA(cudaMemcpyAsync(d_bra, bra_mos, nsq * 8, cudaMemcpyHostToDevice, s2));
+    WFO_CUDA(cudaMemcpyAsync(d_ket, ket_mos, nsq * 8, cudaMemcpyHostToDevice, s2));
+    if (ao_side == WFO_AO_GIVEN) WFO_CUDA(cudaMemcpyAsync(d_inv, c_inv, nsq * 8, cudaMemcpyHostToDevice, s2));
+    bool zero = false;
+    WFO_TRY(overlaps_ci_core(ctx, w, d_bra, d_ket, ao_side == WFO_AO_GIVEN ? d_inv : nullptr, ao_side, n_mo, n_occ, d_bci,
+                             n_bra, d_kci, n_ket, ci_thresh, semantics, tier, rank, world, false, info, &zero, st));
+    if (zero) {
+        memset(out, 0, (size_t)n_bra * n_ket * sizeof(double));
+        return WFO_OK;
+    }
+    WFO_CUDA(cudaMemcpyAsync(out, w.out, (size_t)n_bra * n_ket * 8, cudaMemcpyDeviceToHost, st));
+    WFO_CUDA(cudaStreamSynchronize(st));
+    return WFO_OK;
+}
+
+/* Trajectory driver: n_cycles geometries, the state overlaps of n_pairs (bra cycle, ket
+ * cycle) pairs.  Every cycle's MO matrix and CI tensor is uploaded ONCE and stays resident, the inverse
+ * behind S_AO is formed once per cycle that needs it; per pair only S_AO, S_MO, the tables and the fused
+ * stages run.  upstream: a loop over pywfo.main.overlaps_cache / overlaps calls (pysisyphus' use of it). */
+int wfo_trajectory_ci_host(wfo_ctx *ctx, const double *mos, const double *ci, int n_cycles, int n_mo, int n_occ,
+                           int n_states, double ci_thresh, int semantics, int tier, int ao_side,
+                           const int32_t *pairs, int n_pairs, int rank, int world, double *out, int32_t *info) {
+    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL");
+    if (!mos || !ci || !pairs || !out) return set_err(WFO_ERR_ARG, "trajectory: NULL pointer");
+    if (n_cycles < 1 || n_pairs < 0) return set_err(WFO_ERR_ARG, "trajectory: bad sizes");
+    if (ao_side != WFO_AO_BRA && ao_side != WFO_AO_KET)
+        return set_err(WFO_ERR_ARG, "trajectory: ao_side must be WFO_AO_BRA or WFO_AO_KET");
+    WFO_TRY(check_ci_args("trajectory", ao_side, n_mo, n_occ, n_states, n_states, semantics, rank, world));
+    for (int p = 0; p < n_pairs; p++)
+        if (pairs[2 * p] < 0 || pairs[2 * p] >= n_cycles || pairs[2 * p + 1] < 0 || pairs[2 * p + 1] >= n_cycles)
+            return set_err(WFO_ERR_ARG, "trajectory: pair %lld names a cycle outside 0..n_cycles-1", p);
+    WFO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream, s2 = ctx->stream2;
+    const int n = n_occ, v = n_mo - n_occ, count = n * v;
+    const size_t nsq = (size_t)n_mo * n_mo, ncc = (size_t)n_states * count, nout = (size_t)n_states * n_states;
+    if (info) { info[0] = info[1] = 0; info[2] = 0; info[3] = -1; }
+    if (count == 0 || n_pairs == 0) {
+        memset(out, 0, (size_t)n_pairs * nout * sizeof(double));
+        return WFO_OK;
+    }
+    CiWork w;
+    Sizer sz;
+    sz.take<double>(nsq * n_cycles); sz.take<double>(ncc * n_cycles); sz.take<double>(nsq * n_cycles);
+    sz.take<double>(nout * n_pairs);
+    carve_ciwork(sz, w, nsq, count, n_states, n_states);
+    WFO_TRY(ensure_resident(ctx, sz.off));
+    Arena ar{ctx->resident, ctx->resident_bytes, 0};
+    double *d_mos = ar.take<double>(nsq * n_cycles), *d_ci = ar.take<double>(ncc * n_cycles);
+    double *d_inv = ar.take<double>(nsq * n_cycles), *d_outs = ar.take<double>(nout * n_pairs);
+    carve_ciwork(ar, w, nsq, count, n_states, n_states);
+    WFO_CUDA(cudaMemcpyAsync(d_mos, mos, nsq * n_cycles * 8, cudaMemcpyHostToDevice, st));
+    WFO_CUDA(cudaMemcpyAsync(d_ci, ci, ncc * n_cycles * 8, cudaMemcpyHostToDevice, st));
+    std::vector<char> have_inv(n_cycles, 0);
+    for (int p = 0; p < n_pairs; p++) {
+        const int cb = pairs[2 * p], ck = pairs[2 * p + 1];
+        const int ci_c = ao_side == WFO_AO_BRA ? cb : ck;   // the cycle whose MO matrix defines S_AO
+        if (!have_inv[ci_c]) {   // once per cycle; ordered after the uploads and after earlier users of the scratch
+            WFO_CUDA(cudaEventRecord(ctx->ev_fork, st));
+            WFO_CUDA(cudaStreamWaitEvent(s2, ctx->ev_fork, 0));
+            WFO_TRY(wfo_inverse_dev(ctx, d_mos + nsq * ci_c, n_mo, d_inv + nsq * ci_c, w.work, s2));
+            have_inv[ci_c] = 1;
+        }
+        bool zero = false;
+        int32_t pinfo[4];
+        WFO_TRY(overlaps_ci_core(ctx, w, d_mos + nsq * cb, d_mos + nsq * ck, d_inv + nsq * ci_c, WFO_AO_GIVEN, n_mo, n_occ,
+                                 d_ci + ncc * cb, n_states, d_ci + ncc * ck, n_states, ci_thresh, semantics, tier, rank,
+                                 world, true, pinfo, &zero, st));
+        if (info) { info[0] = pinfo[0] > info[0] ? pinfo[0] : info[0]; info[1] = pinfo[1] > info[1] ? pinfo[1] : info[1]; info[3] = pinfo[3]; }
+        if (zero) WFO_CUDA(cudaMemsetAsync(d_outs + nout * p, 0, nout * 8, st));
+        else WFO_CUDA(cudaMemcpyAsync(d_outs + nout * p, w.out, nout * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    WFO_CUDA(cudaMemcpyAsync(out, d_outs, nout * n_pairs * 8, cudaMemcpyDeviceToHost, st));
     WFO_CUDA(cudaStreamSynchronize(st));
     return WFO_OK;
 }

@@ -87,6 +87,8 @@ struct wfo_ctx {
     size_t scratch_bytes;
     double *gscratch;      // per-CTA LU working matrices (global-scratch variant of the T0 kernel)
     size_t gscratch_bytes;
+    char *resident;        // inputs + phase-1 workspace of the raw-CI / trajectory entry points
+    size_t resident_bytes;
     long long launches;
     int last_tier;
     int timing;

@@ -73,3 +73,26 @@ def sharded_state_overlaps(partial_fn, K_bra: int, n_bra: int, n_ket: int, devic
     part = partial_fn(lo, hi)
     assert tuple(part.shape) == (n_bra, n_ket)
     return sum_over_ranks(part, device)
+
+
+def deal_pairs(n_pairs: int, ws: int, rank: int) -> np.ndarray:
+    """Indices of the trajectory pairs rank ``rank`` of ``ws`` computes (round-robin)."""
+    return np.arange(rank, n_pairs, ws)
+
+
+def sharded_trajectory(compute_fn, n_pairs: int, n_states: int, device=None):
+    """Trajectory pairs over the ranks.  ``compute_fn(pair_indices, rank, world)`` returns the
+    ``(len(pair_indices), n_states, n_states)`` matrices of those pairs, computed on ``world`` = 1
+    excitation shards when the pairs are dealt out (at least one pair per rank), else every rank
+    takes ALL pairs with its shard ``rank`` of ``world`` of the bra excitations.  Either way the
+    zero-padded / partial results are summed with the path's one all-reduce."""
+    rank, ws = world()
+    if ws > 1 and n_pairs >= ws:
+        mine = deal_pairs(n_pairs, ws, rank)
+        out = np.zeros((n_pairs, n_states, n_states))
+        if mine.size:
+            out[mine] = compute_fn(mine, 0, 1)
+    else:
+        out = np.asarray(compute_fn(np.arange(n_pairs), rank, ws))
+    assert tuple(out.shape) == (n_pairs, n_states, n_states)
+    return sum_over_ranks(out, device)

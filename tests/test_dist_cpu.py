@@ -68,3 +68,59 @@ def test_two_rank_gloo_allreduce():
     from oracle import pywfo_oracle as orc
     want, _ = orc.ref_overlaps_cache(g["bra_mos"], g["ket_mos"], g["bra_ci"], g["ket_ci"], int(g["occ"]), 0.0)
     np.testing.assert_allclose(res[0][2], want, rtol=1e-10, atol=1e-13)
+
+
+# ---------------------------------------------------------------- trajectory pairs over ranks
+def _traj_worker(rank, world, port, q, n_use):
+    import torch.distributed as dist
+    from oracle import pywfo_oracle as orc
+    from pywfo_b200 import dist as wdist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = load_golden("cytosin_traj")
+        occ, thr = int(g["occ"]), float(g["ci_thresh"])
+        pairs = g["pairs"][:n_use]
+        mo, ci = g["mo_coeffs"], g["ci_coeffs"]
+        calls = []
+
+        def compute(idx, r, w):
+            calls.append((list(map(int, idx)), r, w))
+            outs = []
+            for i, j in pairs[idx]:
+                full, _ = orc.ref_overlaps_cache(mo[i], mo[j], ci[i], ci[j], occ, thr)
+                outs.append(full if w == 1 else full / w)   # stand-in for an excitation shard: partials add up
+            return np.stack(outs)
+
+        out = wdist.sharded_trajectory(compute, len(pairs), ci.shape[1])
+        q.put((rank, calls, out))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("n_use", [3, 1])
+def test_two_rank_trajectory(n_use):
+    """3 pairs on 2 ranks: dealt round-robin (0,2 | 1); 1 pair on 2 ranks: both ranks take it with
+    an excitation shard each.  Either way the all-reduce returns the per-pair reference values."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_traj_worker, args=(r, 2, port, q, n_use)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=500) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    res.sort(key=lambda x: x[0])
+    if n_use == 3:
+        assert res[0][1] == [([0, 2], 0, 1)] and res[1][1] == [([1], 0, 1)]
+    else:
+        assert res[0][1] == [([0], 0, 2)] and res[1][1] == [([0], 1, 2)]
+    np.testing.assert_array_equal(res[0][2], res[1][2])
+    g = load_golden("cytosin_traj")
+    np.testing.assert_allclose(res[0][2], g["ref_overlaps_cache"][:n_use], rtol=1e-10, atol=1e-13)

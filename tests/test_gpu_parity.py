@@ -452,3 +452,37 @@ def test_singular_mo_matrix_raises_like_numpy(ctx):
     ci = np.full((1, 2, 4), 0.3)
     with pytest.raises(np.linalg.LinAlgError):
         main.overlaps_cache(mos, mos, ci, ci, 2)
+
+
+# ---------------------------------------------------------------- trajectory driver
+@pytest.mark.parametrize("tier", ["auto", "lu"])
+def test_trajectory_matches_pairwise_reference(ctx, tier):
+    """One library call for the whole cytosine trajectory == the reference called pair by pair."""
+    from pywfo_b200 import main, trajectory
+    g = load_golden("cytosin_traj")
+    occ, thr = int(g["occ"]), float(g["ci_thresh"])
+    mo, ci, pairs = g["mo_coeffs"], g["ci_coeffs"], g["pairs"]
+    got = trajectory.trajectory_overlaps(mo, ci, occ, ci_thresh=thr, pairs=pairs, tier=tier)
+    assert_parity(got, g["ref_overlaps_cache"])
+    if tier == "auto":
+        got_m = trajectory.trajectory_overlaps(mo, ci, occ, ci_thresh=thr, pairs=pairs, semantics="minus")
+        assert_parity(got_m, g["ref_overlaps"])
+        got_b = trajectory.trajectory_overlaps(mo, ci, occ, ci_thresh=thr, pairs=pairs[:2], ao_ovlps="bra")
+        assert_parity(got_b, g["ref_overlaps_cache_bra"])
+        # default pairs = consecutive cycles; same numbers as single calls through the public entry point
+        cons = trajectory.trajectory_overlaps(mo, ci, occ, ci_thresh=thr)
+        assert cons.shape == (3, 2, 2)
+        for p in range(3):
+            one = main.overlaps_cache(mo[p], mo[p + 1], ci[p], ci[p + 1], occ, ci_thresh=thr)
+            np.testing.assert_allclose(cons[p], one, rtol=1e-12, atol=1e-14)
+            assert_parity(cons[p], g["ref_overlaps_cache"][p])
+
+
+def test_trajectory_excitation_shards_add_up(ctx):
+    g = load_golden("cytosin_traj")
+    occ, thr = int(g["occ"]), float(g["ci_thresh"])
+    full, info = ctx.trajectory_ci_host(g["mo_coeffs"], g["ci_coeffs"], occ, g["pairs"][:2], thr)
+    parts = sum(ctx.trajectory_ci_host(g["mo_coeffs"], g["ci_coeffs"], occ, g["pairs"][:2], thr, rank=r, world=3)[0]
+                for r in range(3))
+    np.testing.assert_allclose(parts, full, rtol=1e-12, atol=1e-14 * np.abs(full).max())
+    assert info[0] > 0 and info[1] > 0
