@@ -256,18 +256,44 @@ static int det_table(wfo_ctx *ctx, const double *S, int ld_s, int n, const int32
     return WFO_OK;
 }
 
+// Variants of the rank-update kernel: (row stride in tiles, DMMA tiles, DFMA columns) for n_ket = 1..55.
+// DFMA columns (REM > 0) are compiled out of the dispatch: measured on B200, a DFMA issued between
+// DMMAs costs ~11 pipe cycles per SMSP instead of 2, so 2 leftover columns as DFMA are slower
+// (+0.94 ms at C4) than padding them to a seventh DMMA tile (+0.69 ms).
+#define WFO_T1_VARIANTS(X)                                            \
+    X(1, 1, 0)                                                        \
+    X(3, 1, 0) X(3, 2, 0) X(3, 3, 0)                                  \
+    X(5, 3, 0) X(5, 4, 0) X(5, 5, 0)                                  \
+    X(7, 5, 0) X(7, 6, 0) X(7, 7, 0)
+
+static int pick_ldg(int n_ket) {
+    int nt = cdiv(n_ket + 1, 8);
+    if ((nt & 1) == 0) nt++;   // odd tile count: conflict-free B-fragment loads (stride = 8 mod 16)
+    return nt * 8;
+}
+
+// how the n_ket state columns are split between the tensor cores and DFMA (see pair_update.cuh)
+static void t1_split(int n_ket, int *nt, int *nd, int *rem) {
+    *nt = pick_ldg(n_ket) / 8;
+    *nd = (n_ket + 7) / 8;   // the D(k,0) column behind the states is filled in by the epilogue, not here
+    *rem = 0;
+}
+
 // the rank-update kernel runs one persistent CTA per SM; opt in to its dynamic shared memory once
-static int t1_prepare(int ldg) {
-    static bool done[8] = {false, false, false, false, false, false, false, false};
-    const int nt = ldg / 8;
-    if (nt < 1 || nt > 7 || !(nt & 1)) return set_err(WFO_ERR_ARG, "state_overlaps: unsupported ldg %lld", ldg);
-    if (!done[nt]) {
-        switch (nt) {
-#define T1_ATTR(NT_) case NT_: WFO_CUDA(cudaFuncSetAttribute(t1_fused_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t1_smem_bytes<NT_>())); break;
-            T1_ATTR(1) T1_ATTR(3) T1_ATTR(5) T1_ATTR(7)
+static int t1_prepare(int n_ket) {
+    static bool done[1000];
+    int nt, nd, rem;
+    t1_split(n_ket, &nt, &nd, &rem);
+    const int key = nt * 100 + nd * 10 + rem;
+    if (nt < 1 || nt > 7) return set_err(WFO_ERR_ARG, "state_overlaps: unsupported number of ket states %lld per pass", n_ket);
+    if (!done[key]) {
+        switch (key) {
+#define T1_ATTR(NT_, ND_, REM_) case NT_ * 100 + ND_ * 10 + REM_: WFO_CUDA(cudaFuncSetAttribute(t1_fused_kernel<NT_, ND_, REM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t1_smem_bytes<NT_>())); break;
+            WFO_T1_VARIANTS(T1_ATTR)
 #undef T1_ATTR
+            default: return set_err(WFO_ERR_ARG, "state_overlaps: no rank-update kernel for %lld ket states", n_ket);
         }
-        done[nt] = true;
+        done[key] = true;
     }
     return WFO_OK;
 }
@@ -313,11 +339,6 @@ static void carve(AR &ar, Plan &p, int n, int v, int ksh, int kk, int n_bra, int
     }
 }
 
-static int pick_ldg(int n_ket) {
-    int nt = cdiv(n_ket + 1, 8);
-    if ((nt & 1) == 0) nt++;   // odd tile count: conflict-free B-fragment loads (stride = 8 mod 16)
-    return nt * 8;
-}
 
 
 struct Part {   // how the pair space of one call is cut up
@@ -365,7 +386,7 @@ static int make_part(wfo_ctx *ctx, int ksh, int kk, int n_ket, bool may_t0, bool
     memset(&q.t1, 0, sizeof(q.t1));
     if (want_t1) {
         // T1: iterations (bra tile, ket tile) in equal contiguous ranges over the resident CTAs
-        WFO_TRY(t1_prepare(q.ldg));
+        WFO_TRY(t1_prepare(n_ket));
         const int slots = ctx->sm_count;
         const int ktiles = cdiv(ksh + 1, T1_KTILE), n_ltiles = cdiv(kk, T1_LT);
         const long long I = (long long)ktiles * n_ltiles;
@@ -850,11 +871,15 @@ static int state_overlaps_block(wfo_ctx *ctx, size_t arena_off, const double *s_
             WFO_PHASE(ctx, st, "prep");
             if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev0, st));
             pmap = q.t1;
-            switch (ldg / 8) {
-#define T1_CASE(NT_) case NT_: t1_fused_kernel<NT_><<<pmap.G, T1_WARPS * 32, t1_smem_bytes<NT_>(), st>>>(p.Ai, p.Wb, p.bmeta, p.bscale, ksh + 1, p.kmeta, p.ckt, kk, pmap, p.gpart); break;
-                T1_CASE(1) T1_CASE(3) T1_CASE(5) T1_CASE(7)
+            {
+                int nt, nd, rem;
+                t1_split(n_ket, &nt, &nd, &rem);
+                switch (nt * 100 + nd * 10 + rem) {
+#define T1_CASE(NT_, ND_, REM_) case NT_ * 100 + ND_ * 10 + REM_: t1_fused_kernel<NT_, ND_, REM_><<<pmap.G, T1_WARPS * 32, t1_smem_bytes<NT_>(), st>>>(p.Ai, p.Wb, p.bmeta, p.bscale, ksh + 1, p.kmeta, p.ckt, kk, pmap, p.gpart); break;
+                    WFO_T1_VARIANTS(T1_CASE)
 #undef T1_CASE
-                default: return set_err(WFO_ERR_ARG, "state_overlaps: unsupported ldg %lld", ldg);
+                    default: return set_err(WFO_ERR_ARG, "state_overlaps: no rank-update kernel for %lld ket states", n_ket);
+                }
             }
             WFO_LAUNCH_CHECK(ctx);
             if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev1, st));

@@ -36,6 +36,9 @@
 
 namespace wfo {
 
+#ifndef WFO_T1_EXP
+#define WFO_T1_EXP 0
+#endif
 #ifndef WFO_T1_WARPS
 #define WFO_T1_WARPS 12
 #endif
@@ -142,12 +145,17 @@ __device__ long long g_t1_clk[2048][4];   // per CTA: elapsed clocks, SM id, sta
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #endif
 
-// NT = ldg / 8 column tiles of G.  One persistent CTA per SM; ckts and ket are padded with zero
-// rows to a multiple of T1_LT excitations, so every tile is a full tile.
+// NT = ldg / 8: row stride of CkTs / G in 8-column tiles (odd: conflict-free fragment loads).
+// Of those columns the first 8*ND are contracted on the tensor cores (DMMA); ND = ceil(n_ket/8)
+// can be smaller than NT (the D(k,0) column and the odd-stride padding are never computed here).
+// REM further columns can be contracted with plain DFMA; measured on B200 that loses (a DFMA
+// between DMMAs costs ~11 pipe cycles per SMSP, not 2), so the dispatch only uses REM = 0.
+// One persistent CTA per SM; ckts and ket are padded with zero rows to a multiple of T1_LT
+// excitations, so every tile is a full tile.
 template <int NT>
 constexpr size_t t1_smem_bytes() { return (size_t)T1_STAGES * (T1_LT * NT * 8 * sizeof(double) + T1_LT * sizeof(KetMeta)); }
 
-template <int NT>
+template <int NT, int ND, int REM>
 __global__ void __launch_bounds__(T1_WARPS * 32, 1)
 t1_fused_kernel(const double *__restrict__ Ai, const double *__restrict__ W,
                 const BraMeta *__restrict__ bra, const double *__restrict__ bra_scale, int ksh,
@@ -225,11 +233,15 @@ t1_fused_kernel(const double *__restrict__ Ai, const double *__restrict__ W,
                 bf[mi] = 0; bw[mi] = 0; bx[mi] = 0.0;   // harmless duplicates, never stored
             }
         }
-        double acc[T1_MT][NT][2];
+        double acc[T1_MT][ND > 0 ? ND : 1][2];
+        double acc2[T1_MT][REM > 0 ? REM : 1];   // DFMA columns: this thread's share (its l = 4 ks + t)
 #pragma unroll
-        for (int mi = 0; mi < T1_MT; mi++)
+        for (int mi = 0; mi < T1_MT; mi++) {
 #pragma unroll
-            for (int ni = 0; ni < NT; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+            for (int ni = 0; ni < ND; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+#pragma unroll
+            for (int jj = 0; jj < REM; jj++) acc2[mi][jj] = 0.0;
+        }
 
         for (int j = 0; j < cnt; j++, q++) {
             const int s = q % T1_STAGES;
@@ -254,7 +266,13 @@ t1_fused_kernel(const double *__restrict__ Ai, const double *__restrict__ W,
 #pragma unroll
             for (int ks = 0; ks < T1_LT / 4; ks++) {
 #pragma unroll
+#if WFO_T1_EXP == 1
+                for (int mi = 0; mi < T1_MT; mi++) a_cur[mi] = ai_n[mi] * w_n[mi];
+#elif WFO_T1_EXP == 2
+                for (int mi = 0; mi < T1_MT; mi++) a_cur[mi] = __hiloint2double(__double2hiint(ai_n[mi]) ^ __double2loint(w_n[mi]), __double2loint(ai_n[mi]) + (int)y_n);
+#else
                 for (int mi = 0; mi < T1_MT; mi++) a_cur[mi] = fma(bx[mi], y_n, ai_n[mi] * w_n[mi]);
+#endif
                 if (ks + 1 < T1_LT / 4) {
                     const KetMeta m = ms[4 * (ks + 1) + t];
                     y_n = m.y;
@@ -264,13 +282,29 @@ t1_fused_kernel(const double *__restrict__ Ai, const double *__restrict__ W,
                         w_n[mi] = __ldg(W + bw[mi] + m.tp);
                     }
                 }
-                double b[NT];
+                // DFMA columns first, as one group (volatile: ptxas keeps them together in front of the
+                // DMMAs of this k-step instead of sprinkling them between tensor instructions)
+                if (REM > 0) {
+                    double c2[REM > 0 ? REM : 1];
 #pragma unroll
-                for (int ni = 0; ni < NT; ni++) b[ni] = bs[(4 * ks + t) * LDG + 8 * ni + g];
+                    for (int jj = 0; jj < REM; jj += 2) {
+                        const double2 v = *reinterpret_cast<const double2 *>(bs + (4 * ks + t) * LDG + 8 * ND + jj);
+                        c2[jj] = v.x;
+                        c2[jj + 1] = v.y;
+                    }
+#pragma unroll
+                    for (int mi = 0; mi < T1_MT; mi++)
+#pragma unroll
+                        for (int jj = 0; jj < REM; jj++)
+                            asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(acc2[mi][jj]) : "d"(a_cur[mi]), "d"(c2[jj]));
+                }
+                double b[ND > 0 ? ND : 1];
+#pragma unroll
+                for (int ni = 0; ni < ND; ni++) b[ni] = bs[(4 * ks + t) * LDG + 8 * ni + g];
 #pragma unroll
                 for (int mi = 0; mi < T1_MT; mi++)
 #pragma unroll
-                    for (int ni = 0; ni < NT; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a_cur[mi], b[ni]);
+                    for (int ni = 0; ni < ND; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a_cur[mi], b[ni]);
                 if (ks == T1_LT / 8 - 1 && warp == 0) produce_upto(q + T1_STAGES, false);
             }
             __syncwarp();
@@ -281,13 +315,38 @@ t1_fused_kernel(const double *__restrict__ Ai, const double *__restrict__ W,
 #pragma unroll
         for (int mi = 0; mi < T1_MT; mi++) {
             const int k = k0 + 8 * mi + g;
+            // DFMA columns: add the four lanes (t = 0..3) that share the row, fixed order
+            double r2[REM > 0 ? REM : 1];
+#pragma unroll
+            for (int jj = 0; jj < REM; jj++) {
+                double v = acc2[mi][jj];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                r2[jj] = v;
+            }
             if (k >= ksh) continue;
             const double sc = bra_scale[k];
-            double *dst = gpart + ((size_t)split * ksh + k) * LDG + 2 * t;
+            double *row = gpart + ((size_t)split * ksh + k) * LDG;
 #pragma unroll
-            for (int ni = 0; ni < NT; ni++) {
+            for (int ni = 0; ni < ND; ni++) {
                 const double2 v = make_double2(sc * acc[mi][ni][0], sc * acc[mi][ni][1]);
-                *reinterpret_cast<double2 *>(dst + 8 * ni) = v;
+                *reinterpret_cast<double2 *>(row + 8 * ni + 2 * t) = v;
+            }
+            // the rest of the row: the DFMA columns, then zeros up to the row stride
+            constexpr int REST = LDG - 8 * ND;   // <= 16
+#pragma unroll
+            for (int c = 0; c < REST; c += 8) {
+                const int j = c + 2 * t;
+                if (j + 1 < REST || j < REST) {
+                    double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+                    for (int jj = 0; jj < REM; jj++) {
+                        v0 = (jj == j) ? sc * r2[jj] : v0;
+                        v1 = (jj == j + 1) ? sc * r2[jj] : v1;
+                    }
+                    if (j < REST) row[8 * ND + j] = v0;
+                    if (j + 1 < REST) row[8 * ND + j + 1] = v1;
+                }
             }
         }
     }
