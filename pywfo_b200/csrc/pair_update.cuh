@@ -36,9 +36,6 @@
 
 namespace wfo {
 
-#ifndef WFO_T1_EXP
-#define WFO_T1_EXP 0
-#endif
 #ifndef WFO_T1_WARPS
 #define WFO_T1_WARPS 12
 #endif
@@ -266,13 +263,7 @@ t1_fused_kernel(const double *__restrict__ Ai, const double *__restrict__ W,
 #pragma unroll
             for (int ks = 0; ks < T1_LT / 4; ks++) {
 #pragma unroll
-#if WFO_T1_EXP == 1
-                for (int mi = 0; mi < T1_MT; mi++) a_cur[mi] = ai_n[mi] * w_n[mi];
-#elif WFO_T1_EXP == 2
-                for (int mi = 0; mi < T1_MT; mi++) a_cur[mi] = __hiloint2double(__double2hiint(ai_n[mi]) ^ __double2loint(w_n[mi]), __double2loint(ai_n[mi]) + (int)y_n);
-#else
                 for (int mi = 0; mi < T1_MT; mi++) a_cur[mi] = fma(bx[mi], y_n, ai_n[mi] * w_n[mi]);
-#endif
                 if (ks + 1 < T1_LT / 4) {
                     const KetMeta m = ms[4 * (ks + 1) + t];
                     y_n = m.y;
