@@ -16,8 +16,9 @@
 // (CkTs = s_l * Ck^T, zero padded to ldg columns).  Pair values never reach HBM
 // (pywfo/main.py:613-626 is the loop this replaces).
 //
-// ONE persistent CTA per SM: 12 warps x 24 bra excitations (3 m-tiles of 8 per warp, 168
-// registers) = 288 bra excitations per bra tile.  Work decomposition is "stream-K": the iteration
+// ONE persistent CTA per SM: 8 warps x 32 bra excitations (4 m-tiles of 8 per warp) = 256 bra
+// excitations per bra tile (12 warps x 24 rows run at the same speed at C4 but waste more of a
+// small shard's ragged last tile).  Work decomposition is "stream-K": the iteration
 // space (bra tile, ket tile of 32) is cut into gridDim.x equal contiguous ranges, one per CTA, so
 // every SM executes the same number of inner iterations (+-1) whatever the shard size -- no wave
 // quantisation, no atomic work counter, a static and therefore run-to-run deterministic summation
@@ -27,7 +28,7 @@
 // touch the tile, see t1_part_range); the epilogue kernel adds the few parts of each tile.  The ket
 // coefficient tiles (32 excitations x ldg, one contiguous block of CkTs) are staged in shared
 // memory by TMA bulk copies (cp.async.bulk, SASS UBLKCP) through a 4-stage ring with full/empty
-// mbarriers -- no block barrier in the main loop; the 12 warps share every tile and may drift by
+// mbarriers -- no block barrier in the main loop; the 8 warps share every tile and may drift by
 // up to three tiles.  Ai and W are gathered
 // through L1 (the host orders the ket excitations so that a CTA's working set
 // of W is a few KB at a time, see pywfo_b200/excitations.py).
@@ -37,17 +38,17 @@
 namespace wfo {
 
 #ifndef WFO_T1_WARPS
-#define WFO_T1_WARPS 12
+#define WFO_T1_WARPS 8
 #endif
 #ifndef WFO_T1_STAGES
 #define WFO_T1_STAGES 4
 #endif
 #ifndef WFO_T1_MT
-#define WFO_T1_MT 3
+#define WFO_T1_MT 4
 #endif
 constexpr int T1_WARPS = WFO_T1_WARPS;
 constexpr int T1_MT = WFO_T1_MT;                 // m-tiles (8 bra excitations) per warp
-constexpr int T1_KTILE = T1_WARPS * T1_MT * 8;   // 288 bra excitations per CTA
+constexpr int T1_KTILE = T1_WARPS * T1_MT * 8;   // 256 bra excitations per CTA
 #ifndef WFO_T1_LT
 #define WFO_T1_LT 32
 #endif
