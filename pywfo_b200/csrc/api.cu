@@ -76,42 +76,39 @@ static int gemm(wfo_ctx *ctx, bool ta, bool tb, int m, int n, int k, double alph
     if (m <= 0 || n <= 0) return WFO_OK;
     if (kslab <= 0 || batch > 0) kslab = k > 0 ? k : 1;
     int nz = batch > 0 ? batch : (k > 0 ? cdiv(k, kslab) : 1);
-    // 64-row CTA tiles unless that leaves SMs idle
-    const bool small = (long long)cdiv(n, GN) * cdiv(m, 64) * nz < ctx->sm_count;
-    const int gm = small ? 32 : 64;
-    dim3 grid(cdiv(n, GN), cdiv(m, gm), nz), block(128);
+    // 64x64 CTA tiles unless that leaves SMs idle: then 32x64, then 32x32
+    int gm = 64, gn = 64;
+    if ((long long)cdiv(n, 64) * cdiv(m, 64) * nz < ctx->sm_count) gm = 32;
+    if (gm == 32 && (long long)cdiv(n, 64) * cdiv(m, 32) * nz < ctx->sm_count) gn = 32;
+    dim3 grid(cdiv(n, gn), cdiv(m, gm), nz), block(128);
     // 16-byte async copies need even leading dimensions / slab starts / batch strides and aligned bases
     const bool vec = !ta && !((lda | ldb) & 1) && !(((uintptr_t)A | (uintptr_t)B) & 15) &&
                      !((batch_a | batch_b) & 1) && (nz == 1 || batch > 0 || !(kslab & 1));
-#define GEMM_LAUNCH2(TA_, TB_, GM_, VEC_)                                                                         \
+#define GEMM_LAUNCH2(TA_, TB_, GM_, GN_, VEC_)                                                                    \
     do {                                                                                                          \
         static bool attr_done_ = false;                                                                           \
         if (!attr_done_) {                                                                                        \
-            WFO_CUDA(cudaFuncSetAttribute(gemm_f64_kernel<TA_, TB_, GM_, VEC_>,                                   \
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<GM_>())); \
+            WFO_CUDA(cudaFuncSetAttribute(gemm_f64_kernel<TA_, TB_, GM_, GN_, VEC_>,                              \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,                            \
+                                          (int)gemm_smem_bytes<GM_, GN_>()));                                     \
             attr_done_ = true;                                                                                    \
         }                                                                                                         \
-        gemm_f64_kernel<TA_, TB_, GM_, VEC_><<<grid, block, gemm_smem_bytes<GM_>(), st>>>(                        \
+        gemm_f64_kernel<TA_, TB_, GM_, GN_, VEC_><<<grid, block, gemm_smem_bytes<GM_, GN_>(), st>>>(              \
             m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kslab, slab_stride, batch_a, batch_b);                  \
     } while (0)
-#define GEMM_LAUNCH(TA_, TB_)                                             \
+#define GEMM_LAUNCH(TA_, TB_, VEC_)                                       \
     do {                                                                  \
-        if (small) { GEMM_LAUNCH2(TA_, TB_, 32, false); }                 \
-        else { GEMM_LAUNCH2(TA_, TB_, 64, false); }                       \
+        if (gm == 64) { GEMM_LAUNCH2(TA_, TB_, 64, 64, VEC_); }           \
+        else if (gn == 64) { GEMM_LAUNCH2(TA_, TB_, 32, 64, VEC_); }      \
+        else { GEMM_LAUNCH2(TA_, TB_, 32, 32, VEC_); }                    \
     } while (0)
-#define GEMM_LAUNCH_V(TB_)                                                \
-    do {                                                                  \
-        if (small) { GEMM_LAUNCH2(false, TB_, 32, true); }                \
-        else { GEMM_LAUNCH2(false, TB_, 64, true); }                      \
-    } while (0)
-    if (vec && !tb) GEMM_LAUNCH_V(false);
-    else if (vec && tb) GEMM_LAUNCH_V(true);
-    else if (!ta && !tb) GEMM_LAUNCH(false, false);
-    else if (!ta && tb) GEMM_LAUNCH(false, true);
-    else if (ta && !tb) GEMM_LAUNCH(true, false);
-    else GEMM_LAUNCH(true, true);
+    if (vec && !tb) GEMM_LAUNCH(false, false, true);
+    else if (vec && tb) GEMM_LAUNCH(false, true, true);
+    else if (!ta && !tb) GEMM_LAUNCH(false, false, false);
+    else if (!ta && tb) GEMM_LAUNCH(false, true, false);
+    else if (ta && !tb) GEMM_LAUNCH(true, false, false);
+    else GEMM_LAUNCH(true, true, false);
 #undef GEMM_LAUNCH
-#undef GEMM_LAUNCH_V
 #undef GEMM_LAUNCH2
     WFO_LAUNCH_CHECK(ctx);
     return WFO_OK;

@@ -4,8 +4,8 @@
 // for the base-block products X = C Ai, Y = Ai B, W = Dv - C Y of the rank-update
 // tier, and (with split-K slabs) for the final CI contraction S = Cb G.
 //
-// CTA tile GM x 64 (GM = 64, or 32 when that is needed to fill the 148 SMs), 4 warps in a
-// 2x2 grid, warp tile (GM/2) x 32 = (GM/16) x 4 DMMA.8x8x4 tiles, K tile 16.  Operand tiles
+// CTA tile GM x GN (64x64, or 32x64 / 32x32 when that is needed to fill the 148 SMs), 4 warps
+// in a 2x2 grid, warp tile (GM/2) x (GN/2) = (GM/16) x (GN/16) DMMA.8x8x4 tiles, K tile 16.  Operand tiles
 // are brought in with cp.async (16-byte copies when the operands allow it, else 8-byte elements;
 // zero fill at the edges) through a 3-stage shared-memory ring, so the L2 latency of tile t+2 hides behind the DMMAs of tile t with one
 // block barrier per K tile.  Padded shared tiles make both fragment loads conflict-free
@@ -17,14 +17,14 @@
 
 namespace wfo {
 
-constexpr int GN = 64, GK = 16;   // GM (64 or 32 rows per CTA) is a template parameter
+constexpr int GK = 16;            // GM (64 / 32 rows) and GN (64 / 32 columns per CTA) are template parameters
 constexpr int GLDA = GK + 4;      // 20: row stride of k-contiguous tiles (A, and B when it is stored transposed)
-constexpr int GLDB = GN + 8;      // 72: row stride of the n-contiguous B tile
 constexpr int GSTAGES = 3;
-constexpr int GBS = GN * GLDA;    // doubles reserved for the B tile of a stage (>= GK * GLDB)
+template <int GN> constexpr int gemm_ldb() { return GN + 8; }        // 72 / 40: row stride of the n-contiguous B tile
+template <int GN> constexpr int gemm_bs() { return GN * GLDA; }      // doubles reserved for the B tile (>= GK * ldb)
 
-template <int GM>
-constexpr size_t gemm_smem_bytes() { return (size_t)GSTAGES * (GM * GLDA + GBS) * sizeof(double); }
+template <int GM, int GN>
+constexpr size_t gemm_smem_bytes() { return (size_t)GSTAGES * (GM * GLDA + gemm_bs<GN>()) * sizeof(double); }
 
 // async copies global -> shared; a source size below the copy size zero-fills the rest
 __device__ __forceinline__ void cp_async8(double *dst, const double *src, bool ok) {
@@ -38,19 +38,21 @@ __device__ __forceinline__ void cp_async16(double *dst, const double *src, int b
 }
 
 // VEC: 16-byte copies (needs !TA, even leading dimensions and K-slab starts, 16-byte aligned bases)
-template <bool TA, bool TB, int GM, bool VEC>
+template <bool TA, bool TB, int GM, int GN, bool VEC>
 __global__ void __launch_bounds__(128)
 gemm_f64_kernel(int m, int n, int k, double alpha, const double *__restrict__ A, int lda,
                 const double *__restrict__ B, int ldb, double beta, double *__restrict__ C, int ldc,
                 int kslab, long long slab_stride, long long batch_a, long long batch_b) {
     extern __shared__ __align__(16) double gsm[];
-    constexpr int STAGE = GM * GLDA + GBS;   // doubles per stage
+    constexpr int GLDB = GN + 8;
+    constexpr int STAGE = GM * GLDA + GN * GLDA;   // doubles per stage
+    constexpr int NTW = GN / 16;                       // 8-column tiles per warp
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     constexpr int MT = GM / 16;               // 8-row tiles per warp (warps are 2 x 2)
-    const int wm = (warp >> 1) * (GM / 2), wn = (warp & 1) * 32;
+    const int wm = (warp >> 1) * (GM / 2), wn = (warp & 1) * (GN / 2);
     const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
     // blockIdx.z is either a K slab (batch strides 0) or a batch index (kslab >= k, batch strides set)
     const bool batched = (batch_a | batch_b) != 0;
@@ -60,11 +62,11 @@ gemm_f64_kernel(int m, int n, int k, double alpha, const double *__restrict__ A,
     B += (long long)blockIdx.z * batch_b;
     C += (long long)blockIdx.z * slab_stride;
 
-    double acc[MT][4][2];
+    double acc[MT][NTW][2];
 #pragma unroll
     for (int i = 0; i < MT; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < NTW; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     // shared layouts: As[mm][kk] (stride GLDA); Bs[kb][nn] (stride GLDB) for B as stored k x n,
     // Bs[nn][kb] (stride GLDA) for B stored n x k (TB)
@@ -81,7 +83,7 @@ gemm_f64_kernel(int m, int n, int k, double alpha, const double *__restrict__ A,
                 cp_async16(As + mm * GLDA + kc, bytes ? A + (long long)gm * lda + gk : A, bytes);
             }
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
+            for (int e = 0; e < GN / 16; e++) {
                 const int idx = tid + e * 128;
                 if (TB) {
                     const int nn = idx >> 3, kc = (idx & 7) * 2;
@@ -89,7 +91,7 @@ gemm_f64_kernel(int m, int n, int k, double alpha, const double *__restrict__ A,
                     const int bytes = (gn < n) ? max(0, min(16, (kend - gk) * 8)) : 0;
                     cp_async16(Bs + nn * GLDA + kc, bytes ? B + (long long)gn * ldb + gk : B, bytes);
                 } else {
-                    const int kb = idx >> 5, nc = (idx & 31) * 2;
+                    const int kb = idx / (GN / 2), nc = (idx % (GN / 2)) * 2;
                     const int gkb = k0 + kb, gn = n0 + nc;
                     const int bytes = (gkb < kend) ? max(0, min(16, (n - gn) * 8)) : 0;
                     cp_async16(Bs + kb * GLDB + nc, bytes ? B + (long long)gkb * ldb + gn : B, bytes);
@@ -107,7 +109,7 @@ gemm_f64_kernel(int m, int n, int k, double alpha, const double *__restrict__ A,
                 cp_async8(As + mm * GLDA + kk, src, ok);
             }
 #pragma unroll
-            for (int e = 0; e < 8; e++) {
+            for (int e = 0; e < GN / 8; e++) {
                 const int idx = tid + e * 128;
                 int nn, kb;
                 if (TB) { nn = idx / GK; kb = idx % GK; } else { kb = idx / GN; nn = idx % GN; }
@@ -135,16 +137,16 @@ gemm_f64_kernel(int m, int n, int k, double alpha, const double *__restrict__ A,
         const double *Bs = As + GM * GLDA;
 #pragma unroll
         for (int ks = 0; ks < GK; ks += 4) {
-            double a[MT], b[4];
+            double a[MT], b[NTW];
 #pragma unroll
             for (int i = 0; i < MT; i++) a[i] = As[(wm + 8 * i + g) * GLDA + ks + t];
 #pragma unroll
-            for (int j = 0; j < 4; j++)
+            for (int j = 0; j < NTW; j++)
                 b[j] = TB ? Bs[(wn + 8 * j + g) * GLDA + ks + t] : Bs[(ks + t) * GLDB + wn + 8 * j + g];
 #pragma unroll
             for (int i = 0; i < MT; i++)
 #pragma unroll
-                for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                for (int j = 0; j < NTW; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
     }
     asm volatile("cp.async.wait_group 0;\n");
@@ -154,7 +156,7 @@ gemm_f64_kernel(int m, int n, int k, double alpha, const double *__restrict__ A,
         int row = m0 + wm + 8 * i + g;
         if (row >= m) continue;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < NTW; j++) {
             int col = n0 + wn + 8 * j + 2 * t;
 #pragma unroll
             for (int c = 0; c < 2; c++) {
