@@ -1366,6 +1366,14 @@ int wfo_trajectory_ci_host(wfo_ctx *ctx, const double *mos, const double *ci, in
     return WFO_OK;
 }
 
+#ifdef WFO_WPM_CLOCKS
+int wfo_debug_wpm_clocks(long long *out8, int reset) {
+    if (out8) cudaMemcpyFromSymbol(out8, g_wpm_clk, sizeof(long long) * 8);
+    if (reset) { long long z[8] = {0}; cudaMemcpyToSymbol(g_wpm_clk, z, sizeof(z)); }
+    return 0;
+}
+#endif
+
 #ifdef WFO_LUB_CLOCKS
 int wfo_debug_lub_clocks(long long *out16, int reset) {
     if (out16) cudaMemcpyFromSymbol(out16, g_lub_clk, sizeof(long long) * 16);

@@ -28,8 +28,16 @@
 
 namespace wfo {
 
+#ifdef WFO_WPM_CLOCKS
+__device__ long long g_wpm_clk[8];
+#define WPM_T(i) do { long long now_ = clock64(); t_acc[i] += now_ - t_prev; t_prev = now_; } while (0)
+#else
+#define WPM_T(i)
+#endif
+
 struct WpmShared {            // per warp
     double L11[16][16];       // unit-lower factor of the current pivot block (strict lower part)
+    double urow[16];          // pivot row of the current column step (written by its lane, read by all)
     unsigned char rowmap[128];   // active rows in order
     unsigned char piv[16];    // pivot rows of the current panel, in step order
 };
@@ -109,6 +117,10 @@ __device__ __forceinline__ double wpm_lu_det(const double *__restrict__ S, int l
     double det = 1.0;
     bool zero = false;
     unsigned par = 0;
+#ifdef WFO_WPM_CLOCKS
+    long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long t_prev = clock64();
+#endif
     for (int j = 0; j < n; j += 16) {
         const int w = min(16, n - j);
         const bool first = (j == 0);
@@ -138,6 +150,7 @@ __device__ __forceinline__ double wpm_lu_det(const double *__restrict__ S, int l
                 }
             }
         }
+        WPM_T(0);
         int ppos[16];
         // ---- 16 column steps
 #pragma unroll
@@ -153,21 +166,23 @@ __device__ __forceinline__ double wpm_lu_det(const double *__restrict__ S, int l
                 const unsigned kmax = __reduce_max_sync(FULL, key);
                 const int wl = kmax & 31, ws = (kmax >> 5) & 3;
                 ppos[jj] = wl + 32 * ws;
+                // the pivot row goes through shared memory (one lane writes, all read it back): a
+                // handful of STS/LDS instead of up to 34 shuffles, which 8 warps per SM saturate
                 double u[16];
-                int pp = 0;
 #pragma unroll
                 for (int s = 0; s < SLOTS; s++) {
-                    if (ws == s) {   // warp-uniform
+                    if (ws == s && lane == wl) {
 #pragma unroll
-                        for (int c = jj; c < 16; c++) u[c] = __shfl_sync(FULL, a[s][c], wl);
-                        pp = __shfl_sync(FULL, pr[s], wl);
-                        if (lane == wl) {
+                        for (int c = jj; c < 16; c++) sh->urow[c] = a[s][c];
 #pragma unroll
-                            for (int c = 0; c < jj; c++) sh->L11[jj][c] = a[s][c];
-                        }
+                        for (int c = 0; c < jj; c++) sh->L11[jj][c] = a[s][c];
+                        sh->piv[jj] = (unsigned char)pr[s];
                     }
                 }
-                if (lane == 0) sh->piv[jj] = (unsigned char)pp;
+                __syncwarp();
+#pragma unroll
+                for (int c = jj; c < 16; c++) u[c] = sh->urow[c];
+                __syncwarp();
                 const double piv = u[jj];
                 det *= piv;
                 zero = zero || (piv == 0.0);
@@ -184,6 +199,7 @@ __device__ __forceinline__ double wpm_lu_det(const double *__restrict__ S, int l
                 }
             }
         }
+        WPM_T(1);
         // ---- sign: rank of every pivot among the rows still active when it is extracted
         {
             int myp = 0;
@@ -198,6 +214,7 @@ __device__ __forceinline__ double wpm_lu_det(const double *__restrict__ S, int l
             const bool odd = (lane < w) && (((myp - cnt) & 1) != 0);
             par ^= (unsigned)(__popc(__ballot_sync(FULL, odd)) & 1);
         }
+        WPM_T(2);
         if (j + 16 >= n) break;
         __syncwarp();   // L11[][] and piv[] complete
         // ---- M = L21 L11^-1 (axpy form of x L11 = l); pivot rows are modified too, harmlessly
@@ -210,6 +227,7 @@ __device__ __forceinline__ double wpm_lu_det(const double *__restrict__ S, int l
                 for (int s = 0; s < SLOTS; s++) a[s][c] = fma(-a[s][q], lqc, a[s][c]);
             }
         }
+        WPM_T(3);
         // ---- write M of the remaining rows, drop the pivot rows from the row map
         int newL[SLOTS];
         int below = 0;
@@ -235,10 +253,15 @@ __device__ __forceinline__ double wpm_lu_det(const double *__restrict__ S, int l
         }
         act -= 16;
         __syncwarp();   // M (global) and the row map are visible to the whole warp
+        WPM_T(4);
         if (first) wpm_update<true>(S, ld_s, rows, cols, W, LD, sh, n, j, act, lane);
         else wpm_update<false>(S, ld_s, rows, cols, W, LD, sh, n, j, act, lane);
         __syncwarp();
+        WPM_T(5);
     }
+#ifdef WFO_WPM_CLOCKS
+    if (lane == 0 && blockIdx.x == 0 && (threadIdx.x >> 5) == 1) for (int i = 0; i < 8; i++) g_wpm_clk[i] += t_acc[i];
+#endif
     return zero ? 0.0 : (par ? -det : det);
 }
 
