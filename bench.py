@@ -4,8 +4,8 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference ...                       # reference algorithm on host cores
 
-One "step" = one pass of the whole hot path over the workload: S_AO = Cinv Cinv^T,
-S_MO = C_bra S_AO C_ket^T, every (bra SD, ket SD) determinant and the CI-weighted
+One "step" = one pass of the whole hot path over the workload: S_MO = C_bra S_AO C_ket^T with
+S_AO = Cinv Cinv^T (evaluated as (C_bra Cinv)(C_ket Cinv)^T), every (bra SD, ket SD) determinant and the CI-weighted
 reduction into the n_bra x n_ket matrix (+ the all-reduce for N > 1).
 Metric: determinant-pair overlaps per second, N_pairs = (K_bra+1)(K_ket+1).
 
@@ -207,7 +207,7 @@ def run_ours(args, w):
     f64 = dict(dtype=torch.float64, device=dev)
     d_bra, d_ket, d_inv = (torch.tensor(np.ascontiguousarray(x), **f64).contiguous()
                            for x in (bra_mos, ket_mos, c_inv))
-    d_sao, d_smo = torch.empty((n_mo, n_mo), **f64), torch.empty((n_mo, n_mo), **f64)
+    d_work, d_smo = torch.empty((2, n_mo, n_mo), **f64), torch.empty((n_mo, n_mo), **f64)
     d_be = torch.tensor(bt.exc, dtype=torch.int32, device=dev)
     d_ke = torch.tensor(kt.exc, dtype=torch.int32, device=dev)
     d_cb, d_ck = torch.tensor(bt.coeff, **f64).contiguous(), torch.tensor(kt.coeff, **f64).contiguous()
@@ -217,8 +217,7 @@ def run_ours(args, w):
     ctx.set_timing(True)
 
     def step():
-        ctx.sao_dev(d_inv, d_sao, stream)
-        ctx.smo_dev(d_bra, d_sao, d_ket, d_smo, stream)
+        ctx.smo_inv_dev(d_bra, d_ket, d_inv, d_smo, d_work, stream)   # S_MO = bra (Cinv Cinv^T) ket^T
         ctx.state_overlaps_dev(d_smo, n, d_be, d_cb, d_ke, d_ck, d_out, sigma=sigma, tier=tier,
                                k_begin=lo, k_end=hi, stream=stream)
         if world > 1:

@@ -76,6 +76,10 @@ int wfo_smo_host(wfo_ctx *ctx, const double *bra_mos, const double *s_ao, const 
 /* S_AO = Cinv Cinv^T, replaces the product in pywfo/main.py:304 (the inverse
  * itself stays numpy/LAPACK on the host, as in the reference). */
 int wfo_sao_dev(wfo_ctx *ctx, const double *c_inv, int n, double *s_ao, void *stream);
+/* S_MO from the inverse behind S_AO in two launches: S_MO = (bra Cinv)(ket Cinv)^T -- the same product as
+ * pywfo/main.py:304 + :532, associated so that S_AO is never materialised (work: 2 n*n doubles or NULL). */
+int wfo_smo_inv_dev(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos, const double *c_inv, int n,
+                    double *s_mo, double *work, void *stream);
 /* a_inv = a^-1 (n x n), replaces np.linalg.inv in pywfo/main.py:303 (98, 212): Newton-Schulz
  * iteration X <- X (2I - A X) from X0 = A^T / (|A|_1 |A|_inf), i.e. nothing but FP64 tensor-core
  * GEMMs; quadratically convergent for every non-singular A, about 2 log2(cond) + 10 iterations.

@@ -45,6 +45,7 @@ SIGNATURES = {
                                           c_vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, c_vp]),
     "wfo_overlaps_host": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, C.c_int, c_vp, C.c_int, c_vp,
                                     C.c_int, c_vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, c_vp]),
+    "wfo_smo_inv_dev": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp]),
     "wfo_inverse_dev": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp]),
     "wfo_inverse_host": (C.c_int, [c_vp, c_vp, C.c_int, c_vp]),
     "wfo_overlaps_ci_host": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, c_vp, C.c_int,
@@ -260,6 +261,14 @@ class Context:
         q, v = ket.shape
         check(self.lib.wfo_smo_dev(self.handle, bra.data_ptr(), s_ao.data_ptr(), ket.data_ptr(), p, u, v, q,
                                    out.data_ptr(), None, stream))
+
+    def smo_inv_dev(self, bra, ket, c_inv, out, work, stream=0):
+        """S_MO = (bra Cinv)(ket Cinv)^T; ``work`` holds 2 n*n doubles."""
+        self._dev(bra, ket, c_inv, out, work)
+        if work.numel() < 2 * bra.shape[0] * bra.shape[0]:
+            raise ValueError("work must hold 2 n*n doubles")
+        check(self.lib.wfo_smo_inv_dev(self.handle, bra.data_ptr(), ket.data_ptr(), c_inv.data_ptr(), bra.shape[0],
+                                       out.data_ptr(), work.data_ptr(), stream))
 
     def sao_dev(self, c_inv, out, stream=0):
         self._dev(c_inv, out)

@@ -619,6 +619,36 @@ int wfo_inverse_host(wfo_ctx *ctx, const double *a, int n, double *a_inv) {
     return WFO_OK;
 }
 
+/* S_MO straight from the inverse behind S_AO: S_MO = bra (Cinv Cinv^T) ket^T = (bra Cinv)(ket Cinv)^T.
+ * Same product as pywfo/main.py:304 + :532 with the matrix chain associated the other way: two
+ * launches (the two left factors as one batched GEMM, then P Q^T) instead of three dependent ones,
+ * and S_AO is never materialised.  work: 2 n*n doubles. */
+int wfo_smo_inv_dev(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos, const double *c_inv, int n,
+                    double *s_mo, double *work, void *stream) {
+    if (!ctx || !bra_mos || !ket_mos || !c_inv || !s_mo) return set_err(WFO_ERR_ARG, "smo_inv: NULL argument");
+    WFO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nn = (size_t)n * n;
+    if (!work) {
+        WFO_TRY(ensure_scratch(ctx, 2 * nn * sizeof(double) + 512));
+        work = reinterpret_cast<double *>(ctx->scratch);
+    }
+    double *P = work, *Q = work + nn;
+    const ptrdiff_t dbytes = reinterpret_cast<const char *>(ket_mos) - reinterpret_cast<const char *>(bra_mos);
+    if (bra_mos == ket_mos) {
+        WFO_TRY(gemm(ctx, false, false, n, n, n, 1.0, bra_mos, n, c_inv, n, 0.0, P, n, 0, 0, st));
+        Q = P;
+    } else if (dbytes % (ptrdiff_t)sizeof(double) == 0) {
+        // one launch, grid.z = 2: z = 0 -> P = bra Cinv, z = 1 -> Q = ket Cinv
+        WFO_TRY(gemm(ctx, false, false, n, n, n, 1.0, bra_mos, n, c_inv, n, 0.0, P, n, 0, (long long)nn, st, 2,
+                     (long long)(dbytes / (ptrdiff_t)sizeof(double)), 0));
+    } else {
+        WFO_TRY(gemm(ctx, false, false, n, n, n, 1.0, bra_mos, n, c_inv, n, 0.0, P, n, 0, 0, st));
+        WFO_TRY(gemm(ctx, false, false, n, n, n, 1.0, ket_mos, n, c_inv, n, 0.0, Q, n, 0, 0, st));
+    }
+    return gemm(ctx, false, true, n, n, n, 1.0, P, n, Q, n, 0.0, s_mo, n, 0, 0, st);
+}
+
 int wfo_smo_host(wfo_ctx *ctx, const double *bra_mos, const double *s_ao, const double *ket_mos, int p, int u,
                  int v, int q, double *s_mo) {
     if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL");
@@ -1179,8 +1209,7 @@ static int overlaps_ci_core(wfo_ctx *ctx, const CiWork &w, const double *d_bra, 
         WFO_TRY(wfo_inverse_dev(ctx, ao_side == WFO_AO_BRA ? d_bra : d_ket, n_mo, w.inv, w.work, s2));
         d_inv = w.inv;
     }
-    WFO_TRY(wfo_sao_dev(ctx, d_inv, n_mo, w.sao, s2));
-    WFO_TRY(wfo_smo_dev(ctx, d_bra, w.sao, d_ket, n_mo, n_mo, n_mo, n_mo, w.smo, w.work, s2));
+    WFO_TRY(wfo_smo_inv_dev(ctx, d_bra, d_ket, d_inv, n_mo, w.smo, w.work, s2));   // work, work2 contiguous
     WFO_CUDA(cudaEventRecord(ctx->ev_join, s2));
     WFO_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     // ---- the table sizes (and per-state counts) come back: 2 small copies, one sync

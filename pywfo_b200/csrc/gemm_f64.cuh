@@ -5,11 +5,11 @@
 // tier, and (with split-K slabs) for the final CI contraction S = Cb G.
 //
 // CTA tile GM x GN (64x64, or 32x64 / 32x32 when that is needed to fill the 148 SMs), 4 warps
-// in a 2x2 grid, warp tile (GM/2) x (GN/2) = (GM/16) x (GN/16) DMMA.8x8x4 tiles, K tile 16.  Operand tiles
+// in a 2x2 grid, warp tile (GM/2) x (GN/2) = (GM/16) x (GN/16) DMMA.8x8x4 tiles, K tile 32.  Operand tiles
 // are brought in with cp.async (16-byte copies when the operands allow it, else 8-byte elements;
 // zero fill at the edges) through a 3-stage shared-memory ring, so the L2 latency of tile t+2 hides behind the DMMAs of tile t with one
 // block barrier per K tile.  Padded shared tiles make both fragment loads conflict-free
-// (k-contiguous tiles: stride 20 doubles, n-contiguous B tile: stride 72 doubles).  blockIdx.z selects a K slab (split-K): slab z
+// (k-contiguous tiles: stride 36 doubles, n-contiguous B tile: stride GN + 8 doubles).  blockIdx.z selects a K slab (split-K): slab z
 // covers k in [z*kslab, min(k,(z+1)*kslab)) and writes C + z*slab_stride; deterministic,
 // summed by a later kernel in fixed order.  With batch strides blockIdx.z is a batch index.
 #pragma once
@@ -17,11 +17,11 @@
 
 namespace wfo {
 
-constexpr int GK = 16;            // GM (64 / 32 rows) and GN (64 / 32 columns per CTA) are template parameters
-constexpr int GLDA = GK + 4;      // 20: row stride of k-contiguous tiles (A, and B when it is stored transposed)
+constexpr int GK = 32;            // GM (64 / 32 rows) and GN (64 / 32 columns per CTA) are template parameters
+constexpr int GLDA = GK + 4;      // 36: row stride of k-contiguous tiles (A, and B when it is stored transposed)
 constexpr int GSTAGES = 3;
 template <int GN> constexpr int gemm_ldb() { return GN + 8; }        // 72 / 40: row stride of the n-contiguous B tile
-template <int GN> constexpr int gemm_bs() { return GN * GLDA; }      // doubles reserved for the B tile (>= GK * ldb)
+template <int GN> constexpr int gemm_bs() { return GN * GLDA > GK * (GN + 8) ? GN * GLDA : GK * (GN + 8); }   // B tile of a stage, either layout
 
 template <int GM, int GN>
 constexpr size_t gemm_smem_bytes() { return (size_t)GSTAGES * (GM * GLDA + gemm_bs<GN>()) * sizeof(double); }
@@ -45,7 +45,7 @@ gemm_f64_kernel(int m, int n, int k, double alpha, const double *__restrict__ A,
                 int kslab, long long slab_stride, long long batch_a, long long batch_b) {
     extern __shared__ __align__(16) double gsm[];
     constexpr int GLDB = GN + 8;
-    constexpr int STAGE = GM * GLDA + GN * GLDA;   // doubles per stage
+    constexpr int STAGE = GM * GLDA + (GN * GLDA > GK * (GN + 8) ? GN * GLDA : GK * (GN + 8));   // doubles per stage
     constexpr int NTW = GN / 16;                       // 8-column tiles per warp
 
     const int tid = threadIdx.x;
@@ -75,18 +75,18 @@ gemm_f64_kernel(int m, int n, int k, double alpha, const double *__restrict__ A,
         double *Bs = As + GM * GLDA;
         if (VEC) {
 #pragma unroll
-            for (int e = 0; e < GM / 16; e++) {
+            for (int e = 0; e < GM * (GK / 2) / 128; e++) {
                 const int idx = tid + e * 128;
-                const int mm = idx >> 3, kc = (idx & 7) * 2;
+                const int mm = idx / (GK / 2), kc = (idx % (GK / 2)) * 2;
                 const int gm = m0 + mm, gk = k0 + kc;
                 const int bytes = (gm < m) ? max(0, min(16, (kend - gk) * 8)) : 0;
                 cp_async16(As + mm * GLDA + kc, bytes ? A + (long long)gm * lda + gk : A, bytes);
             }
 #pragma unroll
-            for (int e = 0; e < GN / 16; e++) {
+            for (int e = 0; e < GN * (GK / 2) / 128; e++) {
                 const int idx = tid + e * 128;
                 if (TB) {
-                    const int nn = idx >> 3, kc = (idx & 7) * 2;
+                    const int nn = idx / (GK / 2), kc = (idx % (GK / 2)) * 2;
                     const int gn = n0 + nn, gk = k0 + kc;
                     const int bytes = (gn < n) ? max(0, min(16, (kend - gk) * 8)) : 0;
                     cp_async16(Bs + nn * GLDA + kc, bytes ? B + (long long)gn * ldb + gk : B, bytes);
@@ -109,7 +109,7 @@ gemm_f64_kernel(int m, int n, int k, double alpha, const double *__restrict__ A,
                 cp_async8(As + mm * GLDA + kk, src, ok);
             }
 #pragma unroll
-            for (int e = 0; e < GN / 8; e++) {
+            for (int e = 0; e < GN * GK / 128; e++) {
                 const int idx = tid + e * 128;
                 int nn, kb;
                 if (TB) { nn = idx / GK; kb = idx % GK; } else { kb = idx / GN; nn = idx % GN; }

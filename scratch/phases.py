@@ -24,7 +24,7 @@ kt = ex.build_tables(kci, thr, "cache", order="locality")
 c_inv = np.linalg.inv(ket_mos)
 f64 = dict(dtype=torch.float64, device=dev)
 d_bra, d_ket, d_inv = (torch.tensor(np.ascontiguousarray(x), **f64) for x in (bra_mos, ket_mos, c_inv))
-d_sao, d_smo = torch.empty((n_mo, n_mo), **f64), torch.empty((n_mo, n_mo), **f64)
+d_work, d_smo = torch.empty((2, n_mo, n_mo), **f64), torch.empty((n_mo, n_mo), **f64)
 d_be = torch.tensor(bt.exc, dtype=torch.int32, device=dev)
 d_ke = torch.tensor(kt.exc, dtype=torch.int32, device=dev)
 d_cb, d_ck = torch.tensor(bt.coeff, **f64), torch.tensor(kt.coeff, **f64)
@@ -44,8 +44,7 @@ for world in (1, 8):
         torch.cuda.synchronize()
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record()
-        ctx.sao_dev(d_inv, d_sao, stream)
-        ctx.smo_dev(d_bra, d_sao, d_ket, d_smo, stream)
+        ctx.smo_inv_dev(d_bra, d_ket, d_inv, d_smo, d_work, stream)
         e1.record()
         ctx.state_overlaps_dev(d_smo, n, d_be, d_cb, d_ke, d_ck, d_out, tier="auto", k_begin=lo, k_end=hi, stream=stream)
         e2.record()

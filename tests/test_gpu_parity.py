@@ -486,3 +486,24 @@ def test_trajectory_excitation_shards_add_up(ctx):
                 for r in range(3))
     np.testing.assert_allclose(parts, full, rtol=1e-12, atol=1e-14 * np.abs(full).max())
     assert info[0] > 0 and info[1] > 0
+
+
+def test_smo_from_inverse_two_launch_chain(ctx):
+    """S_MO = (bra Cinv)(ket Cinv)^T (wfo_smo_inv_dev) == bra (Cinv Cinv^T) ket^T (main.py:304, 532)."""
+    import torch
+    for name in ("h2o2", "r_n34", "r_odd"):
+        g = load_golden(name)
+        for ao in ("ket", "bra"):
+            inv = np.linalg.inv(g["ket_mos"] if ao == "ket" else g["bra_mos"])
+            want = orc.mo_overlap(g["bra_mos"], g["ket_mos"], orc.get_S_AO(g["bra_mos"], g["ket_mos"], ao))
+            f64 = dict(dtype=torch.float64, device="cuda")
+            d_bra, d_ket, d_inv = (torch.tensor(np.ascontiguousarray(x), **f64) for x in (g["bra_mos"], g["ket_mos"], inv))
+            n = d_bra.shape[0]
+            out, work = torch.empty((n, n), **f64), torch.empty((2, n, n), **f64)
+            ctx.smo_inv_dev(d_bra, d_ket, d_inv, out, work)
+            torch.cuda.synchronize()
+            np.testing.assert_allclose(out.cpu().numpy(), want, rtol=1e-11, atol=1e-12)
+            ctx.smo_inv_dev(d_bra, d_bra, d_inv, out, work)      # same matrix on both sides: single left factor
+            torch.cuda.synchronize()
+            want2 = orc.mo_overlap(g["bra_mos"], g["bra_mos"], inv @ inv.T)
+            np.testing.assert_allclose(out.cpu().numpy(), want2, rtol=1e-11, atol=1e-12)
