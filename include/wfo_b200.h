@@ -81,8 +81,9 @@ int wfo_sao_dev(wfo_ctx *ctx, const double *c_inv, int n, double *s_ao, void *st
 int wfo_smo_inv_dev(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos, const double *c_inv, int n,
                     double *s_mo, double *work, void *stream);
 /* a_inv = a^-1 (n x n), replaces np.linalg.inv in pywfo/main.py:303 (98, 212): Newton-Schulz
- * iteration X <- X (2I - A X) from X0 = A^T / (|A|_1 |A|_inf), i.e. nothing but FP64 tensor-core
- * GEMMs; quadratically convergent for every non-singular A, about 2 log2(cond) + 10 iterations.
+ * iteration X <- X (2I - A X) from X0 = A^T / |A^T A|_inf, i.e. nothing but FP64 tensor-core
+ * GEMMs; quadratically convergent for every non-singular A, about 2 log2(cond) + 6 iterations
+ * (orthonormal MOs: the first iterate is already the inverse).
  * `work` = 2 n*n doubles of device scratch (NULL: from the context).  Synchronises the stream
  * every few iterations to read the residual max|A X - I|.  WFO_ERR_NOCONV if it does not
  * converge within 100 iterations (singular or extremely ill-conditioned input). */

@@ -569,7 +569,10 @@ int wfo_inverse_dev(wfo_ctx *ctx, const double *a, int n, double *a_inv, double 
     double *X = a_inv, *Xn = Xb;   // ping-pong; the result must end in a_inv
     double *slots = ctx->ns_slots;
     WFO_CUDA(cudaMemsetAsync(slots, 0, 128 * sizeof(double), st));
-    ns_norms_kernel<<<n, 256, 0, st>>>(a, n, slots);
+    // starting scale 1 / |A^T A|_inf: a rigorous bound on sigma_max^2 that is never worse than
+    // |A|_1 |A|_inf and EXACT for orthonormal MO matrices (A^T A = I: the first iterate is the answer)
+    WFO_TRY(gemm(ctx, true, false, n, n, n, 1.0, a, n, a, n, 0.0, T, n, 0, 0, st));
+    ns_norms_kernel<<<n, 256, 0, st>>>(T, n, slots);
     WFO_LAUNCH_CHECK(ctx);
     ns_init_kernel<<<dim3(cdiv(n, 32), cdiv(n, 32)), dim3(32, 8), 0, st>>>(a, n, slots, X);
     WFO_LAUNCH_CHECK(ctx);
@@ -578,7 +581,7 @@ int wfo_inverse_dev(wfo_ctx *ctx, const double *a, int n, double *a_inv, double 
     bool converged = false;
     ctx->last_inverse_iters = 0;
     while (it < NS_MAX_ITERS && !converged) {
-        const int batch = (it == 0) ? 10 : 4;   // iterations between two looks at the residuals
+        const int batch = 3;   // iterations between two looks at the residuals
         for (int b = 0; b < batch && it < NS_MAX_ITERS; b++, it++) {
             // T = A X; residual max|T - I| -> slots[2 + it], Xn = X; Xn = 2 Xn - X T
             WFO_TRY(gemm(ctx, false, false, n, n, n, 1.0, a, n, X, n, 0.0, T, n, 0, 0, st));

@@ -274,10 +274,10 @@ __global__ void __launch_bounds__(256) ns_norms_kernel(const double *__restrict_
         atomic_max_nonneg(slots + 1, red[1][0]);
     }
 }
-// X0 = A^T / (|A|_1 |A|_inf)
+// X0 = A^T / slots[0]   (slots[0] = |A^T A|_inf >= sigma_max(A)^2)
 __global__ void ns_init_kernel(const double *__restrict__ A, int n, const double *__restrict__ slots, double *__restrict__ X) {
     __shared__ double tile[32][33];
-    const double sc = 1.0 / (slots[0] * slots[1]);
+    const double sc = 1.0 / slots[0];
     const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
     for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
         const int r = by + dy, c = bx + threadIdx.x;
