@@ -507,3 +507,33 @@ def test_smo_from_inverse_two_launch_chain(ctx):
             torch.cuda.synchronize()
             want2 = orc.mo_overlap(g["bra_mos"], g["bra_mos"], inv @ inv.T)
             np.testing.assert_allclose(out.cpu().numpy(), want2, rtol=1e-11, atol=1e-12)
+
+
+@pytest.mark.parametrize("n_ket", [1, 2, 7, 8, 9, 15, 16, 17, 23, 24, 25, 32, 39, 40, 41, 47, 48, 49, 55, 56, 57, 111])
+def test_every_rank_update_kernel_variant(ctx, n_ket):
+    """All (row stride, DMMA tile count) variants of the rank-update kernel, and the multi-pass path for more
+    than 55 ket states; ragged bra/ket tile edges (kb, kk not multiples of the 256 x 32 tiles); shard offsets."""
+    rng = np.random.default_rng(1000 + n_ket)
+    occ, n_mo = 7, 30
+    q, _ = np.linalg.qr(rng.standard_normal((n_mo, n_mo)))
+    S = q + 0.05 * rng.standard_normal((n_mo, n_mo))
+    bra, Cb, ket, Ck = _random_tables(rng, occ, n_mo - occ, 301, 77, 5, n_ket, with_gs=True)
+    want = orc.state_overlaps_bruteforce(S, occ, [tuple(e) for e in bra], Cb, [tuple(e) for e in ket], Ck, 1.0)
+    got = ctx.state_overlaps_host(S, occ, bra, Cb, ket, Ck, tier="update")
+    assert ctx.last_tier() == 1
+    assert_parity(got, want)
+    parts = sum(ctx.state_overlaps_host(S, occ, bra, Cb, ket, Ck, tier="update", k_begin=lo, k_end=hi)
+                for lo, hi in ((0, 1), (1, 257), (257, 301)))
+    np.testing.assert_allclose(parts, got, rtol=1e-11, atol=1e-13 * np.abs(got).max())
+
+
+def test_results_are_run_to_run_identical(ctx):
+    """no floating-point atomics, static stream-K split, fixed-order reductions -> bitwise
+    reproducible on a fixed GPU count (both tiers, and the whole path from raw inputs)."""
+    from pywfo_b200 import helpers, main
+    bra_mos, ket_mos, bci, kci = helpers.synthetic_case(5, 60, 20, 7, 9)
+    for tier in ("update", "lu"):
+        a = main.overlaps_cache(bra_mos, ket_mos, bci, kci, 20, ci_thresh=0.02, tier=tier)
+        for _ in range(3):
+            b = main.overlaps_cache(bra_mos, ket_mos, bci, kci, 20, ci_thresh=0.02, tier=tier)
+            assert np.array_equal(a, b)
