@@ -399,7 +399,11 @@ def run_ours(args, w):
         "config": {"workload": f"{args.workload}: {w['desc']}", "n_occ": n, "n_mo": n_mo, "n_bra": w["n_bra"],
                    "n_ket": w["n_ket"], "K_bra": Kb, "K_ket": Kk, "pairs": n_pairs, "sigma": sigma,
                    "tier": {0: "lu", 1: "update"}.get(used_tier, str(used_tier)), "parallelism": f"bra-shard x{world}",
-                   "l2": "flushed (256 MB write) between timed steps; inputs 38 MB < L2"},
+                   "l2": "flushed (256 MB write) between timed steps; inputs 38 MB < L2",
+                   "inputs": "device leg (value): MO matrices, the inverse behind S_AO (pywfo/main.py:303, a host-side "
+                             "prologue upstream) and the excitation tables are resident in HBM before the timed region; "
+                             "e2e leg: MO matrices and raw CI tensors in pinned host memory, inverse and thresholding "
+                             "on the device inside the timed region"},
         "wall_ms_per_matrix": ms_per_step,
         "clocks": clocks,
         "e2e": {"value": n_pairs / e2e_s, "unit": "pairs/s", "ms_per_call": e2e_s * 1e3,

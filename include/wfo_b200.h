@@ -73,8 +73,8 @@ int wfo_smo_dev(wfo_ctx *ctx, const double *bra_mos, const double *s_ao, const d
                 int p, int u, int v, int q, double *s_mo, double *work, void *stream);
 int wfo_smo_host(wfo_ctx *ctx, const double *bra_mos, const double *s_ao, const double *ket_mos,
                  int p, int u, int v, int q, double *s_mo);
-/* S_AO = Cinv Cinv^T, replaces the product in pywfo/main.py:304 (the inverse
- * itself stays numpy/LAPACK on the host, as in the reference). */
+/* S_AO = Cinv Cinv^T, replaces the product in pywfo/main.py:304 (the inverse itself:
+ * wfo_inverse_dev below, or any inverse the caller already has). */
 int wfo_sao_dev(wfo_ctx *ctx, const double *c_inv, int n, double *s_ao, void *stream);
 /* S_MO from the inverse behind S_AO in two launches: S_MO = (bra Cinv)(ket Cinv)^T -- the same product as
  * pywfo/main.py:304 + :532, associated so that S_AO is never materialised (work: 2 n*n doubles or NULL). */
