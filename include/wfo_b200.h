@@ -45,7 +45,8 @@ extern "C" {
 #define WFO_AO_BRA 1   /* ao_ovlps="bra": bra_mos is inverted on the device */
 #define WFO_AO_KET 2   /* ao_ovlps="ket": ket_mos is inverted on the device */
 
-/* algorithm tiers (identical results to ~1e-13) */
+/* algorithm tiers (identical results to ~1e-13).  n_occ <= 128 for the brute-force tier,
+ * n_occ <= 4096 for the rank-update and closed-form tiers (base block inverted blockwise above 128). */
 #define WFO_TIER_LU 0      /* T0: one partially pivoted LU per determinant pair          */
 #define WFO_TIER_UPDATE 1  /* T1: one base LU + rank-1 row/column update per pair        */
 #define WFO_TIER_CLOSED 2  /* T2: closed-form contraction (GEMMs only), pair determinants never formed; opt-in */

@@ -114,6 +114,53 @@ static int gemm(wfo_ctx *ctx, bool ta, bool tb, int m, int n, int k, double alph
     return WFO_OK;
 }
 
+// ---- base block of any size: register-resident Gauss-Jordan up to 128, above that a 2x2 block inverse
+// through the Schur complement (recursive), everything else DMMA GEMMs:
+//   inv(A) = [[A11i + T1 Si T2, -T1 Si], [-Si T2, Si]],  T1 = A11i A12, T2 = A21 A11i, S = A22 - A21 T1
+constexpr int WFO_MAX_OCC = 4096;
+static size_t base_work_doubles(int n) {
+    if (n <= LUB_MAXN) return 0;
+    const size_t n1 = n / 2, n2 = n - n1;
+    const size_t a = base_work_doubles((int)n1), b = base_work_doubles((int)n2);
+    return n1 * n1 + 2 * n1 * n2 + 2 * n2 * n2 + 64 + (a > b ? a : b);
+}
+static int copy2d(wfo_ctx *ctx, const double *src, int ld_src, double *dst, int ld_dst, int rows, int cols, cudaStream_t st) {
+    const long long tot = (long long)rows * cols;
+    if (tot <= 0) return WFO_OK;
+    copy2d_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(src, ld_src, dst, ld_dst, rows, cols);
+    WFO_LAUNCH_CHECK(ctx);
+    return WFO_OK;
+}
+static int base_factor(wfo_ctx *ctx, const double *A, int lda, int n, double *Ai, int ldo, BaseInfo *info, double *work,
+                       cudaStream_t st) {
+    if (n <= LUB_MAXN) {
+        base_inverse_kernel<<<1, LUB_THREADS, lub_smem_bytes(n), st>>>(A, lda, n, Ai, ldo, info);
+        WFO_LAUNCH_CHECK(ctx);
+        return WFO_OK;
+    }
+    const int n1 = n / 2, n2 = n - n1;
+    double *A11i = work, *T1 = A11i + (size_t)n1 * n1, *T2 = T1 + (size_t)n1 * n2, *S = T2 + (size_t)n2 * n1,
+           *Si = S + (size_t)n2 * n2;
+    BaseInfo *infos = reinterpret_cast<BaseInfo *>(Si + (size_t)n2 * n2);
+    double *rest = Si + (size_t)n2 * n2 + 64;
+    const double *A12 = A + n1, *A21 = A + (size_t)n1 * lda, *A22 = A21 + n1;
+    WFO_TRY(base_factor(ctx, A, lda, n1, A11i, n1, &infos[0], rest, st));
+    WFO_TRY(gemm(ctx, false, false, n1, n2, n1, 1.0, A11i, n1, A12, lda, 0.0, T1, n2, 0, 0, st));
+    WFO_TRY(gemm(ctx, false, false, n2, n1, n1, 1.0, A21, lda, A11i, n1, 0.0, T2, n1, 0, 0, st));
+    WFO_TRY(copy2d(ctx, A22, lda, S, n2, n2, n2, st));
+    WFO_TRY(gemm(ctx, false, false, n2, n2, n1, -1.0, A21, lda, T1, n2, 1.0, S, n2, 0, 0, st));
+    WFO_TRY(base_factor(ctx, S, n2, n2, Si, n2, &infos[1], rest, st));
+    double *B12 = Ai + n1, *B21 = Ai + (size_t)n1 * ldo, *B22 = B21 + n1;
+    WFO_TRY(copy2d(ctx, Si, n2, B22, ldo, n2, n2, st));
+    WFO_TRY(gemm(ctx, false, false, n1, n2, n2, -1.0, T1, n2, Si, n2, 0.0, B12, ldo, 0, 0, st));
+    WFO_TRY(gemm(ctx, false, false, n2, n1, n2, -1.0, Si, n2, T2, n1, 0.0, B21, ldo, 0, 0, st));
+    WFO_TRY(copy2d(ctx, A11i, n1, Ai, ldo, n1, n1, st));
+    WFO_TRY(gemm(ctx, false, false, n1, n1, n2, -1.0, B12, ldo, T2, n1, 1.0, Ai, ldo, 0, 0, st));
+    combine_info_kernel<<<1, 32, 0, st>>>(&infos[0], &infos[1], info);
+    WFO_LAUNCH_CHECK(ctx);
+    return WFO_OK;
+}
+
 static size_t t0_smem_bytes(int n) { return (size_t)n * (n | 1) * sizeof(double) + 2 * (size_t)n * sizeof(int); }
 static int t0_threads(int n) { return n > 64 ? 256 : 128; }
 
@@ -301,7 +348,7 @@ struct Plan {   // everything wfo_state_overlaps needs from the arena
     // T0
     int32_t *bra_lists, *ket_lists, *gs_list;
     // T1
-    double *Abuf, *Ai, *X, *Y, *Wb, *bscale;
+    double *Abuf, *Ai, *X, *Y, *Wb, *bscale, *bwork;
     BraMeta *bmeta;
     KetMeta *kmeta;
     BaseInfo *info;
@@ -333,6 +380,7 @@ static void carve(AR &ar, Plan &p, int n, int v, int ksh, int kk, int n_bra, int
         p.bmeta = ar.template take<BraMeta>(ksh_g);
         p.kmeta = ar.template take<KetMeta>(kk_pad);
         p.info = ar.template take<BaseInfo>(1);
+        p.bwork = ar.template take<double>(base_work_doubles(n) + 1);
     }
 }
 
@@ -344,7 +392,7 @@ struct Part {   // how the pair space of one call is cut up
     bool may_t0, want_t1;
 };
 
-static size_t base_smem_bytes(int n) { return n <= LUB_MAXN ? 0 : (size_t)1 << 40; }   // register resident, n <= 128
+static size_t base_smem_bytes(int n) { return n <= WFO_MAX_OCC ? 0 : (size_t)1 << 40; }   // block inverse above 128
 
 // which tiers can / should run for this call
 static int resolve_tier(const wfo_ctx *ctx, int n, int tier, bool *want_t1, bool *may_t0) {
@@ -354,7 +402,7 @@ static int resolve_tier(const wfo_ctx *ctx, int n, int tier, bool *want_t1, bool
         *want_t1 = true;
         *may_t0 = false;
         if (base_smem_bytes(n) > ctx->smem_optin)
-            return set_err(WFO_ERR_ARG, "state_overlaps: tier CLOSED supports n_occ <= 128, got %lld", n);
+            return set_err(WFO_ERR_ARG, "state_overlaps: tier CLOSED supports n_occ <= 4096, got %lld", n);
         return WFO_OK;
     }
     *want_t1 = (tier == WFO_TIER_AUTO || tier == WFO_TIER_UPDATE);
@@ -364,7 +412,7 @@ static int resolve_tier(const wfo_ctx *ctx, int n, int tier, bool *want_t1, bool
     if (tier == WFO_TIER_LU && !t0_fits)
         return set_err(WFO_ERR_ARG, "state_overlaps: tier LU supports n_occ <= 128, got %lld", n);
     if (tier == WFO_TIER_UPDATE && !t1_fits)
-        return set_err(WFO_ERR_ARG, "state_overlaps: tier UPDATE supports n_occ <= 128, got %lld", n);
+        return set_err(WFO_ERR_ARG, "state_overlaps: tier UPDATE supports n_occ <= 4096, got %lld", n);
     if (tier == WFO_TIER_AUTO) {
         if (!t1_fits) *want_t1 = false;
         if (!t0_fits) *may_t0 = false;
@@ -726,6 +774,7 @@ static size_t closed_form_bytes(int n, int v, int n_bra, int n_ket) {
     z.take<double>((size_t)n_bra * nv); z.take<double>((size_t)n_ket * nv); z.take<double>((size_t)n_bra * nv);
     z.take<double>((size_t)n_bra * nv); z.take<double>((size_t)cdiv((int)nv, 1024) * n_bra * n_ket);
     z.take<double>(n_bra); z.take<double>(n_ket); z.take<BaseInfo>(1); z.take<int>(1);
+    z.take<double>(base_work_doubles(n) + 1);
     return z.off;
 }
 
@@ -741,6 +790,7 @@ static int closed_form_impl(wfo_ctx *ctx, size_t arena_off, const double *s_mo, 
     const int kslab = 1024, n_slabs = cdiv((int)nv, kslab);
     Sizer sz;
     sz.off = arena_off;
+    double *bwork = nullptr;
     auto carve2 = [&](auto &ar, double *&Ai, double *&Xt, double *&Y, double *&Wb, double *&cb, double *&ck, double *&Z,
                       double *&T, double *&P, double *&bx, double *&ky, BaseInfo *&info, int *&flag) {
         Ai = ar.template take<double>((size_t)n * n);
@@ -756,6 +806,7 @@ static int closed_form_impl(wfo_ctx *ctx, size_t arena_off, const double *s_mo, 
         ky = ar.template take<double>(n_ket);
         info = ar.template take<BaseInfo>(1);
         flag = ar.template take<int>(1);
+        bwork = ar.template take<double>(base_work_doubles(n) + 1);
     };
     double *Ai, *Xt, *Y, *Wb, *cb, *ck, *Z, *T, *P, *bx, *ky;
     BaseInfo *info;
@@ -765,8 +816,7 @@ static int closed_form_impl(wfo_ctx *ctx, size_t arena_off, const double *s_mo, 
     Arena ar{ctx->scratch, ctx->scratch_bytes, arena_off};
     carve2(ar, Ai, Xt, Y, Wb, cb, ck, Z, T, P, bx, ky, info, flag);
 
-    base_inverse_kernel<<<1, LUB_THREADS, lub_smem_bytes(n), st>>>(s_mo, n_mo, n, Ai, info);
-    WFO_LAUNCH_CHECK(ctx);
+    WFO_TRY(base_factor(ctx, s_mo, n_mo, n, Ai, n, info, bwork, st));
     WFO_CUDA(cudaMemsetAsync(cb, 0, (size_t)n_bra * nv * 8, st));
     WFO_CUDA(cudaMemsetAsync(ck, 0, (size_t)n_ket * nv * 8, st));
     WFO_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
@@ -873,8 +923,7 @@ static int state_overlaps_block(wfo_ctx *ctx, size_t arena_off, const double *s_
         }
         WFO_CUDA(cudaEventRecord(ctx->ev_join, s2));
         // ---- one base factorisation, then the three block products
-        base_inverse_kernel<<<1, LUB_THREADS, lub_smem_bytes(n), st>>>(s_mo, n_mo, n, p.Ai, p.info);
-        WFO_LAUNCH_CHECK(ctx);
+        WFO_TRY(base_factor(ctx, s_mo, n_mo, n, p.Ai, n, p.info, p.bwork, st));
         // the conditioning of the base block decides whether the rank-update tier is usable.  The
         // 32-byte verdict travels to pinned host memory behind the kernel; the rank-update kernels
         // are queued right away (speculatively) and the host looks at the verdict after queueing

@@ -34,7 +34,7 @@ constexpr int LUB_RS = 4;                     // 4 row slots per thread (rows 4 
 constexpr int LUB_LDS = LUB_MAXN + 1;         // row stride of the staging tile
 inline size_t lub_smem_bytes(int n) { return (size_t)n * LUB_LDS * sizeof(double); }
 
-// A_src: n x n block with leading dimension ld_src.  Ai_out: n x n, ld = n.
+// A_src: n x n block with leading dimension ld_src.  Ai_out: n x n, leading dimension ld_out.
 // Dynamic shared memory: lub_smem_bytes(n) (staging tile for coalesced load / store).
 //
 // Ownership: lane l holds rows 4l..4l+3, warp w holds columns w, w+16, ..., w+112, so
@@ -49,7 +49,7 @@ inline size_t lub_smem_bytes(int n) { return (size_t)n * LUB_LDS * sizeof(double
 //     searches its pivot and publishes it while the other warps still work on the current step;
 //   * det / min / max pivot are accumulated by the owning warps and combined at the end.
 __global__ void __launch_bounds__(LUB_THREADS)
-base_inverse_kernel(const double *__restrict__ A_src, int ld_src, int n, double *__restrict__ Ai_out,
+base_inverse_kernel(const double *__restrict__ A_src, int ld_src, int n, double *__restrict__ Ai_out, int ld_out,
                     BaseInfo *__restrict__ info) {
     extern __shared__ __align__(16) double lub_tile[];    // n x LUB_LDS
     __shared__ __align__(16) double mcol[2][LUB_MAXN];    // multiplier column, double buffered by step parity
@@ -244,7 +244,7 @@ base_inverse_kernel(const double *__restrict__ A_src, int ld_src, int n, double 
     if (!tsing)
         for (int idx = tid; idx < n * n; idx += LUB_THREADS) {
             const int r = idx / n, c = idx - r * n;
-            Ai_out[idx] = lub_tile[r * LUB_LDS + c];
+            Ai_out[(size_t)r * ld_out + c] = lub_tile[r * LUB_LDS + c];
         }
     LUB_T(9);
 #ifdef WFO_LUB_CLOCKS
@@ -256,6 +256,28 @@ base_inverse_kernel(const double *__restrict__ A_src, int ld_src, int n, double 
         info->max_piv = tmax;
         info->singular = tsing;
     }
+}
+
+// verdict of a 2x2 block inverse: A = [[A11, A12], [A21, A22]], det(A) = det(A11) det(S), S the Schur complement
+__global__ void combine_info_kernel(const BaseInfo *__restrict__ a, const BaseInfo *__restrict__ b, BaseInfo *__restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        BaseInfo r;
+        r.det = a->det * b->det;
+        r.min_piv = fmin(a->min_piv, b->min_piv);
+        r.max_piv = fmax(a->max_piv, b->max_piv);
+        r.singular = a->singular | b->singular;
+        r.pad = 0;
+        *out = r;
+    }
+}
+
+// dst (rows x cols, ld_dst) = src (ld_src)
+__global__ void copy2d_kernel(const double *__restrict__ src, int ld_src, double *__restrict__ dst, int ld_dst, int rows,
+                              int cols) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)rows * cols) return;
+    const int r = (int)(idx / cols), c = (int)(idx - (long long)r * cols);
+    dst[(size_t)r * ld_dst + c] = src[(size_t)r * ld_src + c];
 }
 
 }  // namespace wfo

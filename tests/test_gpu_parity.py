@@ -537,3 +537,25 @@ def test_results_are_run_to_run_identical(ctx):
         for _ in range(3):
             b = main.overlaps_cache(bra_mos, ket_mos, bci, kci, 20, ci_thresh=0.02, tier=tier)
             assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("occ,n_mo", [(129, 150), (200, 260), (300, 340)])
+def test_base_blocks_larger_than_128(ctx, occ, n_mo):
+    """n_occ > 128: the base block is inverted blockwise (Schur complement on the DMMA GEMM around the
+    register-resident 128-kernels); rank-update and closed-form tiers against the oracle."""
+    rng = np.random.default_rng(occ)
+    q, _ = np.linalg.qr(rng.standard_normal((n_mo, n_mo)))
+    S = q + 0.02 * rng.standard_normal((n_mo, n_mo))
+    bra, Cb, ket, Ck = _random_tables(rng, occ, n_mo - occ, 70, 45, 3, 4)
+    want = orc.state_overlaps_closed_form(S, occ, [tuple(e) for e in bra], Cb, [tuple(e) for e in ket], Ck, 1.0)
+    for tier in ("update", "closed", "auto"):
+        got = ctx.state_overlaps_host(S, occ, bra, Cb, ket, Ck, tier=tier)
+        assert_parity(got, want, rtol=1e-9)
+    # a few pair determinants directly against LAPACK, to pin the oracle's closed form at this size too
+    from pywfo_b200 import _lib
+    with pytest.raises(_lib.WfoError):
+        ctx.state_overlaps_host(S, occ, bra, Cb, ket, Ck, tier="lu")      # brute-force tier stops at 128
+    k, l = tuple(bra[3]), tuple(ket[5])
+    one = orc.state_overlaps_bruteforce(S, occ, [k], np.ones((1, 1)), [l], np.ones((1, 1)), 1.0)
+    got1 = ctx.state_overlaps_host(S, occ, bra[3:4], np.ones((1, 1)), ket[5:6], np.ones((1, 1)), tier="update")
+    assert_parity(got1, one, rtol=1e-9)
