@@ -106,162 +106,169 @@ __device__ __forceinline__ void wpm_update(const double *__restrict__ S, int ld_
 }
 
 // whole factorisation by one warp; returns det to every lane.  W: n x LD scratch (global).
+// One 16-column panel with A active row slots (A = ceil(active rows / 32): the panel code is
+// instantiated for every slot count and the factorisation picks the smallest that covers the rows
+// still active, so the later, shorter panels do not pay for empty slots).  Factors the panel, turns
+// the multipliers into M = L21 L11^-1, writes M and drops the pivot rows from the row map.
+// Returns true when this was the last panel.
+template <int A>
+__device__ __forceinline__ bool wpm_panel(const double *__restrict__ S, int ld_s, const int *__restrict__ rows,
+                                          const int *__restrict__ cols, int n, double *W, int LD, WpmShared *sh, int lane,
+                                          int j, int &act, double &det, bool &zero, unsigned &par) {
+    const unsigned FULL = 0xffffffffu;
+    const int w = min(16, n - j);
+    const bool first = (j == 0);
+    // ---- load the panel: lane/slot <-> active position lane + 32 s
+    int pr[A];
+    bool done[A];
+    int pstep[A];
+    double a[A][16];
+#pragma unroll
+    for (int s = 0; s < A; s++) {
+        const int L = lane + 32 * s;
+        const bool valid = L < act;
+        pr[s] = sh->rowmap[valid ? L : 0];
+        done[s] = !valid;
+        pstep[s] = -1;
+        if (first) {
+            const double *src = S + (size_t)rows[pr[s]] * ld_s;
+#pragma unroll
+            for (int c = 0; c < 16; c++) a[s][c] = (c < w) ? __ldg(src + cols[c]) : 0.0;
+        } else {
+            const double2 *src = reinterpret_cast<const double2 *>(W + (size_t)pr[s] * LD + j);
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const double2 v = src[c];
+                a[s][2 * c] = v.x;
+                a[s][2 * c + 1] = v.y;
+            }
+        }
+    }
+    int ppos[16];
+    // ---- 16 column steps
+#pragma unroll
+    for (int jj = 0; jj < 16; jj++) {
+        ppos[jj] = 0;
+        if (jj < w) {   // uniform
+            unsigned key = 0;
+#pragma unroll
+            for (int s = 0; s < A; s++) {
+                const unsigned k = (hi_abs(a[s][jj]) & 0xffffff00u) | 0x80u | (unsigned)(s << 5) | (unsigned)lane;
+                key = max(key, done[s] ? 0u : k);
+            }
+            const unsigned kmax = __reduce_max_sync(FULL, key);
+            const int wl = kmax & 31, ws = (kmax >> 5) & 3;
+            ppos[jj] = wl + 32 * ws;
+            // the pivot row goes through shared memory (one lane writes, all read it back): a
+            // handful of STS/LDS instead of up to 34 shuffles, which 8 warps per SM saturate
+            double u[16];
+#pragma unroll
+            for (int s = 0; s < A; s++) {
+                if (ws == s && lane == wl) {
+#pragma unroll
+                    for (int c = jj; c < 16; c++) sh->urow[c] = a[s][c];
+#pragma unroll
+                    for (int c = 0; c < jj; c++) sh->L11[jj][c] = a[s][c];
+                    sh->piv[jj] = (unsigned char)pr[s];
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int c = jj; c < 16; c++) u[c] = sh->urow[c];
+            __syncwarp();
+            const double piv = u[jj];
+            det *= piv;
+            zero = zero || (piv == 0.0);
+            const double rcp = fast_rcp(piv);
+#pragma unroll
+            for (int s = 0; s < A; s++) {
+                const bool win = (lane == wl) && (ws == s) && (kmax != 0u);
+                pstep[s] = win ? jj : pstep[s];
+                done[s] = done[s] || win;
+                const double l = done[s] ? 0.0 : a[s][jj] * rcp;
+                a[s][jj] = done[s] ? a[s][jj] : l;
+#pragma unroll
+                for (int c = jj + 1; c < 16; c++) a[s][c] = fma(-l, u[c], a[s][c]);
+            }
+        }
+    }
+    // ---- sign: rank of every pivot among the rows still active when it is extracted
+    {
+        int myp = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) myp = (lane == i) ? ppos[i] : myp;
+        int cnt = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const int pi = __shfl_sync(FULL, myp, i);
+            cnt += (i < lane && pi < myp) ? 1 : 0;
+        }
+        const bool odd = (lane < w) && (((myp - cnt) & 1) != 0);
+        par ^= (unsigned)(__popc(__ballot_sync(FULL, odd)) & 1);
+    }
+    if (j + 16 >= n) return true;
+    __syncwarp();   // L11[][] and piv[] complete
+    // ---- M = L21 L11^-1 (axpy form of x L11 = l); pivot rows are modified too, harmlessly
+#pragma unroll
+    for (int q = 15; q >= 1; q--) {
+#pragma unroll
+        for (int c = 0; c < q; c++) {
+            const double lqc = sh->L11[q][c];
+#pragma unroll
+            for (int s = 0; s < A; s++) a[s][c] = fma(-a[s][q], lqc, a[s][c]);
+        }
+    }
+    // ---- write M of the remaining rows, drop the pivot rows from the row map
+    int newL[A];
+    int below = 0;
+#pragma unroll
+    for (int s = 0; s < A; s++) {
+        const int L = lane + 32 * s;
+        const bool valid = L < act;
+        const bool isp = valid && pstep[s] >= 0;
+        const unsigned bal = __ballot_sync(FULL, isp);
+        newL[s] = L - (below + __popc(bal & ((1u << lane) - 1u)));
+        below += __popc(bal);
+        if (valid && !isp) {
+            double2 *dst = reinterpret_cast<double2 *>(W + (size_t)pr[s] * LD + j);
+#pragma unroll
+            for (int c = 0; c < 8; c++) dst[c] = make_double2(a[s][2 * c], a[s][2 * c + 1]);
+        }
+    }
+    __syncwarp();   // every lane has read its rowmap entries (pr[]) long ago; order the writes below
+#pragma unroll
+    for (int s = 0; s < A; s++) {
+        const int L = lane + 32 * s;
+        if (L < act && pstep[s] < 0) sh->rowmap[newL[s]] = (unsigned char)pr[s];
+    }
+    act -= 16;
+    __syncwarp();   // M (global) and the row map are visible to the whole warp
+    return false;
+}
+
 template <int SLOTS>
 __device__ __forceinline__ double wpm_lu_det(const double *__restrict__ S, int ld_s, const int *__restrict__ rows,
                                              const int *__restrict__ cols, int n, double *W, int LD, WpmShared *sh,
                                              int lane) {
-    const unsigned FULL = 0xffffffffu;
     for (int i = lane; i < n; i += 32) sh->rowmap[i] = (unsigned char)i;
     __syncwarp();
     int act = n;
     double det = 1.0;
     bool zero = false;
     unsigned par = 0;
-#ifdef WFO_WPM_CLOCKS
-    long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long t_prev = clock64();
-#endif
     for (int j = 0; j < n; j += 16) {
-        const int w = min(16, n - j);
         const bool first = (j == 0);
-        // ---- load the panel: lane/slot <-> active position lane + 32 s
-        int pr[SLOTS];
-        bool done[SLOTS];
-        int pstep[SLOTS];
-        double a[SLOTS][16];
-#pragma unroll
-        for (int s = 0; s < SLOTS; s++) {
-            const int L = lane + 32 * s;
-            const bool valid = L < act;
-            pr[s] = sh->rowmap[valid ? L : 0];
-            done[s] = !valid;
-            pstep[s] = -1;
-            if (first) {
-                const double *src = S + (size_t)rows[pr[s]] * ld_s;
-#pragma unroll
-                for (int c = 0; c < 16; c++) a[s][c] = (c < w) ? __ldg(src + cols[c]) : 0.0;
-            } else {
-                const double2 *src = reinterpret_cast<const double2 *>(W + (size_t)pr[s] * LD + j);
-#pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    const double2 v = src[c];
-                    a[s][2 * c] = v.x;
-                    a[s][2 * c + 1] = v.y;
-                }
-            }
-        }
-        WPM_T(0);
-        int ppos[16];
-        // ---- 16 column steps
-#pragma unroll
-        for (int jj = 0; jj < 16; jj++) {
-            ppos[jj] = 0;
-            if (jj < w) {   // uniform
-                unsigned key = 0;
-#pragma unroll
-                for (int s = 0; s < SLOTS; s++) {
-                    const unsigned k = (hi_abs(a[s][jj]) & 0xffffff00u) | 0x80u | (unsigned)(s << 5) | (unsigned)lane;
-                    key = max(key, done[s] ? 0u : k);
-                }
-                const unsigned kmax = __reduce_max_sync(FULL, key);
-                const int wl = kmax & 31, ws = (kmax >> 5) & 3;
-                ppos[jj] = wl + 32 * ws;
-                // the pivot row goes through shared memory (one lane writes, all read it back): a
-                // handful of STS/LDS instead of up to 34 shuffles, which 8 warps per SM saturate
-                double u[16];
-#pragma unroll
-                for (int s = 0; s < SLOTS; s++) {
-                    if (ws == s && lane == wl) {
-#pragma unroll
-                        for (int c = jj; c < 16; c++) sh->urow[c] = a[s][c];
-#pragma unroll
-                        for (int c = 0; c < jj; c++) sh->L11[jj][c] = a[s][c];
-                        sh->piv[jj] = (unsigned char)pr[s];
-                    }
-                }
-                __syncwarp();
-#pragma unroll
-                for (int c = jj; c < 16; c++) u[c] = sh->urow[c];
-                __syncwarp();
-                const double piv = u[jj];
-                det *= piv;
-                zero = zero || (piv == 0.0);
-                const double rcp = fast_rcp(piv);
-#pragma unroll
-                for (int s = 0; s < SLOTS; s++) {
-                    const bool win = (lane == wl) && (ws == s) && (kmax != 0u);
-                    pstep[s] = win ? jj : pstep[s];
-                    done[s] = done[s] || win;
-                    const double l = done[s] ? 0.0 : a[s][jj] * rcp;
-                    a[s][jj] = done[s] ? a[s][jj] : l;
-#pragma unroll
-                    for (int c = jj + 1; c < 16; c++) a[s][c] = fma(-l, u[c], a[s][c]);
-                }
-            }
-        }
-        WPM_T(1);
-        // ---- sign: rank of every pivot among the rows still active when it is extracted
-        {
-            int myp = 0;
-#pragma unroll
-            for (int i = 0; i < 16; i++) myp = (lane == i) ? ppos[i] : myp;
-            int cnt = 0;
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const int pi = __shfl_sync(FULL, myp, i);
-                cnt += (i < lane && pi < myp) ? 1 : 0;
-            }
-            const bool odd = (lane < w) && (((myp - cnt) & 1) != 0);
-            par ^= (unsigned)(__popc(__ballot_sync(FULL, odd)) & 1);
-        }
-        WPM_T(2);
-        if (j + 16 >= n) break;
-        __syncwarp();   // L11[][] and piv[] complete
-        // ---- M = L21 L11^-1 (axpy form of x L11 = l); pivot rows are modified too, harmlessly
-#pragma unroll
-        for (int q = 15; q >= 1; q--) {
-#pragma unroll
-            for (int c = 0; c < q; c++) {
-                const double lqc = sh->L11[q][c];
-#pragma unroll
-                for (int s = 0; s < SLOTS; s++) a[s][c] = fma(-a[s][q], lqc, a[s][c]);
-            }
-        }
-        WPM_T(3);
-        // ---- write M of the remaining rows, drop the pivot rows from the row map
-        int newL[SLOTS];
-        int below = 0;
-#pragma unroll
-        for (int s = 0; s < SLOTS; s++) {
-            const int L = lane + 32 * s;
-            const bool valid = L < act;
-            const bool isp = valid && pstep[s] >= 0;
-            const unsigned bal = __ballot_sync(FULL, isp);
-            newL[s] = L - (below + __popc(bal & ((1u << lane) - 1u)));
-            below += __popc(bal);
-            if (valid && !isp) {
-                double2 *dst = reinterpret_cast<double2 *>(W + (size_t)pr[s] * LD + j);
-#pragma unroll
-                for (int c = 0; c < 8; c++) dst[c] = make_double2(a[s][2 * c], a[s][2 * c + 1]);
-            }
-        }
-        __syncwarp();   // every lane has read its rowmap entries (pr[]) long ago; order the writes below
-#pragma unroll
-        for (int s = 0; s < SLOTS; s++) {
-            const int L = lane + 32 * s;
-            if (L < act && pstep[s] < 0) sh->rowmap[newL[s]] = (unsigned char)pr[s];
-        }
-        act -= 16;
-        __syncwarp();   // M (global) and the row map are visible to the whole warp
-        WPM_T(4);
+        const int need = (act + 31) >> 5;   // row slots this panel needs
+        bool last;
+        if (SLOTS >= 4 && need >= 4) last = wpm_panel<(SLOTS >= 4 ? 4 : 1)>(S, ld_s, rows, cols, n, W, LD, sh, lane, j, act, det, zero, par);
+        else if (SLOTS >= 3 && need == 3) last = wpm_panel<(SLOTS >= 3 ? 3 : 1)>(S, ld_s, rows, cols, n, W, LD, sh, lane, j, act, det, zero, par);
+        else if (SLOTS >= 2 && need == 2) last = wpm_panel<(SLOTS >= 2 ? 2 : 1)>(S, ld_s, rows, cols, n, W, LD, sh, lane, j, act, det, zero, par);
+        else last = wpm_panel<1>(S, ld_s, rows, cols, n, W, LD, sh, lane, j, act, det, zero, par);
+        if (last) break;
         if (first) wpm_update<true>(S, ld_s, rows, cols, W, LD, sh, n, j, act, lane);
         else wpm_update<false>(S, ld_s, rows, cols, W, LD, sh, n, j, act, lane);
         __syncwarp();
-        WPM_T(5);
     }
-#ifdef WFO_WPM_CLOCKS
-    if (lane == 0 && blockIdx.x == 0 && (threadIdx.x >> 5) == 1) for (int i = 0; i < 8; i++) g_wpm_clk[i] += t_acc[i];
-#endif
     return zero ? 0.0 : (par ? -det : det);
 }
 
