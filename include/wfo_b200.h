@@ -150,6 +150,13 @@ int wfo_overlaps_ci_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_
                          const double *c_inv, int ao_side, int n_mo, int n_occ, const double *bra_ci, int n_bra,
                          const double *ket_ci, int n_ket, double ci_thresh, int semantics, int tier,
                          int rank, int world, double *out, int32_t *info);
+/* The same with every buffer on the device (orbitals and CI vectors that already live in HBM).  Runs on
+ * `stream` and a side stream of the context, synchronises `stream` once (table sizes) and returns with the
+ * rest queued; `out` (n_bra x n_ket, device) is valid after the stream has drained. */
+int wfo_overlaps_ci_dev(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos, const double *c_inv,
+                        int ao_side, int n_mo, int n_occ, const double *bra_ci, int n_bra,
+                        const double *ket_ci, int n_ket, double ci_thresh, int semantics, int tier,
+                        int rank, int world, double *out, int32_t *info, void *stream);
 /* Trajectory driver: n_cycles geometries (mos: n_cycles x n_mo x n_mo, ci: n_cycles x n_states x n_occ x
  * n_virt, host), the state-overlap matrices of n_pairs (bra cycle, ket cycle) index pairs -> out
  * (n_pairs x n_states x n_states).  Replaces a loop of pywfo.main.overlaps_cache / overlaps calls over

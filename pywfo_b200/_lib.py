@@ -50,6 +50,8 @@ SIGNATURES = {
     "wfo_inverse_host": (C.c_int, [c_vp, c_vp, C.c_int, c_vp]),
     "wfo_overlaps_ci_host": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, c_vp, C.c_int,
                                        C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
+    "wfo_overlaps_ci_dev": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, c_vp, C.c_int,
+                                      C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
     "wfo_trajectory_ci_host": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
                                          C.c_int, c_vp, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
     "wfo_last_tier": (C.c_int, [c_vp]),
@@ -287,6 +289,24 @@ class Context:
     def exc_lists_dev(self, exc, n_occ, lists, stream=0):
         self._dev(exc, lists)
         check(self.lib.wfo_exc_lists_dev(self.handle, exc.data_ptr(), exc.shape[0], n_occ, lists.data_ptr(), stream))
+
+    def overlaps_ci_dev(self, bra_mos, ket_mos, n_occ, bra_ci, ket_ci, out, ci_thresh, c_inv=None, ao_side=AO_KET,
+                        semantics=0, tier="auto", rank=0, world=1, stream=0):
+        """Whole path from raw inputs that already live on the device (contiguous CUDA tensors)."""
+        self._dev(bra_mos, ket_mos, bra_ci, ket_ci, out)
+        if c_inv is not None:
+            self._dev(c_inv)
+        info = np.zeros(4, dtype=np.int32)
+        rc = self.lib.wfo_overlaps_ci_dev(self.handle, bra_mos.data_ptr(), ket_mos.data_ptr(),
+                                          c_inv.data_ptr() if c_inv is not None else None,
+                                          AO_GIVEN if c_inv is not None else int(ao_side), bra_mos.shape[0], int(n_occ),
+                                          bra_ci.data_ptr(), bra_ci.shape[0], ket_ci.data_ptr(), ket_ci.shape[0],
+                                          float(ci_thresh), int(semantics), TIERS[tier], int(rank), int(world),
+                                          out.data_ptr(), _hptr(info), stream)
+        if rc == 4:
+            raise ValueError("not enough values to unpack (expected 2, got 0)")   # pywfo/main.py:186
+        check(rc)
+        return info
 
     def state_overlaps_dev(self, s_mo, n_occ, bra_exc, Cb, ket_exc, Ck, out, sigma=1.0, tier="auto",
                            k_begin=0, k_end=None, stream=0):

@@ -1386,6 +1386,41 @@ int wfo_overlaps_ci_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_
     return WFO_OK;
 }
 
+/* The same from DEVICE buffers (bra_mos, ket_mos, c_inv or NULL, bra_ci, ket_ci, out all on the device):
+ * for callers whose orbitals and CI vectors already live in HBM.  Runs on `stream` plus the context's side
+ * stream; synchronises `stream` once (the number of surviving excitations sizes the second phase) and
+ * returns with the remaining work queued.  *zero_out is set when no excitation survives (out is zeroed). */
+int wfo_overlaps_ci_dev(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos, const double *c_inv, int ao_side,
+                        int n_mo, int n_occ, const double *bra_ci, int n_bra, const double *ket_ci, int n_ket,
+                        double ci_thresh, int semantics, int tier, int rank, int world, double *out, int32_t *info,
+                        void *stream) {
+    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL");
+    if (!bra_mos || !ket_mos || !bra_ci || !ket_ci || !out) return set_err(WFO_ERR_ARG, "overlaps_ci_dev: NULL pointer");
+    WFO_TRY(check_ci_args("overlaps_ci_dev", ao_side, n_mo, n_occ, n_bra, n_ket, semantics, rank, world));
+    if (ao_side == WFO_AO_GIVEN && !c_inv) return set_err(WFO_ERR_ARG, "overlaps_ci_dev: c_inv is NULL");
+    WFO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = n_occ, v = n_mo - n_occ, count = n * v;
+    const size_t nsq = (size_t)n_mo * n_mo, nout = (size_t)n_bra * n_ket;
+    if (info) { info[0] = info[1] = 0; info[2] = 0; info[3] = -1; }
+    if (count == 0) {
+        WFO_CUDA(cudaMemsetAsync(out, 0, nout * sizeof(double), st));
+        return WFO_OK;
+    }
+    CiWork w;
+    Sizer sz;
+    carve_ciwork(sz, w, nsq, count, n_bra, n_ket);
+    WFO_TRY(ensure_resident(ctx, sz.off));
+    Arena ar{ctx->resident, ctx->resident_bytes, 0};
+    carve_ciwork(ar, w, nsq, count, n_bra, n_ket);
+    bool zero = false;
+    WFO_TRY(overlaps_ci_core(ctx, w, bra_mos, ket_mos, ao_side == WFO_AO_GIVEN ? c_inv : nullptr, ao_side, n_mo, n_occ,
+                             bra_ci, n_bra, ket_ci, n_ket, ci_thresh, semantics, tier, rank, world, true, info, &zero, st));
+    if (zero) WFO_CUDA(cudaMemsetAsync(out, 0, nout * sizeof(double), st));
+    else WFO_CUDA(cudaMemcpyAsync(out, w.out, nout * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return WFO_OK;
+}
+
 /* Trajectory driver: n_cycles geometries, the state overlaps of n_pairs (bra cycle, ket
  * cycle) pairs.  Every cycle's MO matrix and CI tensor is uploaded ONCE and stays resident, the inverse
  * behind S_AO is formed once per cycle that needs it; per pair only S_AO, S_MO, the tables and the fused

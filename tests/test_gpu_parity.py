@@ -559,3 +559,21 @@ def test_base_blocks_larger_than_128(ctx, occ, n_mo):
     one = orc.state_overlaps_bruteforce(S, occ, [k], np.ones((1, 1)), [l], np.ones((1, 1)), 1.0)
     got1 = ctx.state_overlaps_host(S, occ, bra[3:4], np.ones((1, 1)), ket[5:6], np.ones((1, 1)), tier="update")
     assert_parity(got1, one, rtol=1e-9)
+
+
+def test_raw_ci_entry_point_from_device_buffers(ctx):
+    """wfo_overlaps_ci_dev: orbitals and CI tensors already in HBM (torch tensors as plain memory)."""
+    import torch
+    for name, key, sem in (("r_n17", "ref_overlaps_cache", 0), ("r_odd", "ref_overlaps_cache", 0), ("r_n17", "ref_overlaps", 1)):
+        g = load_golden(name)
+        occ, thr = int(g["occ"]), float(g["ci_thresh"])
+        nmin = min(g["bra_ci"].shape[0], g["ket_ci"].shape[0]) if sem else None
+        f64 = dict(dtype=torch.float64, device="cuda")
+        d = [torch.tensor(np.ascontiguousarray(x), **f64) for x in (g["bra_mos"], g["ket_mos"], g["bra_ci"][:nmin], g["ket_ci"][:nmin])]
+        out = torch.full((d[2].shape[0], d[3].shape[0]), float("nan"), **f64)
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            info = ctx.overlaps_ci_dev(d[0], d[1], occ, d[2], d[3], out, thr, semantics=sem, stream=s.cuda_stream)
+        s.synchronize()
+        assert info[0] > 0 and info[1] > 0
+        assert_parity(out.cpu().numpy(), g[key])
