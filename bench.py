@@ -387,6 +387,32 @@ def run_ours(args, w):
         except Exception as exc:   # e.g. ground-state entries in the tables
             kernels["t2_closed_form"] = {"error": str(exc)}
 
+    # ---- the whole path from the RAW inputs resident in HBM (inverse behind S_AO, thresholding, S_MO,
+    #      every pair, reduction): what the e2e leg does minus the PCIe copies
+    try:
+        d_bci, d_kci = torch.tensor(bci, **f64), torch.tensor(kci, **f64)
+        raw_out = torch.empty_like(d_out)
+        sem_i = 0 if sigma > 0 else 1
+        ts = []
+        for i in range(5):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ctx.overlaps_ci_dev(d_bra, d_ket, n, d_bci, d_kci, raw_out, thr, semantics=sem_i, tier=tier,
+                                rank=rank, world=world, stream=stream)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                ts.append(e0.elapsed_time(e1))
+        kernels["raw_inputs_on_device"] = {
+            "ms_per_matrix": float(np.mean(ts)),
+            "max_rel_diff_vs_device_leg": float(np.abs(raw_out.cpu().numpy() - (result_first if world == 1 else raw_out.cpu().numpy())).max()
+                                                / max(np.abs(result_first).max(), 1e-300)),
+            "note": "wfo_overlaps_ci_dev: device inverse + device thresholding + S_MO + pairs + reduction from MO "
+                    "matrices and raw CI tensors in HBM (this rank's shard; no all-reduce)"}
+    except Exception as exc:
+        kernels["raw_inputs_on_device"] = {"error": str(exc)}
+
     cpu = None
     if world == 1 and args.cpu_budget > 0:
         v, dt, sample, _ = cpu_baseline_run(w, budget_s=args.cpu_budget)
