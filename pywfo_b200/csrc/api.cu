@@ -86,12 +86,12 @@ static int gemm(wfo_ctx *ctx, bool ta, bool tb, int m, int n, int k, double alph
                      !((batch_a | batch_b) & 1) && (nz == 1 || batch > 0 || !(kslab & 1));
 #define GEMM_LAUNCH2(TA_, TB_, GM_, GN_, VEC_)                                                                    \
     do {                                                                                                          \
-        static bool attr_done_ = false;                                                                           \
-        if (!attr_done_) {                                                                                        \
+        static bool attr_done_[64];   /* per device: function attributes belong to the device's context */      \
+        if (!attr_done_[ctx->device & 63]) {                                                                      \
             WFO_CUDA(cudaFuncSetAttribute(gemm_f64_kernel<TA_, TB_, GM_, GN_, VEC_>,                              \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize,                            \
                                           (int)gemm_smem_bytes<GM_, GN_>()));                                     \
-            attr_done_ = true;                                                                                    \
+            attr_done_[ctx->device & 63] = true;                                                                  \
         }                                                                                                         \
         gemm_f64_kernel<TA_, TB_, GM_, GN_, VEC_><<<grid, block, gemm_smem_bytes<GM_, GN_>(), st>>>(              \
             m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, kslab, slab_stride, batch_a, batch_b);                  \
@@ -324,8 +324,9 @@ static void t1_split(int n_ket, int *nt, int *nd, int *rem) {
 }
 
 // the rank-update kernel runs one persistent CTA per SM; opt in to its dynamic shared memory once
-static int t1_prepare(int n_ket) {
-    static bool done[1000];
+static int t1_prepare(const wfo_ctx *ctx, int n_ket) {
+    static bool done_all[64][1000];   // per device
+    bool *done = done_all[ctx->device & 63];
     int nt, nd, rem;
     t1_split(n_ket, &nt, &nd, &rem);
     const int key = nt * 100 + nd * 10 + rem;
@@ -431,7 +432,7 @@ static int make_part(wfo_ctx *ctx, int ksh, int kk, int n_ket, bool may_t0, bool
     memset(&q.t1, 0, sizeof(q.t1));
     if (want_t1) {
         // T1: iterations (bra tile, ket tile) in equal contiguous ranges over the resident CTAs
-        WFO_TRY(t1_prepare(n_ket));
+        WFO_TRY(t1_prepare(ctx, n_ket));
         const int slots = ctx->sm_count;
         const int ktiles = cdiv(ksh + 1, T1_KTILE), n_ltiles = cdiv(kk, T1_LT);
         const long long I = (long long)ktiles * n_ltiles;
