@@ -1186,15 +1186,21 @@ struct DevTables {
 // build one side's tables.  ci_dev: (n_states, n, v) on the device.  flags/offs/exc_buf are
 // caller-provided device buffers of n*v ints / n*v ints / 2*n*v ints; totals: 1 int + n_states ints.
 static int build_tables_dev(wfo_ctx *ctx, const double *ci_dev, int n_states, int n, int v, double thr, int strict,
-                            int order, int *flags, int *offs, int *totals, cudaStream_t st) {
+                            int order, int *flags, int *offs, int *totals, cudaStream_t st, int pos0 = 0, int cnt = -1,
+                            long long stride = -1) {
     const int count = n * v;
+    if (cnt < 0) { cnt = count; stride = count; }
     if (count <= 0) return WFO_OK;
-    union_flags_kernel<<<cdiv(count, 256), 256, 0, st>>>(ci_dev, n_states, n, v, thr, strict, order, flags);
+    if (cnt > 0) {
+        union_flags_kernel<<<cdiv(cnt, 256), 256, 0, st>>>(ci_dev, n_states, n, v, thr, strict, order, flags, pos0, cnt, stride);
+        WFO_LAUNCH_CHECK(ctx);
+    }
+    scan_flags_kernel<<<1, 1024, 0, st>>>(flags, cnt, offs, totals);
     WFO_LAUNCH_CHECK(ctx);
-    scan_flags_kernel<<<1, 1024, 0, st>>>(flags, count, offs, totals);
-    WFO_LAUNCH_CHECK(ctx);
-    state_counts_kernel<<<n_states, 256, 0, st>>>(ci_dev, n, v, thr, strict, totals + 1);
-    WFO_LAUNCH_CHECK(ctx);
+    if (cnt == count) {   // per-state totals only make sense (and are only needed) for the whole tensor
+        state_counts_kernel<<<n_states, 256, 0, st>>>(ci_dev, n, v, thr, strict, totals + 1);
+        WFO_LAUNCH_CHECK(ctx);
+    }
     return WFO_OK;
 }
 
@@ -1246,8 +1252,12 @@ static int ensure_resident(wfo_ctx *ctx, size_t bytes) {
 static int overlaps_ci_core(wfo_ctx *ctx, const CiWork &w, const double *d_bra, const double *d_ket,
                             const double *d_inv, int ao_side, int n_mo, int n_occ, const double *d_bci, int n_bra,
                             const double *d_kci, int n_ket, double ci_thresh, int semantics, int tier, int rank,
-                            int world, bool side_after_main, int32_t *info, bool *zero, cudaStream_t st) {
+                            int world, bool side_after_main, int32_t *info, bool *zero, cudaStream_t st,
+                            int bra_pos0 = 0, int bra_cnt = -1, long long bra_stride = -1) {
+    // bra window: d_bci points at position bra_pos0 of state 0 and covers bra_cnt positions (a rank's
+    // slice of the (from, to) space, see wfo_overlaps_ci_host); default = the whole tensor
     const int n = n_occ, v = n_mo - n_occ, count = n * v;
+    if (bra_cnt < 0) { bra_cnt = count; bra_stride = count; }
     const int strict = semantics == 1;
     const double sigma = semantics == 1 ? -1.0 : 1.0;
     *zero = false;
@@ -1256,7 +1266,8 @@ static int overlaps_ci_core(wfo_ctx *ctx, const CiWork &w, const double *d_bra, 
         WFO_CUDA(cudaEventRecord(ctx->ev_fork, st));
         WFO_CUDA(cudaStreamWaitEvent(s2, ctx->ev_fork, 0));
     }
-    WFO_TRY(build_tables_dev(ctx, d_bci, n_bra, n, v, ci_thresh, strict, 0, w.fl_b, w.of_b, w.tot_b, st));
+    WFO_TRY(build_tables_dev(ctx, d_bci, n_bra, n, v, ci_thresh, strict, 0, w.fl_b, w.of_b, w.tot_b, st, bra_pos0, bra_cnt,
+                             bra_stride));
     WFO_TRY(build_tables_dev(ctx, d_kci, n_ket, n, v, ci_thresh, strict, 1, w.fl_k, w.of_k, w.tot_k, st));
     if (!d_inv) {
         WFO_TRY(wfo_inverse_dev(ctx, ao_side == WFO_AO_BRA ? d_bra : d_ket, n_mo, w.inv, w.work, s2));
@@ -1273,7 +1284,7 @@ static int overlaps_ci_core(wfo_ctx *ctx, const CiWork &w, const double *d_bra, 
     WFO_CUDA(cudaStreamSynchronize(st));
     const int kb = hb[0], kk = hk[0];
     if (info) { info[0] = kb; info[1] = kk; info[2] = 0; info[3] = -1; }
-    if (semantics == 1) {   // pywfo/main.py:186: a state without excitations cannot be unpacked
+    if (semantics == 1 && bra_cnt == count) {   // pywfo/main.py:186: a state without excitations cannot be unpacked
         bool empty = false;
         for (int i = 0; i < n_bra; i++) empty = empty || hb[1 + i] == 0;
         for (int i = 0; i < n_ket; i++) empty = empty || hk[1 + i] == 0;
@@ -1309,15 +1320,15 @@ static int overlaps_ci_core(wfo_ctx *ctx, const CiWork &w, const double *d_bra, 
     WFO_TRY(ensure_scratch(ctx, total));   // nothing of this call lives in the arena yet
     Arena ar2{ctx->scratch, ctx->scratch_bytes, 0};
     double *d_cb = ar2.take<double>((size_t)n_bra * kb), *d_ck = ar2.take<double>((size_t)n_ket * kk);
-    emit_exc_kernel<<<cdiv(count, 256), 256, 0, st>>>(w.fl_b, w.of_b, n, v, 0, w.exc_b);
+    emit_exc_kernel<<<cdiv(bra_cnt, 256), 256, 0, st>>>(w.fl_b, w.of_b, n, v, 0, w.exc_b, bra_pos0, bra_cnt);
     WFO_LAUNCH_CHECK(ctx);
-    emit_exc_kernel<<<cdiv(count, 256), 256, 0, st>>>(w.fl_k, w.of_k, n, v, 1, w.exc_k);
+    emit_exc_kernel<<<cdiv(count, 256), 256, 0, st>>>(w.fl_k, w.of_k, n, v, 1, w.exc_k, 0, count);
     WFO_LAUNCH_CHECK(ctx);
-    emit_coeff_kernel<<<dim3(cdiv(count, 256), n_bra), 256, 0, st>>>(d_bci, w.fl_b, w.of_b, n, v, ci_thresh, strict, 0,
-                                                                    semantics == 1, kb, d_cb);
+    emit_coeff_kernel<<<dim3(cdiv(bra_cnt, 256), n_bra), 256, 0, st>>>(d_bci, w.fl_b, w.of_b, n, v, ci_thresh, strict, 0,
+                                                                      semantics == 1, kb, d_cb, bra_pos0, bra_cnt, bra_stride);
     WFO_LAUNCH_CHECK(ctx);
     emit_coeff_kernel<<<dim3(cdiv(count, 256), n_ket), 256, 0, st>>>(d_kci, w.fl_k, w.of_k, n, v, ci_thresh, strict, 1,
-                                                                    semantics == 1, kk, d_ck);
+                                                                    semantics == 1, kk, d_ck, 0, count, (long long)count);
     WFO_LAUNCH_CHECK(ctx);
     char *before = ctx->scratch;
     WFO_TRY(state_overlaps_impl(ctx, ar2.off, w.smo, n_mo, n, w.exc_b, kb, d_cb, n_bra, w.exc_k, kk, d_ck, n_ket, sigma,
@@ -1369,15 +1380,33 @@ int wfo_overlaps_ci_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_
     double *d_bci = ar.take<double>((size_t)n_bra * count), *d_kci = ar.take<double>((size_t)n_ket * count);
     carve_ciwork(ar, w, nsq, count, n_bra, n_ket);
     // main stream: raw CI tensors up (then the tables); side stream, concurrently: MO matrices up (then the
-    // inverse behind S_AO, S_AO, S_MO)
-    WFO_CUDA(cudaMemcpyAsync(d_bci, bra_ci, (size_t)n_bra * count * 8, cudaMemcpyHostToDevice, st));
+    // inverse behind S_AO, S_AO, S_MO).  With several ranks and the singlet semantics each rank uploads and
+    // thresholds only ITS slice of the bra (from, to) space -- any partition of the bra excitations gives
+    // partial matrices that add up -- so the bra-side copies and table work shrink with the rank count.
+    const bool slice = world > 1 && semantics == 0;
+    int p_lo = 0, p_len = count;
+    if (slice) {
+        const int base = count / world, rem = count % world;
+        p_lo = rank * base + (rank < rem ? rank : rem);
+        p_len = base + (rank < rem ? 1 : 0);
+        if (p_len > 0)
+            WFO_CUDA(cudaMemcpy2DAsync(d_bci, (size_t)p_len * 8, bra_ci + p_lo, (size_t)count * 8, (size_t)p_len * 8,
+                                       n_bra, cudaMemcpyHostToDevice, st));
+    } else {
+        WFO_CUDA(cudaMemcpyAsync(d_bci, bra_ci, (size_t)n_bra * count * 8, cudaMemcpyHostToDevice, st));
+    }
     WFO_CUDA(cudaMemcpyAsync(d_kci, ket_ci, (size_t)n_ket * count * 8, cudaMemcpyHostToDevice, st));
     WFO_CUDA(cudaMemcpyAsync(d_bra, bra_mos, nsq * 8, cudaMemcpyHostToDevice, s2));
     WFO_CUDA(cudaMemcpyAsync(d_ket, ket_mos, nsq * 8, cudaMemcpyHostToDevice, s2));
     if (ao_side == WFO_AO_GIVEN) WFO_CUDA(cudaMemcpyAsync(d_inv, c_inv, nsq * 8, cudaMemcpyHostToDevice, s2));
     bool zero = false;
-    WFO_TRY(overlaps_ci_core(ctx, w, d_bra, d_ket, ao_side == WFO_AO_GIVEN ? d_inv : nullptr, ao_side, n_mo, n_occ, d_bci,
-                             n_bra, d_kci, n_ket, ci_thresh, semantics, tier, rank, world, false, info, &zero, st));
+    if (slice)
+        WFO_TRY(overlaps_ci_core(ctx, w, d_bra, d_ket, ao_side == WFO_AO_GIVEN ? d_inv : nullptr, ao_side, n_mo, n_occ, d_bci,
+                                 n_bra, d_kci, n_ket, ci_thresh, semantics, tier, 0, 1, false, info, &zero, st, p_lo, p_len,
+                                 (long long)p_len));
+    else
+        WFO_TRY(overlaps_ci_core(ctx, w, d_bra, d_ket, ao_side == WFO_AO_GIVEN ? d_inv : nullptr, ao_side, n_mo, n_occ, d_bci,
+                                 n_bra, d_kci, n_ket, ci_thresh, semantics, tier, rank, world, false, info, &zero, st));
     if (zero) {
         memset(out, 0, (size_t)n_bra * n_ket * sizeof(double));
         return WFO_OK;

@@ -38,16 +38,20 @@ __device__ __forceinline__ bool ci_keep(double c, double thr, int strict) {
     return strict ? (a > thr) : (a >= thr);
 }
 
+// A WINDOW of the (from, to) space can be processed on its own (one rank's slice of the bra side):
+// positions [pos0, pos0 + cnt) in traversal order 0, `ci` then points at the window's first element
+// of state 0 and `stride` is the distance between states (cnt for a compact slice, n*v in place).
+// The whole tensor is pos0 = 0, cnt = n*v, stride = n*v.
 __global__ void union_flags_kernel(const double *__restrict__ ci, int n_states, int n, int v, double thr,
-                                   int strict, int order, int *__restrict__ flags) {
-    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >= n * v) return;
+                                   int strict, int order, int *__restrict__ flags, int pos0, int cnt, long long stride) {
+    const int local = blockIdx.x * blockDim.x + threadIdx.x;
+    if (local >= cnt) return;
     int f, t;
-    pos_to_ft(pos, n, v, order, f, t);
-    const size_t off = (size_t)f * v + t, stride = (size_t)n * v;
+    pos_to_ft(pos0 + local, n, v, order, f, t);
+    const long long off = (long long)f * v + t - pos0;
     int any = 0;
     for (int s = 0; s < n_states; s++) any |= ci_keep(ci[s * stride + off], thr, strict) ? 1 : 0;
-    flags[pos] = any;
+    flags[local] = any;
 }
 
 // kept[s] = number of excitations state s keeps (main.overlaps raises on 0, main.py:186)
@@ -93,28 +97,29 @@ scan_flags_kernel(const int *__restrict__ flags, int count, int *__restrict__ of
 }
 
 __global__ void emit_exc_kernel(const int *__restrict__ flags, const int *__restrict__ offs, int n, int v,
-                                int order, int32_t *__restrict__ exc) {
-    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >= n * v || !flags[pos]) return;
+                                int order, int32_t *__restrict__ exc, int pos0, int cnt) {
+    const int local = blockIdx.x * blockDim.x + threadIdx.x;
+    if (local >= cnt || !flags[local]) return;
     int f, t;
-    pos_to_ft(pos, n, v, order, f, t);
-    exc[2 * offs[pos]] = f;
-    exc[2 * offs[pos] + 1] = t;
+    pos_to_ft(pos0 + local, n, v, order, f, t);
+    exc[2 * offs[local]] = f;
+    exc[2 * offs[local] + 1] = t;
 }
 
 // coeff is n_states x K row-major.  grid.y = state.
 __global__ void emit_coeff_kernel(const double *__restrict__ ci, const int *__restrict__ flags,
                                   const int *__restrict__ offs, int n, int v, double thr, int strict,
-                                  int order, int minus_sign, int K, double *__restrict__ coeff) {
-    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+                                  int order, int minus_sign, int K, double *__restrict__ coeff, int pos0, int cnt,
+                                  long long stride) {
+    const int local = blockIdx.x * blockDim.x + threadIdx.x;
     const int s = blockIdx.y;
-    if (pos >= n * v || !flags[pos]) return;
+    if (local >= cnt || !flags[local]) return;
     int f, t;
-    pos_to_ft(pos, n, v, order, f, t);
-    const double c = ci[(size_t)s * n * v + (size_t)f * v + t];
+    pos_to_ft(pos0 + local, n, v, order, f, t);
+    const double c = ci[s * stride + (long long)f * v + t - pos0];
     double val = ci_keep(c, thr, strict) ? c : 0.0;
     if (minus_sign && (n & 1) && ((n - f + 1) & 1)) val = -val;   // ((-1)^(n-f+1))^n
-    coeff[(size_t)s * K + offs[pos]] = val;
+    coeff[(size_t)s * K + offs[local]] = val;
 }
 
 }  // namespace wfo

@@ -260,6 +260,17 @@ def test_raw_ci_entry_point_shards_add_up(ctx):
         parts = sum(ctx.overlaps_ci_host(g["bra_mos"], g["ket_mos"], inv, occ, bci, kci, float(g["ci_thresh"]), sem,
                                          rank=r, world=3)[0] for r in range(3))
         np.testing.assert_allclose(parts, full, rtol=1e-12, atol=1e-14 * np.abs(full).max())
+    # sparse CI vectors, more ranks than some slices have survivors: each rank uploads and thresholds only
+    # its slice of the bra (from, to) space (singlet semantics)
+    g = load_golden("r_sparse")
+    occ, thr = int(g["occ"]), float(g["ci_thresh"])
+    inv = np.linalg.inv(g["ket_mos"])
+    full, _ = ctx.overlaps_ci_host(g["bra_mos"], g["ket_mos"], inv, occ, g["bra_ci"], g["ket_ci"], thr, 0)
+    assert_parity(full, g["ref_overlaps_cache"])
+    for world in (2, 7, 40):
+        parts = sum(ctx.overlaps_ci_host(g["bra_mos"], g["ket_mos"], inv, occ, g["bra_ci"], g["ket_ci"], thr, 0,
+                                         rank=r, world=world)[0] for r in range(world))
+        np.testing.assert_allclose(parts, full, rtol=1e-12, atol=1e-14 * np.abs(full).max())
 
 
 def test_singular_base_block_falls_back_to_lu(ctx):
