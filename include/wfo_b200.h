@@ -168,6 +168,14 @@ int wfo_trajectory_ci_host(wfo_ctx *ctx, const double *mos, const double *ci, in
                            int n_occ, int n_states, double ci_thresh, int semantics, int tier,
                            int ao_side, const int32_t *pairs, int n_pairs, int rank, int world,
                            double *out, int32_t *info);
+/* Brute-force tier, 32 < n_occ <= 128: which of the two warp-per-determinant LU kernels runs.
+ * AUTO = left-looking, all on chip (csrc/det_lu_ll.cuh) up to n_occ = 64, right-looking with an
+ * L2-resident scratch (csrc/det_lu_wpm.cuh) above.  Both compute the same partially pivoted LU
+ * (pywfo/main.py:583-584); the switch exists so that tests and benchmarks can run either one. */
+#define WFO_LU_AUTO 0
+#define WFO_LU_LEFT 1
+#define WFO_LU_RIGHT 2
+int wfo_set_lu_variant(wfo_ctx *ctx, int variant);
 /* tier actually used by the last wfo_state_overlaps_* call of this context */
 int wfo_last_tier(const wfo_ctx *ctx);
 /* device time (ms, CUDA events on the launching stream) of the dominant

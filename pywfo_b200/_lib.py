@@ -54,6 +54,7 @@ SIGNATURES = {
                                       C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
     "wfo_trajectory_ci_host": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
                                          C.c_int, c_vp, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
+    "wfo_set_lu_variant": (C.c_int, [c_vp, C.c_int]),
     "wfo_last_tier": (C.c_int, [c_vp]),
     "wfo_set_timing": (C.c_int, [c_vp, C.c_int]),
     "wfo_last_kernel_ms": (C.c_double, [c_vp]),
@@ -324,6 +325,11 @@ class Context:
 
     def last_tier(self) -> int:
         return int(self.lib.wfo_last_tier(self.handle))
+
+    def set_lu_variant(self, variant):
+        """Brute-force kernel for 32 < n_occ <= 128: 0/"auto", 1/"left" (on chip), 2/"right" (L2 scratch)."""
+        v = {"auto": 0, "left": 1, "right": 2}.get(variant, variant)
+        check(self.lib.wfo_set_lu_variant(self.handle, int(v)))
 
     def set_timing(self, on):
         """0 = off, 1 = dominant kernel only, 2 = phase breakdown (``last_phases``)."""

@@ -5,9 +5,8 @@
 #include <vector>
 
 #include "common.cuh"
-#include "det_lu_blocked.cuh"
-#include "det_lu_v1.cuh"
 #include "det_lu_warp.cuh"
+#include "det_lu_ll.cuh"
 #include "det_lu_wpm.cuh"
 #include "gemm_f64.cuh"
 #include "lu_base.cuh"
@@ -161,48 +160,6 @@ static int base_factor(wfo_ctx *ctx, const double *A, int lda, int n, double *Ai
     return WFO_OK;
 }
 
-static size_t t0_smem_bytes(int n) { return (size_t)n * (n | 1) * sizeof(double) + 2 * (size_t)n * sizeof(int); }
-static int t0_threads(int n) { return n > 64 ? 256 : 128; }
-
-#ifndef WFO_T0_WPM_DEFAULT
-#define WFO_T0_WPM_DEFAULT 1
-#endif
-
-static bool use_v1() {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("WFO_T0_V1"); v = (e && e[0] == '1') ? 1 : 0; }
-    return v == 1;
-}
-
-// blocked-kernel configuration by matrix size: (warps per CTA, panel warps = ceil(n/32)).
-// WFO_T0_WARPS overrides the warp count (tuning only).
-static int t0_warps_override() {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("WFO_T0_WARPS"); v = e ? atoi(e) : 0; }
-    return v;
-}
-#define WFO_BLK_DISPATCH(n, CALL)                                                   \
-    do {                                                                            \
-        const int ov_ = t0_warps_override();                                        \
-        if ((n) <= 32) {                                                            \
-            if (ov_ == 1) { CALL(1, 1); } else if (ov_ == 4) { CALL(4, 1); } else { CALL(2, 1); }      \
-        } else if ((n) <= 64) {                                                     \
-            if (ov_ == 2) { CALL(2, 2); } else if (ov_ == 8) { CALL(8, 2); } else { CALL(4, 2); }      \
-        } else if ((n) <= 96) {                                                     \
-            if (ov_ == 4) { CALL(4, 3); } else { CALL(8, 3); }                      \
-        } else {                                                                    \
-            if (ov_ == 4) { CALL(4, 4); } else { CALL(8, 4); }                      \
-        }                                                                           \
-    } while (0)
-
-// keep the LU working matrices in global memory (L2) instead of shared memory?
-static bool t0_global_scratch(int n) {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("WFO_T0_GLOBAL"); v = e ? atoi(e) : 0; }
-    (void)n;
-    return v == 1;
-}
-
 static int ensure_gscratch(wfo_ctx *ctx, size_t bytes) {
     if (bytes <= ctx->gscratch_bytes) return WFO_OK;
     WFO_CUDA(cudaDeviceSynchronize());
@@ -214,25 +171,34 @@ static int ensure_gscratch(wfo_ctx *ctx, size_t bytes) {
     return WFO_OK;
 }
 
-// warp-per-matrix kernels with an L2-resident scratch for 32 < n <= 128 (WFO_T0_WPM=0 selects the
-// shared-memory CTA-per-matrix kernels instead)
-static bool use_wpm_kernels(int n) {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("WFO_T0_WPM"); v = e ? atoi(e) : WFO_T0_WPM_DEFAULT; }
-    return v == 1 && n > 32 && n <= 128;
+// Brute-force tier, 32 < n <= 128: two warp-per-matrix kernels.
+//   left-looking, all on chip (det_lu_ll.cuh): faster up to n = 64 (20 % of the FP64 peak at n = 64 against 15 %),
+//     no DRAM traffic at any n; at n = 100 only five matrices fit an SM and it falls behind;
+//   right-looking with an L2-resident scratch (det_lu_wpm.cuh): eight matrices per SM at any n.
+// wfo_set_lu_variant() pins one of them (tests run both at every size).
+static bool use_ll_kernels(const wfo_ctx *ctx, int n) {
+    if (n <= 32 || n > 128) return false;
+    if (ctx->lu_variant == WFO_LU_LEFT) return true;
+    if (ctx->lu_variant == WFO_LU_RIGHT) return false;
+    return n <= 64;
 }
+#define WFO_LL_DISPATCH(n, CALL)                                             \
+    do {                                                                     \
+        switch (((n) + 7) / 8) {                                             \
+            case 5: CALL(5); break;   case 6: CALL(6); break;                \
+            case 7: CALL(7); break;   case 8: CALL(8); break;                \
+            case 9: CALL(9); break;   case 10: CALL(10); break;              \
+            case 11: CALL(11); break; case 12: CALL(12); break;              \
+            case 13: CALL(13); break; case 14: CALL(14); break;              \
+            case 15: CALL(15); break; default: CALL(16); break;              \
+        }                                                                    \
+    } while (0)
 #define WFO_WPM_DISPATCH(n, CALL)            \
     do {                                     \
         if ((n) <= 64) { CALL(2); }          \
         else if ((n) <= 96) { CALL(3); }     \
         else { CALL(4); }                    \
     } while (0)
-
-static bool use_warp_kernels(int n) {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("WFO_T0_NOWARP"); v = (e && e[0] == '1') ? 0 : 1; }
-    return v == 1 && n <= 32;
-}
 // register-resident segment kernels for n <= 32: (padded columns, lanes per determinant)
 #define WFO_WARP_DISPATCH(n, CALL)             \
     do {                                       \
@@ -261,40 +227,27 @@ static int det_table(wfo_ctx *ctx, const double *S, int ld_s, int n, const int32
     if (n < 1 || n > 128)
         return set_err(WFO_ERR_ARG, "det_table: n_occ=%lld outside the supported range 1..128", n);
     unsigned grid = 1;
-    if (use_v1()) {
-        size_t smem = t0_smem_bytes(n);
-        int threads = t0_threads(n);
-        WFO_TRY(persistent_grid(ctx, det_table_kernel, threads, smem, npairs, &grid));
-        det_table_kernel<<<grid, threads, smem, st>>>(S, ld_s, n, rows, kb, cols, kk, D);
-    } else if (use_wpm_kernels(n)) {
+    if (use_ll_kernels(ctx, n)) {
+#define CALL_DL(NT_)                                                                                           \
+    WFO_TRY(persistent_grid(ctx, det_table_ll_kernel<NT_>, LLWarps<NT_>::W * 32, LLWarps<NT_>::W * LLCfg<NT_>::BYTES, \
+                            (npairs + LLWarps<NT_>::W - 1) / LLWarps<NT_>::W, &grid));                         \
+    det_table_ll_kernel<NT_><<<grid, LLWarps<NT_>::W * 32, LLWarps<NT_>::W * LLCfg<NT_>::BYTES, st>>>(S, ld_s, n, rows, kb, \
+                                                                                                      cols, kk, D)
+        WFO_LL_DISPATCH(n, CALL_DL);
+#undef CALL_DL
+    } else if (n > 32) {
 #define CALL_DP(SL_)                                                                                          \
     WFO_TRY(persistent_grid(ctx, det_table_wpm_kernel<SL_>, WPM_WARPS * 32, 0, (npairs + WPM_WARPS - 1) / WPM_WARPS, &grid)); \
     WFO_TRY(ensure_gscratch(ctx, (size_t)grid * WPM_WARPS * wpm_mat_bytes(n)));                                \
     det_table_wpm_kernel<SL_><<<grid, WPM_WARPS * 32, 0, st>>>(S, ld_s, n, rows, kb, cols, kk, D, ctx->gscratch)
         WFO_WPM_DISPATCH(n, CALL_DP);
 #undef CALL_DP
-    } else if (use_warp_kernels(n)) {
+    } else {
 #define CALL_DW(NC_, SEG_)                                                                                 \
     WFO_TRY(persistent_grid(ctx, det_table_warp_kernel<NC_, SEG_>, 128, 0, (npairs + 3) / 4, &grid));      \
     det_table_warp_kernel<NC_, SEG_><<<grid, 128, 0, st>>>(S, ld_s, n, rows, kb, cols, kk, D)
         WFO_WARP_DISPATCH(n, CALL_DW);
 #undef CALL_DW
-    } else {
-        const bool gl = t0_global_scratch(n);
-        size_t smem = blk_smem_bytes(n, gl);
-#define CALL_DT(W, SL)                                                                                       \
-    if (gl) {                                                                                                \
-        WFO_TRY(persistent_grid(ctx, det_table_blk_kernel<W, SL, true>, W * 32, smem, npairs, &grid));       \
-        WFO_TRY(ensure_gscratch(ctx, (size_t)grid * blk_mat_bytes(n)));                                      \
-        det_table_blk_kernel<W, SL, true><<<grid, W * 32, smem, st>>>(S, ld_s, n, rows, kb, cols, kk, D,     \
-                                                                      ctx->gscratch);                        \
-    } else {                                                                                                 \
-        WFO_TRY(persistent_grid(ctx, det_table_blk_kernel<W, SL, false>, W * 32, smem, npairs, &grid));      \
-        det_table_blk_kernel<W, SL, false><<<grid, W * 32, smem, st>>>(S, ld_s, n, rows, kb, cols, kk, D,    \
-                                                                       nullptr);                             \
-    }
-        WFO_BLK_DISPATCH(n, CALL_DT);
-#undef CALL_DT
     }
     WFO_LAUNCH_CHECK(ctx);
     return WFO_OK;
@@ -408,7 +361,7 @@ static int resolve_tier(const wfo_ctx *ctx, int n, int tier, bool *want_t1, bool
     }
     *want_t1 = (tier == WFO_TIER_AUTO || tier == WFO_TIER_UPDATE);
     *may_t0 = (tier == WFO_TIER_AUTO || tier == WFO_TIER_LU);
-    const bool t0_fits = n <= 128 && t0_smem_bytes(n) <= ctx->smem_optin;
+    const bool t0_fits = n <= 128;
     const bool t1_fits = base_smem_bytes(n) <= ctx->smem_optin;
     if (tier == WFO_TIER_LU && !t0_fits)
         return set_err(WFO_ERR_ARG, "state_overlaps: tier LU supports n_occ <= 128, got %lld", n);
@@ -499,6 +452,7 @@ int wfo_create(int device, wfo_ctx **out) {
     c->sm_count = prop.multiProcessorCount;
     c->smem_optin = prop.sharedMemPerBlockOptin;
     c->last_tier = -1;
+    c->lu_variant = WFO_LU_AUTO;
     WFO_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     WFO_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     WFO_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
@@ -539,6 +493,12 @@ int wfo_destroy(wfo_ctx *ctx) {
 }
 
 long long wfo_launch_count(const wfo_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int wfo_set_lu_variant(wfo_ctx *ctx, int variant) {
+    if (!ctx || variant < WFO_LU_AUTO || variant > WFO_LU_RIGHT) return set_err(WFO_ERR_ARG, "set_lu_variant: bad argument");
+    ctx->lu_variant = variant;
+    return WFO_OK;
+}
+
 int wfo_last_tier(const wfo_ctx *ctx) { return ctx ? ctx->last_tier : -1; }
 int wfo_set_timing(wfo_ctx *ctx, int on) {
     if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL");
@@ -992,14 +952,16 @@ static int state_overlaps_block(wfo_ctx *ctx, size_t arena_off, const double *s_
         WFO_LAUNCH_CHECK(ctx);
         const long long items = (long long)ksh * t0_chunks;
         unsigned grid = 1;
-        if (use_v1()) {
-            size_t smem = t0_smem_bytes(n);
-            int threads = t0_threads(n);
-            WFO_TRY(persistent_grid(ctx, t0_fused_kernel, threads, smem, items, &grid));
-            if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev0, st));
-            t0_fused_kernel<<<grid, threads, smem, st>>>(s_mo, n_mo, n, p.bra_lists, ksh, p.ket_lists, kk, p.ckt,
-                                                         ldg, chunk_len, t0_chunks, p.gpart);
-        } else if (use_wpm_kernels(n)) {
+        if (use_ll_kernels(ctx, n)) {
+#define CALL_FL(NT_)                                                                                              \
+    WFO_TRY(persistent_grid(ctx, t0_fused_ll_kernel<NT_>, LLWarps<NT_>::W * 32, LLWarps<NT_>::W * LLCfg<NT_>::BYTES, \
+                            (items + LLWarps<NT_>::W - 1) / LLWarps<NT_>::W, &grid));                             \
+    if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev0, st));                                                     \
+    t0_fused_ll_kernel<NT_><<<grid, LLWarps<NT_>::W * 32, LLWarps<NT_>::W * LLCfg<NT_>::BYTES, st>>>(             \
+        s_mo, n_mo, n, p.bra_lists, ksh, p.ket_lists, kk, p.ckt, ldg, chunk_len, t0_chunks, p.gpart)
+            WFO_LL_DISPATCH(n, CALL_FL);
+#undef CALL_FL
+        } else if (n > 32) {
 #define CALL_FP(SL_)                                                                                              \
     WFO_TRY(persistent_grid(ctx, t0_fused_wpm_kernel<SL_>, WPM_WARPS * 32, 0, (items + WPM_WARPS - 1) / WPM_WARPS, &grid)); \
     WFO_TRY(ensure_gscratch(ctx, (size_t)grid * WPM_WARPS * wpm_mat_bytes(n)));                                    \
@@ -1008,7 +970,7 @@ static int state_overlaps_block(wfo_ctx *ctx, size_t arena_off, const double *s_
                                                               p.ckt, ldg, chunk_len, t0_chunks, p.gpart, ctx->gscratch)
             WFO_WPM_DISPATCH(n, CALL_FP);
 #undef CALL_FP
-        } else if (use_warp_kernels(n)) {
+        } else {
 #define CALL_FW(NC_, SEG_)                                                                                      \
     WFO_TRY(persistent_grid(ctx, t0_fused_warp_kernel<NC_, SEG_>, 128, 0, (items + 3) / 4, &grid));             \
     if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev0, st));                                                   \
@@ -1016,24 +978,6 @@ static int state_overlaps_block(wfo_ctx *ctx, size_t arena_off, const double *s_
                                                           p.ckt, ldg, chunk_len, t0_chunks, p.gpart)
             WFO_WARP_DISPATCH(n, CALL_FW);
 #undef CALL_FW
-        } else {
-            const bool gl = t0_global_scratch(n);
-            size_t smem = blk_smem_bytes(n, gl);
-#define CALL_FU(W, SL)                                                                                          \
-    if (gl) {                                                                                                   \
-        WFO_TRY(persistent_grid(ctx, t0_fused_blk_kernel<W, SL, true>, W * 32, smem, items, &grid));            \
-        WFO_TRY(ensure_gscratch(ctx, (size_t)grid * blk_mat_bytes(n)));                                         \
-        if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev0, st));                                               \
-        t0_fused_blk_kernel<W, SL, true><<<grid, W * 32, smem, st>>>(s_mo, n_mo, n, p.bra_lists, ksh,           \
-            p.ket_lists, kk, p.ckt, ldg, chunk_len, t0_chunks, p.gpart, ctx->gscratch);                         \
-    } else {                                                                                                    \
-        WFO_TRY(persistent_grid(ctx, t0_fused_blk_kernel<W, SL, false>, W * 32, smem, items, &grid));           \
-        if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev0, st));                                               \
-        t0_fused_blk_kernel<W, SL, false><<<grid, W * 32, smem, st>>>(s_mo, n_mo, n, p.bra_lists, ksh,          \
-            p.ket_lists, kk, p.ckt, ldg, chunk_len, t0_chunks, p.gpart, nullptr);                               \
-    }
-            WFO_BLK_DISPATCH(n, CALL_FU);
-#undef CALL_FU
         }
         WFO_LAUNCH_CHECK(ctx);
         if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev1, st));
@@ -1520,10 +1464,10 @@ int wfo_debug_wpm_clocks(long long *out8, int reset) {
 }
 #endif
 
-#ifdef WFO_LUB_CLOCKS
-int wfo_debug_lub_clocks(long long *out16, int reset) {
-    if (out16) cudaMemcpyFromSymbol(out16, g_lub_clk, sizeof(long long) * 16);
-    if (reset) { long long z[16] = {0}; cudaMemcpyToSymbol(g_lub_clk, z, sizeof(z)); }
+#ifdef WFO_LL_CLOCKS
+extern "C" int wfo_debug_ll_clocks(long long *out8, int reset) {
+    if (out8) cudaMemcpyFromSymbol(out8, g_ll_clk, sizeof(long long) * 8);
+    if (reset) { long long z[8] = {0}; cudaMemcpyToSymbol(g_ll_clk, z, sizeof(z)); }
     return 0;
 }
 #endif
@@ -1531,14 +1475,6 @@ int wfo_debug_lub_clocks(long long *out16, int reset) {
 #ifdef WFO_T1_CLOCKS
 int wfo_debug_t1_clocks(long long *out, int n_ctas) {
     return (int)cudaMemcpyFromSymbol(out, g_t1_clk, sizeof(long long) * 4 * (size_t)n_ctas);
-}
-#endif
-
-#ifdef WFO_PHASE_TIMING
-int wfo_debug_phases(long long *out16, int reset) {
-    if (out16) cudaMemcpyFromSymbol(out16, g_phase, sizeof(long long) * 16);
-    if (reset) { long long z[16] = {0}; cudaMemcpyToSymbol(g_phase, z, sizeof(z)); }
-    return 0;
 }
 #endif
 

@@ -91,6 +91,7 @@ struct wfo_ctx {
     size_t resident_bytes;
     long long launches;
     int last_tier;
+    int lu_variant;        // WFO_LU_*: which brute-force kernel serves 32 < n <= 128
     int timing;
     float last_ms;
     cudaEvent_t ev0, ev1;

@@ -77,6 +77,57 @@ def test_det_table_vs_lapack(ctx, n):
     assert np.array_equal(np.sign(got), np.sign(want))
 
 
+@pytest.mark.parametrize("variant", ["left", "right"])
+@pytest.mark.parametrize("n", [33, 39, 40, 41, 47, 48, 56, 57, 63, 64, 65, 72, 80, 88, 96, 97, 100, 104, 105, 112, 120, 127, 128])
+@pytest.mark.parametrize("kind", ["near_orthogonal", "random"])
+def test_both_lu_kernels_every_size(ctx, variant, n, kind):
+    """Both warp-per-determinant LU kernels (left-looking on chip, right-looking L2 scratch) at every row-tile
+    count and ragged size; `random` matrices force a row exchange in nearly every column step."""
+    rng = np.random.default_rng(1000 + n)
+    n_mo = n + 9
+    if kind == "random":
+        S = rng.standard_normal((n_mo, n_mo))
+    else:
+        q, _ = np.linalg.qr(rng.standard_normal((n_mo, n_mo)))
+        S = q + 0.02 * rng.standard_normal((n_mo, n_mo))
+    rows = np.array([rng.permutation(n_mo)[:n] for _ in range(7)], dtype=np.int32)
+    cols = np.array([rng.permutation(n_mo)[:n] for _ in range(6)], dtype=np.int32)
+    rows[1] = np.sort(rows[1])
+    cols[1] = np.sort(cols[1])
+    sgn, logdet = np.linalg.slogdet(S[rows[:, None, :, None], cols[None, :, None, :]])
+    ctx.set_lu_variant(variant)
+    try:
+        got = ctx.det_table_host(S, rows, cols)
+    finally:
+        ctx.set_lu_variant("auto")
+    assert np.array_equal(np.sign(got), sgn)
+    np.testing.assert_allclose(np.log(np.abs(got)), logdet, rtol=0, atol=1e-10)
+
+
+@pytest.mark.parametrize("variant", ["left", "right"])
+@pytest.mark.parametrize("n", [34, 64, 100])
+def test_lu_kernels_singular_minors(ctx, variant, n):
+    """Exactly singular minors (a repeated row, a zero column) give 0, not NaN, next to regular ones."""
+    rng = np.random.default_rng(n)
+    n_mo = n + 5
+    S = rng.standard_normal((n_mo, n_mo))
+    S[:, 3] = 0.0                                   # any column list holding 3 is singular
+    S[7] = S[2]                                     # any row list holding 2 and 7 is singular
+    base = np.array([i for i in range(n_mo) if i not in (2, 3, 7)], dtype=np.int32)
+    rows = np.stack([base[:n], np.concatenate([[2, 7], base[: n - 2]])]).astype(np.int32)
+    cols = np.stack([base[:n], np.concatenate([base[: n - 1], [3]])]).astype(np.int32)
+    ctx.set_lu_variant(variant)
+    try:
+        got = ctx.det_table_host(S, rows, cols)
+    finally:
+        ctx.set_lu_variant("auto")
+    sgn, logdet = np.linalg.slogdet(S[np.ix_(rows[0], cols[0])])
+    assert np.sign(got[0, 0]) == sgn and abs(np.log(abs(got[0, 0])) - logdet) < 1e-10
+    scale = abs(got[0, 0])
+    assert abs(got[0, 1]) == 0.0 and np.isfinite(got).all()
+    assert abs(got[1, 0]) <= 1e-9 * scale and abs(got[1, 1]) == 0.0
+
+
 def test_det_table_singular_and_tiny(ctx):
     S = np.arange(36, dtype=float).reshape(6, 6)            # rank 2: every 3x3 minor is singular
     rows = np.array([[0, 1, 2], [1, 3, 5]], dtype=np.int32)
@@ -348,6 +399,23 @@ def test_config_naphthalene_triplet_truncated(ctx):
         assert_parity(main.overlaps(bra_mos, ket_mos, bci, kci, 34, ci_thresh=1e-12, tier=tier), want)
 
 
+def test_config_naphthalene_triplet_full(ctx):
+    """configs[2] at full size: n_occ=34, n_mo=180, 20x20 singlet->triplet states (main.overlaps, sigma=-1), the
+    whole CIS space (K=4964 per side, 2.5e7 pairs).  The reference's pair loop cannot finish this; the checker
+    is the factored closed form of the same sum, the brute-force tier is checked against the rank-update tier."""
+    from pywfo_b200 import helpers, main
+    occ, n_mo, ns = 34, 180, 20
+    bra_mos, ket_mos, bci, kci = helpers.synthetic_case(1, n_mo, occ, ns, ns)
+    S = orc.mo_overlap(bra_mos, ket_mos, orc.get_S_AO(bra_mos, ket_mos, "ket"))
+    # main.overlaps folds sign^occ into the coefficients (pywfo/main.py:154,176): occ is even here
+    want = orc.state_overlaps_factored(S, occ, orc.signed_ci(bci, occ), orc.signed_ci(kci, occ), -1.0)
+    got = main.overlaps(bra_mos, ket_mos, bci, kci, occ, ci_thresh=0.0, tier="update")
+    assert_parity(got, want, rtol=1e-9)
+    got_lu = main.overlaps(bra_mos, ket_mos, bci, kci, occ, ci_thresh=0.0, tier="lu")
+    assert_parity(got_lu, want, rtol=1e-9)
+    assert_parity(got_lu, got, rtol=1e-9)
+
+
 def test_config_large_full_space_properties(ctx):
     """configs[3]: n_occ=100, n_mo=500, 50x50 states, full CIS space (K=40 000 per side, 1.6e9 pairs).
     The reference cannot run this; checked against the factored closed form (O(n^2 v) per state) and
@@ -385,7 +453,22 @@ def test_config_large_lu_sample(ctx):
     assert_parity(got_up, want, rtol=1e-9)
 
 
-@pytest.mark.parametrize("k", [32, 100])
+@pytest.mark.parametrize("variant", ["left", "right"])
+def test_config_large_lu_sample_both_kernels(ctx, variant):
+    """configs[3] shape (n_occ = 100): the brute-force tier through either LU kernel == oracle."""
+    from pywfo_b200 import helpers, main
+    occ, n_mo = 100, 500
+    bra_mos, ket_mos, bci, kci = helpers.synthetic_case(2, n_mo, occ, 3, 3, top_k=12)
+    want, _ = orc.ref_overlaps_cache(bra_mos, ket_mos, bci, kci, occ, 1e-12)
+    ctx.set_lu_variant(variant)
+    try:
+        got = main.overlaps_cache(bra_mos, ket_mos, bci, kci, occ, ci_thresh=1e-12, tier="lu")
+    finally:
+        ctx.set_lu_variant("auto")
+    assert_parity(got, want, rtol=1e-9)
+
+
+@pytest.mark.parametrize("k", [32, 100, 316, 1000])
 def test_config_sweep_n64(ctx, k):
     """configs[4]: n_occ=64, n_mo=320, 8x8 states, K_b=K_k=k random excitations shared by all states."""
     from pywfo_b200 import helpers
