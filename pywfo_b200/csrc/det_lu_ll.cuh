@@ -92,7 +92,7 @@ __device__ __forceinline__ void ll_load_panel(const double *__restrict__ S, cons
 // spent 6 of 10 cycles per instruction in 'no instruction' stalls.)
 // Returns 0 for a singular minor, 1 when no row changed position, 2 when rows moved.
 template <int NT, int SL>
-__device__ __forceinline__ int ll_factor(char *sm, int p, int lane, double &det, unsigned &par, LLClk &clk) {
+__device__ __forceinline__ int ll_factor(char *sm, int p, int n, int lane, double &det, unsigned &par, LLClk &clk) {
     using C = LLCfg<NT>;
     const unsigned FULL = 0xffffffffu;
     const int L = 8 * (NT - p);   // live rows
@@ -123,8 +123,10 @@ __device__ __forceinline__ int ll_factor(char *sm, int p, int lane, double &det,
     __syncwarp();   // the staging rows have been read; from here on a row's staging row holds its multipliers
     LL_T(3);
 
+    const int nsteps = n - 8 * p;   // < 8 in a ragged last panel: the identity padding needs no elimination
 #pragma unroll
     for (int jj = 0; jj < 8; jj++) {
+        if (jj >= nsteps) break;
         unsigned key = 0;
 #pragma unroll
         for (int s = 0; s < SL; s++) {
@@ -273,25 +275,23 @@ __device__ __forceinline__ double ll_lu_det(const double *__restrict__ S, int ld
         if (p < 0) continue;
         LL_T(0);
         // ---- left-looking update with the finished panels
-#pragma unroll 1
-        for (int q = 0; q < p; q++) {
-            double *rb = rbuf + 64 * (q & 1);
+        // (unrolled over q with an early exit: every (q, t) block is three instructions with static
+        // registers; as a loop over q with predicated tiles it cost 2.5x the issue slots)
 #pragma unroll
-            for (int t = 0; t < NT - 1; t++)
-                if (t == q) sts128(rb + g * 8 + 2 * tq, acc[t][0], acc[t][1]);
+        for (int q = 0; q < NT - 1; q++) {
+            if (q >= p) break;
+            double *rb = rbuf + 64 * (q & 1);
+            sts128(rb + g * 8 + 2 * tq, acc[q][0], acc[q][1]);
             __syncwarp();
             const double b0 = rb[tq * 8 + g], b1 = rb[(tq + 4) * 8 + g];
-            const double *Mq = Mall + (size_t)(q * (NT - 1) - q * (q - 1) / 2 - q - 1) * 64 + g * 8 + ((tq ^ swz) << 1);
+            const double *Mq = Mall + (q * (NT - 1) - q * (q - 1) / 2) * 64 + g * 8 + ((tq ^ swz) << 1);
             double2 af[NT];
 #pragma unroll
-            for (int t = 1; t < NT; t++)
-                if (t > q) {
-                    af[t] = lds128(Mq + t * 64);
-                    dmma884(acc[t][0], acc[t][1], af[t].x, b0);
-                }
+            for (int t = q + 1; t < NT; t++) af[t] = lds128(Mq + (t - q - 1) * 64);
 #pragma unroll
-            for (int t = 1; t < NT; t++)
-                if (t > q) dmma884(acc[t][0], acc[t][1], af[t].y, b1);
+            for (int t = q + 1; t < NT; t++) dmma884(acc[t][0], acc[t][1], af[t].x, b0);
+#pragma unroll
+            for (int t = q + 1; t < NT; t++) dmma884(acc[t][0], acc[t][1], af[t].y, b1);
         }
         LL_T(1);
         // ---- live rows to the row-per-lane layout through the staging area (top tile + future M_p)
@@ -309,8 +309,8 @@ __device__ __forceinline__ double ll_lu_det(const double *__restrict__ S, int ld
         LL_T(2);
         const int L = 8 * (NT - p);
         constexpr int SLMAX = (8 * NT + 31) / 32, SLLO = (SLMAX + 1) / 2;
-        if (L > 32 * SLLO) ok = ll_factor<NT, SLMAX>(sm, p, lane, det, par, clk);
-        else ok = ll_factor<NT, SLLO>(sm, p, lane, det, par, clk);
+        if (L > 32 * SLLO) ok = ll_factor<NT, SLMAX>(sm, p, n, lane, det, par, clk);
+        else ok = ll_factor<NT, SLLO>(sm, p, n, lane, det, par, clk);
         if (ok == 0) break;
         if (ok >= 2) {
             // rows moved: the same moves in the finished panels M_0 .. M_{p-1} ...

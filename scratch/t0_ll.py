@@ -3,7 +3,7 @@ python scratch/t0_ll.py  [n ...]"""
 import sys, numpy as np, torch
 sys.path.insert(0, '.')
 from pywfo_b200 import _lib, helpers, excitations as ex
-ns = [int(x) for x in sys.argv[1:]] or [34, 40, 64, 100, 128]
+ns = [int(x) for x in sys.argv[1:]] or [32, 34, 40, 64, 100, 128]
 ctx = _lib.context(0)
 dev = torch.device("cuda:0"); f64 = dict(dtype=torch.float64, device=dev)
 PEAK = 37.17
@@ -15,7 +15,7 @@ for n in ns:
     rng = np.random.default_rng(n)
     S_rand = rng.standard_normal((n_mo, n_mo))
     for name, S in (("near-identity", S_id), ("random", S_rand)):
-        ksh, kl = 128, 256
+        ksh, kl = 256, 512
         v = n_mo - n
         bra = np.stack([rng.integers(0, n, ksh), rng.integers(0, v, ksh)], 1).astype(np.int32)
         ket = np.stack([rng.integers(0, n, kl), rng.integers(0, v, kl)], 1).astype(np.int32)
@@ -27,11 +27,13 @@ for n in ns:
         rows = torch.tensor(rl, dtype=torch.int32, device=dev)
         cols = torch.tensor(cl, dtype=torch.int32, device=dev)
         D = torch.empty((ksh, kl), **f64)
-        ctx.set_timing(True)
+        import os
+        ctx.set_lu_variant(os.environ.get("LU", "auto"))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ts = []
-        for r in range(5):
-            ctx.det_table_dev(dS, n, rows, cols, D, 0); torch.cuda.synchronize()
-            if r >= 2: ts.append(ctx.last_kernel_ms())
+        for r in range(8):
+            e0.record(); ctx.det_table_dev(dS, n, rows, cols, D, torch.cuda.current_stream().cuda_stream); e1.record(); torch.cuda.synchronize()
+            if r >= 3: ts.append(e0.elapsed_time(e1))
         ms = float(np.mean(ts))
         fdet = n*(n-1)//2 + n*(n-1)*(2*n-1)//3 + (n-1)
         Dh = D.cpu().numpy()
