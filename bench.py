@@ -113,11 +113,18 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU baseline
-def cpu_baseline_run(w, budget_s=20.0):
-    """Reference algorithm (oracle port of pywfo.main.overlaps_cache / overlaps: memoised
-    np.linalg.det per unique pair + the Python double loop) on a bounded, truncated instance
-    of the workload.  Returns (pairs_per_s, seconds, sample description, unique pairs)."""
-    from oracle import pywfo_oracle as orc
+def _load_reference():
+    """The unmodified reference copied to oracle/_ref by oracle/make_ref.py (None if absent)."""
+    try:
+        from oracle import make_ref
+        return make_ref.load_ref()
+    except Exception:
+        return None
+
+
+def cpu_sample_inputs(w, budget_s=20.0):
+    """A bounded, truncated instance of the workload (same MOs, fewer states, top-k excitations per
+    state) sized so that the reference's pair loop finishes in about ``budget_s`` seconds."""
     n = w["n_occ"]
     full_k = n * (w["n_mo"] - n)
     # per unique determinant ~ (7 + n^2/115) us, per loop term ~0.5 us: size the sample
@@ -127,20 +134,40 @@ def cpu_baseline_run(w, budget_s=20.0):
     while k > 8 and (ns * k) ** 2 * t_det + ns * ns * 4 * k * k * 0.6e-6 > budget_s:
         k //= 2
     k = min(k, full_k)
-    bra_mos, ket_mos, bci, kci = make_inputs(w, top_k=k, n_states=ns)
+    return make_inputs(w, top_k=k, n_states=ns), ns, k
+
+
+def cpu_baseline_run(w, budget_s=20.0, inputs=None):
+    """The reference on the host: pywfo.main.overlaps_cache / overlaps of the UNMODIFIED reference
+    (oracle/_ref, stdout silenced; kind "reference"), or its oracle port when oracle/_ref is absent
+    (kind "port"), on a bounded, truncated instance of the workload.
+    Returns (pairs_per_s, seconds, sample description, unique pairs, kind, result)."""
+    import contextlib
+    import io
+    n = w["n_occ"]
+    (bra_mos, ket_mos, bci, kci), ns, k = inputs or cpu_sample_inputs(w, budget_s)
+    kb = int((np.abs(bci) >= 1e-12).any(axis=0).sum())
+    kk = int((np.abs(kci) >= 1e-12).any(axis=0).sum())
+    n_unique = (kb + 1) * (kk + 1)
+    ref = _load_reference()
+    fname = "overlaps_cache" if w["sigma"] > 0 else "overlaps"
     t0 = time.perf_counter()
-    if w["sigma"] > 0:
-        _, n_unique = orc.ref_overlaps_cache(bra_mos, ket_mos, bci, kci, n, 1e-12)
+    if ref is not None:
+        kind = "reference"
+        with contextlib.redirect_stdout(io.StringIO()):
+            res = getattr(ref, fname)(bra_mos, ket_mos, bci, kci, n, ci_thresh=1e-12)
     else:
-        orc.ref_overlaps_minus(bra_mos, ket_mos, bci, kci, n, 1e-12)
-        kb = int((np.abs(bci) > 1e-12).any(axis=0).sum())
-        kk = int((np.abs(kci) > 1e-12).any(axis=0).sum())
-        n_unique = (kb + 1) * (kk + 1)
+        from oracle import pywfo_oracle as orc
+        kind = "port"
+        if w["sigma"] > 0:
+            res, n_unique = orc.ref_overlaps_cache(bra_mos, ket_mos, bci, kci, n, 1e-12)
+        else:
+            res = orc.ref_overlaps_minus(bra_mos, ket_mos, bci, kci, n, 1e-12)
     dt = time.perf_counter() - t0
-    sample = (f"oracle port of pywfo.main.{'overlaps_cache' if w['sigma'] > 0 else 'overlaps'} on "
-              f"{ns}x{ns} states, top-{k} excitations/state of the same MOs: {n_unique} unique "
+    what = "unmodified pywfo.main." + fname if kind == "reference" else "oracle port of pywfo.main." + fname
+    sample = (f"{what} on {ns}x{ns} states, top-{k} excitations/state of the same MOs: {n_unique} unique "
               f"determinants + Python reduction loop, {dt:.1f} s")
-    return n_unique / dt, dt, sample, n_unique
+    return n_unique / dt, dt, sample, n_unique, kind, np.asarray(res)
 
 
 def blas_threads():
@@ -155,10 +182,16 @@ def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    try:   # torchrun exports OMP_NUM_THREADS=1: give the reference's BLAS/LAPACK calls every host core back
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
     vals = []
     sample = ""
+    kind = "port"
     for i in range(args.warmup + args.steps):
-        v, dt, sample, n_unique = cpu_baseline_run(w, budget_s=args.cpu_budget)
+        v, dt, sample, n_unique, kind, _ = cpu_baseline_run(w, budget_s=args.cpu_budget)
         if i >= args.warmup:
             vals.append((v, dt))
     value = float(np.mean([v for v, _ in vals]))
@@ -170,7 +203,7 @@ def run_reference(args, w):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": f"{args.workload}: {w['desc']} (bounded sample per step)"},
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host_cores": os.cpu_count(),
     }
@@ -364,7 +397,8 @@ def run_ours(args, w):
                     f"{n_pairs / (ks * kl / (t0m * 1e-3)):.1f} s"}
 
     # ---- the opt-in closed-form tier (GEMMs only, pair determinants never formed): wall time only
-    if args.t2:
+    #      (one GPU only: at N > 1 a rank holds a shard's partial, which has nothing to compare with)
+    if args.t2 and world == 1:
         try:
             for _ in range(2):
                 ctx.state_overlaps_dev(d_smo, n, d_be, d_cb, d_ke, d_ck, d_out, sigma=sigma, tier="closed",
@@ -379,7 +413,7 @@ def run_ours(args, w):
                 e1.record()
                 torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1))
-            t2_res = d_out.cpu().numpy()
+            t2_res = d_out.cpu().numpy()   # (this block runs on one GPU only, so this is the full matrix)
             kernels["t2_closed_form"] = {
                 "ms_per_matrix_stages_2_3": float(np.mean(ts)),
                 "max_rel_diff_vs_default_tier": float(np.abs(t2_res - result_first).max() / max(np.abs(result_first).max(), 1e-300)),
@@ -406,17 +440,32 @@ def run_ours(args, w):
                 ts.append(e0.elapsed_time(e1))
         kernels["raw_inputs_on_device"] = {
             "ms_per_matrix": float(np.mean(ts)),
-            "max_rel_diff_vs_device_leg": float(np.abs(raw_out.cpu().numpy() - (result_first if world == 1 else raw_out.cpu().numpy())).max()
-                                                / max(np.abs(result_first).max(), 1e-300)),
+            "max_rel_diff_vs_device_leg": (float(np.abs(raw_out.cpu().numpy() - result_first).max()
+                                                 / max(np.abs(result_first).max(), 1e-300)) if world == 1 else None),
             "note": "wfo_overlaps_ci_dev: device inverse + device thresholding + S_MO + pairs + reduction from MO "
                     "matrices and raw CI tensors in HBM (this rank's shard; no all-reduce)"}
     except Exception as exc:
         kernels["raw_inputs_on_device"] = {"error": str(exc)}
 
     cpu = None
+    same_config = None
     if world == 1 and args.cpu_budget > 0:
-        v, dt, sample, _ = cpu_baseline_run(w, budget_s=args.cpu_budget)
-        cpu = {"value": v, "unit": "pairs/s", "cores": blas_threads(), "kind": "port", "sample": sample}
+        inputs = cpu_sample_inputs(w, args.cpu_budget)
+        v, dt, sample, n_unique, kind, cpu_res = cpu_baseline_run(w, budget_s=args.cpu_budget, inputs=inputs)
+        cpu = {"value": v, "unit": "pairs/s", "cores": blas_threads(), "kind": kind, "sample": sample}
+        # the SAME truncated inputs once through this repo's public entry point (host arrays in, host
+        # matrix out): one measured same-workload ratio next to the per-pair-rate extrapolation
+        sb, sk, sbc, skc = inputs[0]
+        ts = []
+        for i in range(4):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            gres = fn(sb, sk, sbc, skc, n, ci_thresh=1e-12, ao_ovlps="ket", tier=tier)
+            if i > 0:
+                ts.append(time.perf_counter() - t0)
+        g_s = float(np.mean(ts))
+        same_config = {"workload": sample, "cpu_s": dt, "gpu_e2e_s": g_s, "ratio": dt / g_s, "cpu_kind": kind,
+                       "max_rel_diff": float(np.abs(gres - cpu_res).max() / max(np.abs(cpu_res).max(), 1e-300))}
 
     line = {
         "metric": "determinant-pair overlaps/sec", "value": value, "unit": "pairs/s", "n_gpus": world,
@@ -439,6 +488,7 @@ def run_ours(args, w):
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "same_config_vs_cpu": same_config,
         "parity": parity,
         "kernels": kernels,
         "host_cores": os.cpu_count(),
