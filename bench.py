@@ -218,7 +218,7 @@ def run_ours(args, w):
     from pywfo_b200 import _lib, excitations as ex, main as wmain
     from pywfo_b200 import dist as wdist
 
-    rank, world = wdist.init_from_env()
+    rank, world = wdist.init_from_env(in_library=(args.collective == "peer"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -248,13 +248,17 @@ def run_ours(args, w):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     stream = torch.cuda.current_stream().cuda_stream
     ctx.set_timing(True)
+    peer_collective = world > 1 and wdist.has_comm(ctx)
 
     def step():
         ctx.smo_inv_dev(d_bra, d_ket, d_inv, d_smo, d_work, stream)   # S_MO = bra (Cinv Cinv^T) ket^T
         ctx.state_overlaps_dev(d_smo, n, d_be, d_cb, d_ke, d_ck, d_out, sigma=sigma, tier=tier,
                                k_begin=lo, k_end=hi, stream=stream)
         if world > 1:
-            dist.all_reduce(d_out, op=dist.ReduceOp.SUM)
+            if peer_collective:
+                ctx.allreduce_dev(d_out, stream)   # two kernels on the stream: one-shot peer stores + ordered sum
+            else:
+                dist.all_reduce(d_out, op=dist.ReduceOp.SUM)
 
     def barrier():
         if world > 1:
@@ -330,13 +334,21 @@ def run_ours(args, w):
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_s = float(t_e2e.item())
-    h2d = 2 * n_mo * n_mo * 8 + bci.nbytes + kci.nbytes   # MO matrices + raw CI tensors (the inverse is formed on the device)
+    # per rank: MO matrices + this rank's slice of the bra (from, to) space (singlet semantics) + its 1/world of the
+    # ket CI tensor when the library all-gathers it over NVLink (the inverse is formed on the device)
+    h2d_rank = (2 * n_mo * n_mo * 8 + (bci.nbytes // world if sigma > 0 else bci.nbytes)
+                + (kci.nbytes // world if peer_collective else kci.nbytes))
+    h2d = h2d_rank * world
     d2h = int(res.nbytes)
     e2e_err = float(np.abs(res - result_first).max() / max(np.abs(result_first).max(), 1e-300))
 
+    if peer_collective:
+        ctx.comm_status()   # raises if any wait of the in-library collective timed out
+    if world > 1:
+        dist.barrier()   # last collective use: ranks > 0 leave, rank 0 goes on with single-GPU legs
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        wdist.disable()
+        dist.destroy_process_group()
         return 0
 
     # ---- roofline of the dominant kernel (device time from CUDA events inside the library,
@@ -474,6 +486,8 @@ def run_ours(args, w):
         "config": {"workload": f"{args.workload}: {w['desc']}", "n_occ": n, "n_mo": n_mo, "n_bra": w["n_bra"],
                    "n_ket": w["n_ket"], "K_bra": Kb, "K_ket": Kk, "pairs": n_pairs, "sigma": sigma,
                    "tier": {0: "lu", 1: "update"}.get(used_tier, str(used_tier)), "parallelism": f"bra-shard x{world}",
+                   "collective": ("none" if world == 1 else ("in-library peer-memory all-reduce (csrc/comm.cuh)" if peer_collective
+                                                             else "torch.distributed all_reduce (NCCL)")),
                    "l2": "flushed (256 MB write) between timed steps; inputs 38 MB < L2",
                    "inputs": "device leg (value): MO matrices, the inverse behind S_AO (pywfo/main.py:303, a host-side "
                              "prologue upstream) and the excitation tables are resident in HBM before the timed region; "
@@ -482,7 +496,7 @@ def run_ours(args, w):
         "wall_ms_per_matrix": ms_per_step,
         "clocks": clocks,
         "e2e": {"value": n_pairs / e2e_s, "unit": "pairs/s", "ms_per_call": e2e_s * 1e3,
-                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
+                "h2d_bytes_per_step": int(h2d), "h2d_bytes_per_step_per_rank": int(h2d_rank), "d2h_bytes_per_step": d2h * world,
                 "call": f"pywfo_b200.main.{'overlaps_cache' if sigma > 0 else 'overlaps'}(pinned host numpy arrays)",
                 "max_rel_diff_vs_device_leg": e2e_err},
         "gpu_launches": int(launches),
@@ -495,6 +509,7 @@ def run_ours(args, w):
     }
     print(json.dumps(line))
     if world > 1:
+        wdist.disable()
         dist.destroy_process_group()
     return 0
 
@@ -519,6 +534,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--tier", default="auto", choices=["auto", "lu", "update"])
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: in-library one-shot peer-memory all-reduce (default) or torch.distributed/NCCL")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--t0-sample", type=int, default=16384, help="pairs in the brute-force sample leg (0 = skip)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU baseline work (0 = skip)")

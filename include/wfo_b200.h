@@ -39,6 +39,7 @@ extern "C" {
 #define WFO_ERR_SINGULAR 3 /* base block S_MO[:occ,:occ] singular: tier 1/2 not applicable */
 #define WFO_ERR_EMPTY_STATE 4 /* pywfo.main.overlaps semantics: a state keeps no excitation (ValueError upstream) */
 #define WFO_ERR_NOCONV 5 /* device inverse did not converge (singular / extremely ill-conditioned MO matrix; LinAlgError in Python) */
+#define WFO_ERR_COMM 6 /* in-library collective: rendezvous failed, no peer access, or a rank did not take part */
 
 /* where the inverse of the MO matrix in S_AO = C^-1 C^-T (pywfo/main.py:301-311) comes from */
 #define WFO_AO_GIVEN 0 /* the caller supplies c_inv (e.g. np.linalg.inv, exactly as upstream) */
@@ -168,6 +169,24 @@ int wfo_trajectory_ci_host(wfo_ctx *ctx, const double *mos, const double *ci, in
                            int n_occ, int n_states, double ci_thresh, int semantics, int tier,
                            int ao_side, const int32_t *pairs, int n_pairs, int rank, int world,
                            double *out, int32_t *info);
+/* ---- K5: the one collective of the path, inside the library ------------------
+ * (new: the reference is single-process).  One process per GPU of ONE node.
+ * wfo_comm_init is collective: every rank calls it with the same `world` and the same job-unique
+ * `tag`; the ranks exchange CUDA IPC handles of a per-rank buffer through /dev/shm/wfo_b200_<tag>_*
+ * and map each other's buffers (NVLink peer access).  Afterwards
+ *   - wfo_overlaps_ci_host(.., rank, world, ..) uploads 1/world of the ket CI tensor per rank and
+ *     all-gathers it over NVLink, and returns the FULL n_bra x n_ket matrix on every rank;
+ *   - wfo_allreduce_dev sums `count` doubles (<= 131072) over the ranks in place, in rank order
+ *     (bitwise identical on all ranks), as two kernels on `stream` (one-shot peer stores + flags).
+ * gather_bytes: capacity for the ket CI tensor (0 = 64 MB).  A collective in which a rank does not
+ * take part times out after ~20 s of GPU time: wfo_comm_status / the *_host entry points then
+ * return WFO_ERR_COMM instead of hanging. */
+int wfo_comm_init(wfo_ctx *ctx, int rank, int world, const char *tag, long long gather_bytes);
+int wfo_comm_destroy(wfo_ctx *ctx);
+int wfo_comm_world(const wfo_ctx *ctx);   /* 0 = no communicator */
+int wfo_allreduce_dev(wfo_ctx *ctx, double *buf, long long count, void *stream);
+int wfo_comm_status(wfo_ctx *ctx);        /* after a stream sync: WFO_ERR_COMM if a wait timed out */
+
 /* Brute-force tier, 32 < n_occ <= 128: which of the two warp-per-determinant LU kernels runs.
  * AUTO = left-looking, all on chip (csrc/det_lu_ll.cuh) up to n_occ = 64, right-looking with an
  * L2-resident scratch (csrc/det_lu_wpm.cuh) above.  Both compute the same partially pivoted LU

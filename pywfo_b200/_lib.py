@@ -54,6 +54,11 @@ SIGNATURES = {
                                       C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
     "wfo_trajectory_ci_host": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
                                          C.c_int, c_vp, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
+    "wfo_comm_init": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_char_p, C.c_longlong]),
+    "wfo_comm_destroy": (C.c_int, [c_vp]),
+    "wfo_comm_world": (C.c_int, [c_vp]),
+    "wfo_allreduce_dev": (C.c_int, [c_vp, c_vp, C.c_longlong, c_vp]),
+    "wfo_comm_status": (C.c_int, [c_vp]),
     "wfo_set_lu_variant": (C.c_int, [c_vp, C.c_int]),
     "wfo_last_tier": (C.c_int, [c_vp]),
     "wfo_set_timing": (C.c_int, [c_vp, C.c_int]),
@@ -65,6 +70,7 @@ SIGNATURES = {
 
 AO_GIVEN, AO_BRA, AO_KET = 0, 1, 2
 ERR_NOCONV = 5
+ERR_COMM = 6
 
 
 class WfoError(RuntimeError):
@@ -325,6 +331,25 @@ class Context:
 
     def last_tier(self) -> int:
         return int(self.lib.wfo_last_tier(self.handle))
+
+    # ---- the in-library collective (K5) -----------------------------------------
+    def comm_init(self, rank: int, world: int, tag: str, gather_bytes: int = 0):
+        """Collective: every rank of the node calls this with the same ``world`` and job-unique ``tag``."""
+        check(self.lib.wfo_comm_init(self.handle, int(rank), int(world), tag.encode(), int(gather_bytes)))
+
+    def comm_destroy(self):
+        check(self.lib.wfo_comm_destroy(self.handle))
+
+    def comm_world(self) -> int:
+        return int(self.lib.wfo_comm_world(self.handle))
+
+    def allreduce_dev(self, t, stream=0):
+        """Sum a float64 CUDA tensor over the ranks in place (rank order, bitwise identical everywhere)."""
+        self._dev(t)
+        check(self.lib.wfo_allreduce_dev(self.handle, t.data_ptr(), t.numel(), stream))
+
+    def comm_status(self):
+        check(self.lib.wfo_comm_status(self.handle))
 
     def set_lu_variant(self, variant):
         """Brute-force kernel for 32 < n_occ <= 128: 0/"auto", 1/"left" (on chip), 2/"right" (L2 scratch)."""

@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "comm.cuh"
 #include "det_lu_warp.cuh"
 #include "det_lu_ll.cuh"
 #include "det_lu_wpm.cuh"
@@ -474,6 +475,7 @@ int wfo_destroy(wfo_ctx *ctx) {
     if (!ctx) return WFO_OK;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    wfo_comm_destroy(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->gscratch) cudaFree(ctx->gscratch);
     if (ctx->resident) cudaFree(ctx->resident);
@@ -493,6 +495,146 @@ int wfo_destroy(wfo_ctx *ctx) {
 }
 
 long long wfo_launch_count(const wfo_ctx *ctx) { return ctx ? ctx->launches : 0; }
+/* ------------------------------------------------------------ K5: in-library collective */
+int wfo_comm_destroy(wfo_ctx *ctx) {
+    if (!ctx || !ctx->comm) return WFO_OK;
+    Comm *c = ctx->comm;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < c->world; r++)
+        if (r != c->rank && c->peers.base[r]) cudaIpcCloseMemHandle(c->peers.base[r]);
+    if (c->buf) cudaFree(c->buf);
+    unlink(comm_path(c->tag, c->rank).c_str());
+    delete c;
+    ctx->comm = nullptr;
+    return WFO_OK;
+}
+
+int wfo_comm_init(wfo_ctx *ctx, int rank, int world, const char *tag, long long gather_bytes) {
+    if (!ctx || !tag) return set_err(WFO_ERR_ARG, "comm_init: NULL argument");
+    if (world < 1 || world > COMM_MAX_RANKS || rank < 0 || rank >= world)
+        return set_err(WFO_ERR_ARG, "comm_init: rank %lld of %lld (at most 16 ranks of one node)", rank, world);
+    if (strlen(tag) >= sizeof(Comm::tag)) return set_err(WFO_ERR_ARG, "comm_init: tag too long");
+    WFO_TRY(wfo_comm_destroy(ctx));
+    if (world == 1) return WFO_OK;
+    WFO_CUDA(cudaSetDevice(ctx->device));
+    Comm *c = new (std::nothrow) Comm();
+    if (!c) return set_err(WFO_ERR_ARG, "comm_init: out of host memory");
+    memset(c, 0, sizeof(*c));
+    c->rank = rank;
+    c->world = world;
+    strcpy(c->tag, tag);
+    c->gat_cap = align_up((size_t)(gather_bytes > 0 ? gather_bytes : (64ll << 20)), 4096);
+    c->bytes = comm_gat_off(world) + c->gat_cap;
+    ctx->comm = c;   // from here on wfo_comm_destroy cleans up
+    WFO_CUDA(cudaMalloc(&c->buf, c->bytes));
+    WFO_CUDA(cudaMemset(c->buf, 0, COMM_HDR_BYTES));
+    WFO_CUDA(cudaDeviceSynchronize());
+    CommCard mine;
+    memset(&mine, 0, sizeof(mine));
+    WFO_CUDA(cudaIpcGetMemHandle(&mine.handle, c->buf));
+    mine.device = ctx->device;
+    mine.pid = (int)getpid();
+    mine.bytes = c->bytes;
+    if (!comm_write_card(comm_path(tag, rank), mine)) {
+        wfo_comm_destroy(ctx);
+        return set_err(WFO_ERR_COMM, "comm_init: cannot write the rendezvous file in /dev/shm");
+    }
+    c->peers.base[rank] = c->buf;
+    for (int r = 0; r < world; r++) {
+        if (r == rank) continue;
+        CommCard card;
+        if (!comm_read_card(comm_path(tag, r), &card, 120.0)) {
+            wfo_comm_destroy(ctx);
+            return set_err(WFO_ERR_COMM, "comm_init: rank %lld did not show up within 120 s", r);
+        }
+        if (card.bytes != c->bytes) {
+            wfo_comm_destroy(ctx);
+            return set_err(WFO_ERR_COMM, "comm_init: rank %lld uses a different buffer size", r);
+        }
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, card.handle, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            wfo_comm_destroy(ctx);
+            return set_err(WFO_ERR_COMM, "comm_init: cannot map the buffer of rank %lld (no peer access between the GPUs?)", r);
+        }
+        c->peers.base[r] = static_cast<char *>(p);
+    }
+    return WFO_OK;
+}
+
+int wfo_comm_world(const wfo_ctx *ctx) { return (ctx && ctx->comm) ? ctx->comm->world : 0; }
+
+// raise the epoch of both collectives (every rank, every call, also on an error path: the counters of
+// all ranks stay in step)
+static void comm_next(Comm *c, int *ge, int *re) {
+    *ge = ++c->gat_epoch;
+    *re = ++c->red_epoch;
+}
+
+static int comm_allreduce(wfo_ctx *ctx, double *buf, size_t count, int epoch, cudaStream_t st) {
+    Comm *c = ctx->comm;
+    if (count * sizeof(double) > COMM_RED_CAP)
+        return set_err(WFO_ERR_ARG, "allreduce: %lld doubles exceed the slot size", (long long)count);
+    const int parity = epoch & 1;
+    const int bpp = count > 4096 ? 4 : 1;
+    comm_push_kernel<<<c->world * bpp, 256, 0, st>>>(buf, count, c->peers, comm_red_off(c->world, parity, c->rank),
+                                                      (int)(offsetof(CommHdr, red_flag) / 4), c->rank, c->world, epoch, bpp,
+                                                      true, reinterpret_cast<CommHdr *>(c->buf));
+    WFO_LAUNCH_CHECK(ctx);
+    const int gs = (int)std::min<size_t>(8, (count + 255) / 256);
+    comm_reduce_sum_kernel<<<gs, 256, 0, st>>>(c->buf, c->world, parity, epoch, count, buf);
+    WFO_LAUNCH_CHECK(ctx);
+    return WFO_OK;
+}
+
+// my flat slice [lo, hi) (doubles) of the gather buffer is in place: push it to the peers, wait for theirs
+static int comm_allgather(wfo_ctx *ctx, size_t lo, size_t hi, int epoch, cudaStream_t st) {
+    Comm *c = ctx->comm;
+    double *g = reinterpret_cast<double *>(c->buf + comm_gat_off(c->world));
+    const int bpp = 16;
+    if (hi > lo) {
+        comm_push_kernel<<<c->world * bpp, 256, 0, st>>>(g + lo, hi - lo, c->peers, comm_gat_off(c->world) + lo * 8,
+                                                          (int)(offsetof(CommHdr, gat_flag) / 4), c->rank, c->world, epoch,
+                                                          bpp, false, reinterpret_cast<CommHdr *>(c->buf));
+    } else {   // nothing to send: raise the flags only
+        comm_push_kernel<<<c->world, 32, 0, st>>>(g, 0, c->peers, comm_gat_off(c->world), (int)(offsetof(CommHdr, gat_flag) / 4),
+                                                   c->rank, c->world, epoch, 1, false, reinterpret_cast<CommHdr *>(c->buf));
+    }
+    WFO_LAUNCH_CHECK(ctx);
+    comm_wait_kernel<<<1, 32, 0, st>>>(reinterpret_cast<CommHdr *>(c->buf), (int)(offsetof(CommHdr, gat_flag) / 4), c->world,
+                                       epoch, c->rank);
+    WFO_LAUNCH_CHECK(ctx);
+    return WFO_OK;
+}
+
+// after a stream sync: did a wait time out?
+static int comm_check(wfo_ctx *ctx) {
+    int err = 0;
+    WFO_CUDA(cudaMemcpy(&err, ctx->comm->buf + offsetof(CommHdr, error), sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) {
+        WFO_CUDA(cudaMemset(ctx->comm->buf + offsetof(CommHdr, error), 0, sizeof(int)));
+        return set_err(WFO_ERR_COMM, "collective timed out: a rank did not take part (failed or called with other inputs)");
+    }
+    return WFO_OK;
+}
+
+int wfo_allreduce_dev(wfo_ctx *ctx, double *buf, long long count, void *stream) {
+    if (!ctx || !buf || count < 0) return set_err(WFO_ERR_ARG, "allreduce_dev: bad argument");
+    if (!ctx->comm) return WFO_OK;   // one rank
+    WFO_CUDA(cudaSetDevice(ctx->device));
+    int ge, re;
+    comm_next(ctx->comm, &ge, &re);
+    return comm_allreduce(ctx, buf, (size_t)count, re, (cudaStream_t)stream);
+}
+
+int wfo_comm_status(wfo_ctx *ctx) {
+    if (!ctx || !ctx->comm) return WFO_OK;
+    WFO_CUDA(cudaSetDevice(ctx->device));
+    return comm_check(ctx);
+}
+
 int wfo_set_lu_variant(wfo_ctx *ctx, int variant) {
     if (!ctx || variant < WFO_LU_AUTO || variant > WFO_LU_RIGHT) return set_err(WFO_ERR_ARG, "set_lu_variant: bad argument");
     ctx->lu_variant = variant;
@@ -1328,6 +1470,17 @@ int wfo_overlaps_ci_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_
     // thresholds only ITS slice of the bra (from, to) space -- any partition of the bra excitations gives
     // partial matrices that add up -- so the bra-side copies and table work shrink with the rank count.
     const bool slice = world > 1 && semantics == 0;
+    // With a communicator (wfo_comm_init) the ranks also share the ket side: every rank uploads 1/world
+    // of the ket CI tensor and pushes it to its peers over NVLink, and the partial matrices are summed
+    // on the device, so `out` is the full matrix on every rank.
+    Comm *cm = (ctx->comm && ctx->comm->world == world && world > 1) ? ctx->comm : nullptr;
+    if (ctx->comm && !cm) return set_err(WFO_ERR_ARG, "overlaps_ci_host: world does not match the communicator");
+    if (cm && (size_t)n_bra * n_ket * 8 > COMM_RED_CAP) return set_err(WFO_ERR_ARG, "overlaps_ci_host: result too large for the collective");
+    int gat_epoch = 0, red_epoch = 0;
+    if (cm) comm_next(cm, &gat_epoch, &red_epoch);
+    const size_t kci_n = (size_t)n_ket * count;
+    const bool gather = cm && kci_n * 8 <= cm->gat_cap;
+    if (gather) d_kci = reinterpret_cast<double *>(cm->buf + comm_gat_off(world));
     int p_lo = 0, p_len = count;
     if (slice) {
         const int base = count / world, rem = count % world;
@@ -1339,7 +1492,13 @@ int wfo_overlaps_ci_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_
     } else {
         WFO_CUDA(cudaMemcpyAsync(d_bci, bra_ci, (size_t)n_bra * count * 8, cudaMemcpyHostToDevice, st));
     }
-    WFO_CUDA(cudaMemcpyAsync(d_kci, ket_ci, (size_t)n_ket * count * 8, cudaMemcpyHostToDevice, st));
+    if (gather) {
+        const size_t lo = kci_n * rank / world, hi = kci_n * (rank + 1) / world;
+        if (hi > lo) WFO_CUDA(cudaMemcpyAsync(d_kci + lo, ket_ci + lo, (hi - lo) * 8, cudaMemcpyHostToDevice, st));
+        WFO_TRY(comm_allgather(ctx, lo, hi, gat_epoch, st));
+    } else {
+        WFO_CUDA(cudaMemcpyAsync(d_kci, ket_ci, kci_n * 8, cudaMemcpyHostToDevice, st));
+    }
     WFO_CUDA(cudaMemcpyAsync(d_bra, bra_mos, nsq * 8, cudaMemcpyHostToDevice, s2));
     WFO_CUDA(cudaMemcpyAsync(d_ket, ket_mos, nsq * 8, cudaMemcpyHostToDevice, s2));
     if (ao_side == WFO_AO_GIVEN) WFO_CUDA(cudaMemcpyAsync(d_inv, c_inv, nsq * 8, cudaMemcpyHostToDevice, s2));
@@ -1351,12 +1510,16 @@ int wfo_overlaps_ci_host(wfo_ctx *ctx, const double *bra_mos, const double *ket_
     else
         WFO_TRY(overlaps_ci_core(ctx, w, d_bra, d_ket, ao_side == WFO_AO_GIVEN ? d_inv : nullptr, ao_side, n_mo, n_occ, d_bci,
                                  n_bra, d_kci, n_ket, ci_thresh, semantics, tier, rank, world, false, info, &zero, st));
-    if (zero) {
+    if (cm) {   // every rank takes part, also one whose slice kept no excitation
+        if (zero) WFO_CUDA(cudaMemsetAsync(w.out, 0, (size_t)n_bra * n_ket * 8, st));
+        WFO_TRY(comm_allreduce(ctx, w.out, (size_t)n_bra * n_ket, red_epoch, st));
+    } else if (zero) {
         memset(out, 0, (size_t)n_bra * n_ket * sizeof(double));
         return WFO_OK;
     }
     WFO_CUDA(cudaMemcpyAsync(out, w.out, (size_t)n_bra * n_ket * 8, cudaMemcpyDeviceToHost, st));
     WFO_CUDA(cudaStreamSynchronize(st));
+    if (cm) WFO_TRY(comm_check(ctx));
     return WFO_OK;
 }
 

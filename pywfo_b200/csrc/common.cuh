@@ -69,7 +69,7 @@ __device__ __forceinline__ unsigned hi_abs(double x) {
 
 }  // namespace wfo
 
-namespace wfo { struct BaseInfo; }
+namespace wfo { struct BaseInfo; struct Comm; }
 
 struct wfo_ctx {
     int device;
@@ -91,6 +91,7 @@ struct wfo_ctx {
     size_t resident_bytes;
     long long launches;
     int last_tier;
+    wfo::Comm *comm;       // in-library collective over peer memory (wfo_comm_init), NULL = single rank
     int lu_variant;        // WFO_LU_*: which brute-force kernel serves 32 < n <= 128
     int timing;
     float last_ms;

@@ -13,9 +13,11 @@ thresholding of the CI vectors (main.py:539-540, 112, 122-123), every
 determinant pair and the CI-weighted reduction.  Extra keyword arguments
 (``tier``, ``device``, ``c_inv``) are a superset of the reference signature.
 
-When ``torch.distributed`` is initialised with more than one rank, each rank
-computes the partial matrix of its shard of the bra excitations and the
-partials are summed with one all-reduce (dist.py).
+Calls are purely local, like the reference's, unless the program opts in to
+sharding with ``pywfo_b200.dist.enable()`` / ``init_from_env()``: then every rank
+(one per GPU) must call with identical inputs, computes the partial matrix of its
+shard of the bra excitations, and the partials are summed with one all-reduce
+(inside the CUDA library over NVLink peer memory, dist.py / csrc/comm.cuh).
 """
 from __future__ import annotations
 
@@ -94,6 +96,9 @@ def _state_overlaps(semantics, sigma, bra_mos, ket_mos, bra_ci, ket_ci, occ, ci_
             raise KeyError(ao_ovlps)   # upstream: dict lookup, main.py:303
         side = _lib.AO_BRA if ao_ovlps == "bra" else _lib.AO_KET
         rank, world = dist.world()
+        in_library = dist.has_comm(ctx)   # the library all-gathers the ket side and all-reduces the result itself
+        if world > 1 and not in_library and ctx.comm_world():
+            raise RuntimeError("the context's communicator does not match the enabled process group")
         try:
             part, _ = ctx.overlaps_ci_host(bra_mos, ket_mos, c_inv, occ, bra_ci, ket_ci, ci_thresh,
                                            ao_side=side, semantics=0 if semantics == "cache" else 1,
@@ -102,7 +107,7 @@ def _state_overlaps(semantics, sigma, bra_mos, ket_mos, bra_ci, ket_ci, occ, ci_
             if exc.code != _lib.ERR_NOCONV:
                 raise
             raise np.linalg.LinAlgError("Singular matrix") from exc   # what np.linalg.inv raises upstream
-        return dist.sum_over_ranks(part, device=ctx.device)
+        return part if in_library else dist.sum_over_ranks(part, device=ctx.device)
     if not isinstance(ao_ovlps, np.ndarray):
         raise Exception("Invalid AO overlaps!")
     # explicit AO overlap matrix (documented upstream, main.py:305): tables built on the host

@@ -27,6 +27,9 @@ def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
+        # sharding is opt-in: a process group alone must not change what the entry points do
+        assert wdist.world() == (0, 1)
+        assert wdist.enable() == (rank, world)
         g = load_golden("r_water")
         occ = int(g["occ"])
         S = orc.mo_overlap(g["bra_mos"], g["ket_mos"], orc.get_S_AO(g["bra_mos"], g["ket_mos"], "ket"))
@@ -79,6 +82,7 @@ def _traj_worker(rank, world, port, q, n_use):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
+        wdist.enable()
         g = load_golden("cytosin_traj")
         occ, thr = int(g["occ"]), float(g["ci_thresh"])
         pairs = g["pairs"][:n_use]
@@ -124,3 +128,48 @@ def test_two_rank_trajectory(n_use):
     np.testing.assert_array_equal(res[0][2], res[1][2])
     g = load_golden("cytosin_traj")
     np.testing.assert_allclose(res[0][2], g["ref_overlaps_cache"][:n_use], rtol=1e-10, atol=1e-13)
+
+
+# ---------------------------------------------------------------- a failure on one rank is raised on all
+def _failing_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from pywfo_b200 import dist as wdist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        wdist.enable()
+
+        def compute(idx, r, w):
+            if rank == 1:
+                raise ValueError("a state keeps no excitation")   # e.g. WFO_ERR_EMPTY_STATE of one pair
+            return np.zeros((len(idx), 2, 2))
+
+        try:
+            wdist.sharded_trajectory(compute, 4, 2)
+            q.put((rank, "returned"))
+        except ValueError as e:
+            q.put((rank, "ValueError: " + str(e)))
+        except RuntimeError as e:
+            q.put((rank, "RuntimeError: " + str(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_rank_local_failure_raises_everywhere():
+    """a rank-local exception used to leave the other ranks blocked in the all-reduce."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_failing_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert res[1].startswith("ValueError")
+    assert res[0].startswith("RuntimeError") and "another rank failed" in res[0]
