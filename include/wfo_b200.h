@@ -82,15 +82,22 @@ int wfo_sao_dev(wfo_ctx *ctx, const double *c_inv, int n, double *s_ao, void *st
  * pywfo/main.py:304 + :532, associated so that S_AO is never materialised (work: 2 n*n doubles or NULL). */
 int wfo_smo_inv_dev(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos, const double *c_inv, int n,
                     double *s_mo, double *work, void *stream);
-/* a_inv = a^-1 (n x n), replaces np.linalg.inv in pywfo/main.py:303 (98, 212): Newton-Schulz
- * iteration X <- X (2I - A X) from X0 = A^T / |A^T A|_inf, i.e. nothing but FP64 tensor-core
- * GEMMs; quadratically convergent for every non-singular A, about 2 log2(cond) + 6 iterations
- * (orthonormal MOs: the first iterate is already the inverse).
- * `work` = 2 n*n doubles of device scratch (NULL: from the context).  Synchronises the stream
- * every few iterations to read the residual max|A X - I|.  WFO_ERR_NOCONV if it does not
- * converge within 100 iterations (singular or extremely ill-conditioned input). */
+/* a_inv = a^-1 (n x n), replaces np.linalg.inv in pywfo/main.py:303 (98, 212).
+ * Fast path: Newton-Schulz iteration X <- X (2I - A X) from X0 = A^T / |A^T A|_inf, i.e. nothing but
+ * FP64 tensor-core GEMMs; quadratically convergent, about 2 log2(cond) + 6 iterations (orthonormal
+ * MOs: the first iterate is already the inverse); the stream is synchronised every 3 iterations to
+ * read the residual max|A X - I|.
+ * Fallback (residual stagnating above 1e-8 = rounding has taken over, cond >~ 1e7, or no convergence
+ * in 51 iterations): Gauss-Jordan elimination with PARTIAL PIVOTING on the device (one cooperative
+ * grid, csrc/inverse_gj.cuh), which is to this library what LAPACK getrf/getri is to the reference:
+ * it returns an inverse as good as the conditioning allows instead of an error.
+ * WFO_ERR_NOCONV only for a singular matrix (zero pivot column), where numpy raises LinAlgError.
+ * `work` = 2 n*n doubles of device scratch (NULL: from the context). */
 int wfo_inverse_dev(wfo_ctx *ctx, const double *a, int n, double *a_inv, double *work, void *stream);
 int wfo_inverse_host(wfo_ctx *ctx, const double *a, int n, double *a_inv);
+/* how the last inverse of this context was obtained: Newton-Schulz iterations run, and whether the
+ * pivoted elimination produced the result */
+int wfo_last_inverse_info(const wfo_ctx *ctx, int *iterations, int *pivoted);
 /* generic C = alpha*op(A) op(B) + beta*C (row-major; ta/tb: 0 = N, 1 = T) */
 int wfo_gemm_dev(wfo_ctx *ctx, int ta, int tb, int m, int n, int k, double alpha, const double *A,
                  int lda, const double *B, int ldb, double beta, double *C, int ldc, void *stream);

@@ -48,6 +48,7 @@ SIGNATURES = {
     "wfo_smo_inv_dev": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp]),
     "wfo_inverse_dev": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp]),
     "wfo_inverse_host": (C.c_int, [c_vp, c_vp, C.c_int, c_vp]),
+    "wfo_last_inverse_info": (C.c_int, [c_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "wfo_overlaps_ci_host": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, c_vp, C.c_int,
                                        C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
     "wfo_overlaps_ci_dev": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, c_vp, C.c_int,
@@ -350,6 +351,12 @@ class Context:
 
     def comm_status(self):
         check(self.lib.wfo_comm_status(self.handle))
+
+    def last_inverse_info(self):
+        """(Newton-Schulz iterations, pivoted fallback used) of the last inverse on this context."""
+        it, pv = C.c_int(), C.c_int()
+        check(self.lib.wfo_last_inverse_info(self.handle, C.byref(it), C.byref(pv)))
+        return it.value, bool(pv.value)
 
     def set_lu_variant(self, variant):
         """Brute-force kernel for 32 < n_occ <= 128: 0/"auto", 1/"left" (on chip), 2/"right" (L2 scratch)."""

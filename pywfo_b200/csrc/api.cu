@@ -10,6 +10,7 @@
 #include "det_lu_ll.cuh"
 #include "det_lu_wpm.cuh"
 #include "gemm_f64.cuh"
+#include "inverse_gj.cuh"
 #include "lu_base.cuh"
 #include "misc_kernels.cuh"
 #include "pair_update.cuh"
@@ -478,6 +479,7 @@ int wfo_destroy(wfo_ctx *ctx) {
     wfo_comm_destroy(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->gscratch) cudaFree(ctx->gscratch);
+    if (ctx->gj_buf) cudaFree(ctx->gj_buf);
     if (ctx->resident) cudaFree(ctx->resident);
     if (ctx->ns_slots) cudaFree(ctx->ns_slots);
     if (ctx->h_slots) cudaFreeHost(ctx->h_slots);
@@ -635,6 +637,13 @@ int wfo_comm_status(wfo_ctx *ctx) {
     return comm_check(ctx);
 }
 
+int wfo_last_inverse_info(const wfo_ctx *ctx, int *iterations, int *pivoted) {
+    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL");
+    if (iterations) *iterations = ctx->last_inverse_iters;
+    if (pivoted) *pivoted = ctx->last_inverse_pivoted;
+    return WFO_OK;
+}
+
 int wfo_set_lu_variant(wfo_ctx *ctx, int variant) {
     if (!ctx || variant < WFO_LU_AUTO || variant > WFO_LU_RIGHT) return set_err(WFO_ERR_ARG, "set_lu_variant: bad argument");
     ctx->lu_variant = variant;
@@ -705,7 +714,7 @@ int wfo_smo_dev(wfo_ctx *ctx, const double *bra_mos, const double *s_ao, const d
 }
 
 /* Newton-Schulz inverse on the DMMA GEMM (replaces np.linalg.inv, pywfo/main.py:303) */
-constexpr int NS_MAX_ITERS = 100;
+constexpr int NS_MAX_ITERS = 51;   // enough for cond ~ 1e6; anything slower goes to the pivoted elimination
 int wfo_inverse_dev(wfo_ctx *ctx, const double *a, int n, double *a_inv, double *work, void *stream) {
     if (!ctx || !a || !a_inv) return set_err(WFO_ERR_ARG, "inverse: NULL argument");
     if (n < 1) return set_err(WFO_ERR_ARG, "inverse: n=%lld", n);
@@ -729,9 +738,11 @@ int wfo_inverse_dev(wfo_ctx *ctx, const double *a, int n, double *a_inv, double 
     WFO_LAUNCH_CHECK(ctx);
     const int rblocks = (int)((nn + 255) / 256 < (size_t)ctx->sm_count * 4 ? (nn + 255) / 256 : (size_t)ctx->sm_count * 4);
     int it = 0, checked = 0;
-    bool converged = false;
+    bool converged = false, give_up = false;
+    double prev = 1e300;
     ctx->last_inverse_iters = 0;
-    while (it < NS_MAX_ITERS && !converged) {
+    ctx->last_inverse_pivoted = 0;
+    while (it < NS_MAX_ITERS && !converged && !give_up) {
         const int batch = 3;   // iterations between two looks at the residuals
         for (int b = 0; b < batch && it < NS_MAX_ITERS; b++, it++) {
             // T = A X; residual max|T - I| -> slots[2 + it], Xn = X; Xn = 2 Xn - X T
@@ -743,17 +754,57 @@ int wfo_inverse_dev(wfo_ctx *ctx, const double *a, int n, double *a_inv, double 
         }
         WFO_CUDA(cudaMemcpyAsync(ctx->h_slots, slots, 128 * sizeof(double), cudaMemcpyDeviceToHost, st));
         WFO_CUDA(cudaStreamSynchronize(st));
-        // the residual seen at iteration i is squared by the update that follows it
-        for (; checked < it; checked++) {
+        // the residual seen at iteration i is squared by the update that follows it (max norm: at most
+        // n r^2); once it is below 1e-4 it must keep collapsing: if it does not even halve, rounding has
+        // taken over (cond >~ 1e7)
+        for (; checked < it && !converged; checked++) {
             const double r = ctx->h_slots[2 + checked];
-            if (!(r < 1e250)) return set_err(WFO_ERR_NOCONV, "inverse: Newton-Schulz diverged (singular matrix?)");
-            if (r < 1e-8) { converged = true; }
+            if (!(r < 1e250)) give_up = true;                        // diverged / not finite
+            else if (r < 1e-8) converged = true;
+            else if (prev < 1e-4 && r > 0.5 * prev) give_up = true;   // stagnation
+            prev = r;
         }
     }
     ctx->last_inverse_iters = it;
-    if (!converged)
-        return set_err(WFO_ERR_NOCONV, "inverse: Newton-Schulz did not converge in %lld iterations", it);
-    if (X != a_inv) WFO_CUDA(cudaMemcpyAsync(a_inv, X, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (converged) {
+        if (X != a_inv) WFO_CUDA(cudaMemcpyAsync(a_inv, X, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        return WFO_OK;
+    }
+    // ---- fallback: Gauss-Jordan with partial pivoting (what LAPACK's inverse is to the reference)
+    {
+        double *W = T, *V = Xb;
+        WFO_CUDA(cudaMemcpyAsync(W, a, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        int per_sm = 1;
+        WFO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gj_inverse_kernel, GJ_THREADS, 0));
+        int G = ctx->sm_count * (per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm));
+        if (G > n) G = n;
+        // bookkeeping behind the Newton-Schulz slots: pivots, pivot values, candidates, used flags, state
+        const size_t bytes = align_up((size_t)n * 4, 16) + (size_t)n * 8 + (size_t)G * sizeof(GjCand) + align_up((size_t)n, 16) + 16;
+        if (bytes > ctx->gj_bytes) {
+            WFO_CUDA(cudaStreamSynchronize(st));
+            if (ctx->gj_buf) WFO_CUDA(cudaFree(ctx->gj_buf));
+            ctx->gj_buf = nullptr;
+            ctx->gj_bytes = 0;
+            WFO_CUDA(cudaMalloc(&ctx->gj_buf, bytes));
+            ctx->gj_bytes = bytes;
+        }
+        char *q = ctx->gj_buf;
+        int *piv = reinterpret_cast<int *>(q); q += align_up((size_t)n * 4, 16);
+        double *dval = reinterpret_cast<double *>(q); q += (size_t)n * 8;
+        GjCand *cand = reinterpret_cast<GjCand *>(q); q += (size_t)G * sizeof(GjCand);
+        unsigned char *used = reinterpret_cast<unsigned char *>(q); q += align_up((size_t)n, 16);
+        GjState *state = reinterpret_cast<GjState *>(q);
+        int nn_i = n;
+        double *outp = a_inv;
+        void *args[] = {&W, &V, &nn_i, &outp, &piv, &dval, &cand, &used, &state};
+        WFO_CUDA(cudaLaunchCooperativeKernel((void *)gj_inverse_kernel, dim3(G), dim3(GJ_THREADS), args, 0, st));
+        ctx->launches++;
+        GjState hs;
+        WFO_CUDA(cudaMemcpyAsync(&hs, state, sizeof(hs), cudaMemcpyDeviceToHost, st));
+        WFO_CUDA(cudaStreamSynchronize(st));
+        ctx->last_inverse_pivoted = 1;
+        if (hs.singular) return set_err(WFO_ERR_NOCONV, "inverse: singular matrix (zero pivot column in the pivoted elimination)");
+    }
     return WFO_OK;
 }
 

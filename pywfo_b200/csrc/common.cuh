@@ -81,6 +81,9 @@ struct wfo_ctx {
     double *ns_slots;      // device: norms + per-iteration residuals of the Newton-Schulz inverse (128 doubles)
     double *h_slots;       // pinned host mirror
     int last_inverse_iters;
+    int last_inverse_pivoted;   // 1: the last inverse came from the pivoted Gauss-Jordan fallback
+    char *gj_buf;          // its bookkeeping
+    size_t gj_bytes;
     wfo::BaseInfo *h_info;  // pinned host copy of the base-block verdict
     cudaEvent_t ev_info;
     char *scratch;         // device arena, grown on demand

@@ -95,6 +95,8 @@ def _state_overlaps(semantics, sigma, bra_mos, ket_mos, bra_ci, ket_ci, occ, ci_
         if ao_ovlps not in ("bra", "ket"):
             raise KeyError(ao_ovlps)   # upstream: dict lookup, main.py:303
         side = _lib.AO_BRA if ao_ovlps == "bra" else _lib.AO_KET
+        if c_inv is not None:
+            side = _lib.AO_GIVEN   # the caller's inverse of that MO matrix (e.g. LAPACK's, exactly as upstream)
         rank, world = dist.world()
         in_library = dist.has_comm(ctx)   # the library all-gathers the ket side and all-reduces the result itself
         if world > 1 and not in_library and ctx.comm_world():

@@ -47,13 +47,19 @@ def test_mo_overlap(ctx, name):
     np.testing.assert_allclose(main.get_S_AO(g["bra_mos"], g["ket_mos"], "ket"), S_AO, rtol=1e-11, atol=1e-12)
 
 
-def test_mo_overlap_identity_big(ctx):
-    """pywfo/tests/test_pywfo.py:39-57 (test_big_mo_overlaps, n=1000 upstream; regenerated)."""
+@pytest.mark.parametrize("dim", [500, 1000])
+def test_mo_overlap_identity_big(ctx, dim):
+    """pywfo/tests/test_pywfo.py:39-57 (test_big_mo_overlaps: dim = 1000 upstream, same construction and the
+    same three variants and tolerance; the MOs are regenerated from the seed, upstream's are unseeded)."""
     from pywfo_b200 import helpers, main
-    mos = helpers.get_dummy_mos(500, 20180325)
+    mos = helpers.get_dummy_mos(dim, 20180325)
     inv = np.linalg.inv(mos)
     S_AO = inv.dot(inv.T)
-    np.testing.assert_allclose(main.moovlp(mos, mos, S_AO), np.eye(500), atol=1e-8)
+    for fn in (main.moovlp, main.moovlp_expl, main.moovlp_dots):
+        np.testing.assert_allclose(fn(mos, mos, S_AO), np.eye(dim), atol=1e-8)
+    # and with the inverse / S_AO from the device too (get_S_AO, main.py:301-311)
+    S_dev = main.get_S_AO(mos, mos, "ket")
+    np.testing.assert_allclose(main.moovlp(mos, mos, S_dev), np.eye(dim), atol=1e-8)
 
 
 def test_mo_overlap_rectangular(ctx):
@@ -510,6 +516,62 @@ def test_device_inverse_matches_lapack(ctx, n, cond):
     # forward error of any backward-stable inverse is O(eps * cond)
     assert np.abs(got - want).max() <= 1e-12 * cond * np.abs(want).max()
     assert np.abs(a @ got - np.eye(n)).max() <= 1e-11 * max(cond ** 0.5, 1.0)
+    assert ctx.last_inverse_info()[1] is False   # Newton-Schulz served these
+
+
+@pytest.mark.parametrize("n,cond", [(24, 1e8), (137, 1e10), (500, 1e10), (200, 1e13), (500, 1e13), (1000, 1e9)])
+def test_device_inverse_pivoted_fallback_is_lapack_grade(ctx, n, cond):
+    """pywfo/main.py:303 is np.linalg.inv = LAPACK with partial pivoting, which returns a result up to
+    cond ~ 1/eps.  Newton-Schulz stagnates above cond ~ 1e7 in FP64; the pivoted Gauss-Jordan fallback
+    must then deliver what LAPACK delivers.  Bound: an ABSOLUTE residual.  For an inverse computed by
+    Gaussian elimination with partial pivoting the LEFT residual |X A - I| is O(n eps cond) at worst and
+    in practice far smaller; LAPACK's own residual on the same matrix is measured here and the device
+    result may exceed it by at most 20x (and must stay below 1e-6 up to cond 1e10).  The element-wise
+    difference to LAPACK's inverse is bounded by the forward-error bound eps * cond * |X|."""
+    rng = np.random.default_rng(n + int(np.log10(cond)))
+    u, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    v, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    sv = np.logspace(0, -np.log10(cond), n)
+    a = (u * sv) @ v.T
+    got = ctx.inverse_host(a)
+    its, pivoted = ctx.last_inverse_info()
+    assert pivoted, f"expected the pivoted fallback at cond={cond:g} (Newton-Schulz ran {its} iterations)"
+    want = np.linalg.inv(a)
+    eye = np.eye(n)
+    res_dev = min(np.abs(got @ a - eye).max(), np.abs(a @ got - eye).max())
+    res_lap = min(np.abs(want @ a - eye).max(), np.abs(a @ want - eye).max())
+    assert res_dev <= max(20.0 * res_lap, 1e-9), (res_dev, res_lap)
+    if cond <= 1e10:
+        assert res_dev <= 1e-6, res_dev
+    assert np.abs(got - want).max() <= 50 * np.finfo(float).eps * cond * np.abs(want).max()
+
+
+def test_ill_conditioned_mos_through_the_whole_path(ctx):
+    """Ill-conditioned ket MOs (cond 1e9: Newton-Schulz gives up, the pivoted elimination takes over) through
+    overlaps_cache.  No reference golden can pin this regime: upstream forms S_MO = (bra S_AO) ket^T with
+    S_AO = inv inv^T, whose entries are ~cond^2 and cancel to O(1), so its own answer carries an error of
+    ~eps cond^2 (measured with the unmodified reference: max|S| = 6e8 instead of O(1) at cond 1e10).  What
+    can be pinned: the device-inverse path equals the same path fed with LAPACK's inverse, and both equal
+    the state overlaps computed from the exact S_MO = rot (bra = rot ket by construction)."""
+    from pywfo_b200 import helpers, main
+    from pywfo_b200 import _lib
+    rng = np.random.default_rng(7)
+    n_mo, occ, ns, cond = 40, 6, 3, 1e9
+    u, _ = np.linalg.qr(rng.standard_normal((n_mo, n_mo)))
+    v, _ = np.linalg.qr(rng.standard_normal((n_mo, n_mo)))
+    ket_mos = (u * np.logspace(0, -np.log10(cond), n_mo)) @ v.T
+    k = 0.02 * rng.standard_normal((n_mo, n_mo))
+    rot, _ = np.linalg.qr(np.eye(n_mo) + (k - k.T))
+    bra_mos = rot @ ket_mos
+    _, _, bci, kci = helpers.synthetic_case(3, n_mo, occ, ns, ns)
+    got = main.overlaps_cache(bra_mos, ket_mos, bci, kci, occ, ci_thresh=0.0, ao_ovlps="ket")
+    assert _lib.context().last_inverse_info()[1]
+    got_lapack = main.overlaps_cache(bra_mos, ket_mos, bci, kci, occ, ci_thresh=0.0, ao_ovlps="ket",
+                                     c_inv=np.linalg.inv(ket_mos))
+    want = orc.state_overlaps_factored(rot, occ, orc.signed_ci(bci, occ), orc.signed_ci(kci, occ), 1.0)
+    tol = 1e3 * np.finfo(float).eps * cond   # eps * cond: the error of ket Cinv - I
+    assert np.abs(got - want).max() <= tol * np.abs(want).max()
+    assert np.abs(got_lapack - want).max() <= tol * np.abs(want).max()
 
 
 def test_device_inverse_reports_singular(ctx):
