@@ -176,6 +176,25 @@ int wfo_trajectory_ci_host(wfo_ctx *ctx, const double *mos, const double *ci, in
                            int n_occ, int n_states, double ci_thresh, int semantics, int tier,
                            int ao_side, const int32_t *pairs, int n_pairs, int rank, int world,
                            double *out, int32_t *info);
+/* ---- general determinant lists ----------------------------------
+ * replaces pywfo/dets.py:191-198 (precompute) + :279-283 (contraction) for ARBITRARY alpha/beta block lists
+ * (the on-disk wfoverlap decks; the reference's CI-tensor entry dets.wfoverlap is wfo_state_overlaps_*):
+ *   out[i][j] = sum_{d,e} bc[d][i] alpha[ba_of[d]][ka_of[e]] beta[bb_of[d]][kb_of[e]] kc[e][j]
+ * alpha[x][y] = det(S_MO[ba_blocks[x]][:, ka_blocks[y]]) (n_alpha x n_alpha minors), beta likewise.
+ * s_mo (n_rows x n_cols, host); *_blocks: unique occupation lists; *_of: block of every determinant;
+ * bc (nd_b x ns_b), kc (nd_k x ns_k): coefficients with the string parity of dets.py:42-96 folded in.
+ * Bra blocks that share all but their LAST orbital (dets.py:119-156 `super_map`) are served by one pivoted
+ * factorisation per (super-block, ket block) and one dot product per member (Laplace expansion along the
+ * last row, laplace.py:3-16); the block tables and the contraction stay on the device -- only `out`
+ * comes back.  info (4 ints or NULL): super-blocks used, blocks served by them, blocks redone by
+ * brute force because the shared factorisation was ill conditioned, 0. */
+int wfo_overlap_from_lists_host(wfo_ctx *ctx, const double *s_mo, int n_rows, int n_cols, int n_alpha,
+                                const int32_t *ba_blocks, int nba, const int32_t *ka_blocks, int nka, int n_beta,
+                                const int32_t *bb_blocks, int nbb, const int32_t *kb_blocks, int nkb, int nd_b,
+                                const int32_t *ba_of, const int32_t *bb_of, const double *bc, int ns_b, int nd_k,
+                                const int32_t *ka_of, const int32_t *kb_of, const double *kc, int ns_k, double *out,
+                                int32_t *info);
+
 /* ---- K5: the one collective of the path, inside the library ------------------
  * (new: the reference is single-process).  One process per GPU of ONE node.
  * wfo_comm_init is collective: every rank calls it with the same `world` and the same job-unique

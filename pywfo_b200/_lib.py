@@ -55,6 +55,9 @@ SIGNATURES = {
                                       C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
     "wfo_trajectory_ci_host": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
                                          C.c_int, c_vp, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
+    "wfo_overlap_from_lists_host": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, c_vp, C.c_int, C.c_int,
+                                              c_vp, C.c_int, c_vp, C.c_int, C.c_int, c_vp, c_vp, c_vp, C.c_int, C.c_int,
+                                              c_vp, c_vp, c_vp, C.c_int, c_vp, c_vp]),
     "wfo_comm_init": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_char_p, C.c_longlong]),
     "wfo_comm_destroy": (C.c_int, [c_vp]),
     "wfo_comm_world": (C.c_int, [c_vp]),
@@ -231,6 +234,33 @@ class Context:
         if rc == 4:
             raise ValueError("not enough values to unpack (expected 2, got 0)")   # pywfo/main.py:186
         check(rc)
+        return out, info
+
+    def overlap_from_lists_host(self, s_mo, alpha, beta, bra_coeffs, ket_coeffs):
+        """General determinant lists.  ``alpha`` / ``beta`` = (bra_blocks, ket_blocks, bra_of, ket_of) or None
+        (no electrons of that spin); coefficients (n_dets, n_states) with the string parity folded in.
+        Returns (out (ns_bra, ns_ket), info)."""
+        s_mo, bc, kc = as_f64(s_mo), as_f64(bra_coeffs), as_f64(ket_coeffs)
+        nd_b, ns_b = bc.shape
+        nd_k, ns_k = kc.shape
+        args = []
+        keep = []
+        for spin in (alpha, beta):
+            if spin is None:
+                args.append((0, None, 0, None, 0, None, None))
+                continue
+            bb, kb, bof, kof = (as_i32(x) for x in spin)
+            bb, kb = np.atleast_2d(bb), np.atleast_2d(kb)
+            if bof.shape != (nd_b,) or kof.shape != (nd_k,) or bb.shape[1] != kb.shape[1]:
+                raise ValueError("block maps do not match the determinant lists")
+            keep += [bb, kb, bof, kof]
+            args.append((bb.shape[1], _hptr(bb), bb.shape[0], _hptr(kb), kb.shape[0], _hptr(bof), _hptr(kof)))
+        (na, ba, nba, ka, nka, baof, kaof), (nb, bbp, nbb, kbp, nkb, bbof, kbof) = args
+        out = np.empty((ns_b, ns_k))
+        info = np.zeros(4, dtype=np.int32)
+        check(self.lib.wfo_overlap_from_lists_host(self.handle, _hptr(s_mo), s_mo.shape[0], s_mo.shape[1], na, ba, nba, ka,
+                                                   nka, nb, bbp, nbb, kbp, nkb, nd_b, baof, bbof, _hptr(bc), ns_b, nd_k,
+                                                   kaof, kbof, _hptr(kc), ns_k, _hptr(out), _hptr(info)))
         return out, info
 
     def trajectory_ci_host(self, mos, ci, n_occ, pairs, ci_thresh, semantics=0, tier="auto", ao_side=AO_KET,

@@ -4,6 +4,10 @@
 #include <new>
 #include <vector>
 
+#include <algorithm>
+#include <map>
+#include <vector>
+
 #include "common.cuh"
 #include "comm.cuh"
 #include "det_lu_warp.cuh"
@@ -11,6 +15,7 @@
 #include "det_lu_wpm.cuh"
 #include "gemm_f64.cuh"
 #include "inverse_gj.cuh"
+#include "lists.cuh"
 #include "lu_base.cuh"
 #include "misc_kernels.cuh"
 #include "pair_update.cuh"
@@ -641,6 +646,192 @@ int wfo_last_inverse_info(const wfo_ctx *ctx, int *iterations, int *pivoted) {
     if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL");
     if (iterations) *iterations = ctx->last_inverse_iters;
     if (pivoted) *pivoted = ctx->last_inverse_pivoted;
+    return WFO_OK;
+}
+
+/* ------------------------------------------------------------ general determinant lists */
+namespace {
+
+// Block-determinant table D (nb x nk) of one spin on the device, with super-block reuse on the bra side:
+// bra blocks that share their first n-1 orbitals (pywfo/dets.py:119-156, `super_map`) are served by one
+// pivoted factorisation per (super-block, ket block) plus one dot product per member
+// (cofactor_rows_kernel); super-blocks with fewer than SUPER_MIN members and everything the cofactor path
+// flags as ill conditioned go through the brute-force LU kernels.  stats: [super-blocks used, blocks
+// served by them, blocks redone by brute force].
+constexpr int SUPER_MIN = 4;
+
+int det_table_super(wfo_ctx *ctx, const double *d_S, int ld_s, int n, const int32_t *h_bblk, int nb,
+                    const int32_t *d_bblk, const int32_t *d_kblk, int nk, double *d_D, Arena &ar, cudaStream_t st,
+                    int *stats) {
+    stats[0] = stats[1] = stats[2] = 0;
+    if (nb == 0 || nk == 0) return WFO_OK;
+    std::vector<int> solo;   // blocks that take the brute-force path
+    std::vector<int32_t> rows_rep, mem_off(1, 0), mem_block, mem_row;
+    if (n >= 2 && n <= LUB_MAXN) {
+        std::map<std::vector<int32_t>, std::vector<int>> groups;   // prefix (n-1 orbitals) -> blocks
+        for (int b = 0; b < nb; b++)
+            groups[std::vector<int32_t>(h_bblk + (size_t)b * n, h_bblk + (size_t)b * n + n - 1)].push_back(b);
+        for (auto &g : groups) {
+            if ((int)g.second.size() < SUPER_MIN) {
+                solo.insert(solo.end(), g.second.begin(), g.second.end());
+                continue;
+            }
+            const int rep = g.second[0];
+            rows_rep.insert(rows_rep.end(), h_bblk + (size_t)rep * n, h_bblk + (size_t)rep * n + n);
+            for (int b : g.second) {
+                mem_block.push_back(b);
+                mem_row.push_back(h_bblk[(size_t)b * n + n - 1]);
+            }
+            mem_off.push_back((int32_t)mem_block.size());
+        }
+    } else {
+        for (int b = 0; b < nb; b++) solo.push_back(b);
+    }
+    const int n_super = (int)mem_off.size() - 1;
+    stats[0] = n_super;
+    stats[1] = (int)mem_block.size();
+
+    auto brute = [&](const std::vector<int> &blocks) -> int {   // rows `blocks` of D by one LU per pair
+        if (blocks.empty()) return WFO_OK;
+        const int m = (int)blocks.size();
+        if (m == nb) return det_table(ctx, d_S, ld_s, n, d_bblk, nb, d_kblk, nk, d_D, st);
+        std::vector<int32_t> lists((size_t)m * n), row_of(m);
+        for (int i = 0; i < m; i++) {
+            std::copy(h_bblk + (size_t)blocks[i] * n, h_bblk + (size_t)blocks[i] * n + n, lists.begin() + (size_t)i * n);
+            row_of[i] = blocks[i];
+        }
+        int32_t *d_lists = ar.take<int32_t>((size_t)m * n), *d_row_of = ar.take<int32_t>(m);
+        double *d_tmp = ar.take<double>((size_t)m * nk);
+        WFO_CUDA(cudaMemcpyAsync(d_lists, lists.data(), lists.size() * 4, cudaMemcpyHostToDevice, st));
+        WFO_CUDA(cudaMemcpyAsync(d_row_of, row_of.data(), row_of.size() * 4, cudaMemcpyHostToDevice, st));
+        WFO_CUDA(cudaStreamSynchronize(st));   // the staging vectors go out of scope
+        WFO_TRY(det_table(ctx, d_S, ld_s, n, d_lists, m, d_kblk, nk, d_tmp, st));
+        const long long tot = (long long)m * nk;
+        scatter_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d_tmp, m, nk, d_row_of, d_D, nk);
+        WFO_LAUNCH_CHECK(ctx);
+        return WFO_OK;
+    };
+    WFO_TRY(brute(solo));
+    if (n_super > 0) {
+        int32_t *d_rep = ar.take<int32_t>(rows_rep.size()), *d_off = ar.take<int32_t>(mem_off.size()),
+                *d_mb = ar.take<int32_t>(mem_block.size()), *d_mr = ar.take<int32_t>(mem_row.size());
+        unsigned char *d_flags = ar.take<unsigned char>((size_t)n_super * nk);
+        WFO_CUDA(cudaMemcpyAsync(d_rep, rows_rep.data(), rows_rep.size() * 4, cudaMemcpyHostToDevice, st));
+        WFO_CUDA(cudaMemcpyAsync(d_off, mem_off.data(), mem_off.size() * 4, cudaMemcpyHostToDevice, st));
+        WFO_CUDA(cudaMemcpyAsync(d_mb, mem_block.data(), mem_block.size() * 4, cudaMemcpyHostToDevice, st));
+        WFO_CUDA(cudaMemcpyAsync(d_mr, mem_row.data(), mem_row.size() * 4, cudaMemcpyHostToDevice, st));
+        static bool attr_done[64];
+        if (!attr_done[ctx->device & 63]) {
+            WFO_CUDA(cudaFuncSetAttribute(cofactor_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)lub_smem_bytes(LUB_MAXN)));
+            attr_done[ctx->device & 63] = true;
+        }
+        const long long pairs = (long long)n_super * nk;
+        int per_sm = 1;
+        WFO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cofactor_rows_kernel, LUB_THREADS, lub_smem_bytes(n)));
+        const unsigned grid = (unsigned)std::min<long long>(pairs, (long long)ctx->sm_count * (per_sm < 1 ? 1 : per_sm));
+        cofactor_rows_kernel<<<grid, LUB_THREADS, lub_smem_bytes(n), st>>>(d_S, ld_s, n, d_rep, n_super, d_off, d_mb, d_mr,
+                                                                          d_kblk, nk, d_D, nk, d_flags);
+        WFO_LAUNCH_CHECK(ctx);
+        std::vector<unsigned char> flags((size_t)n_super * nk);
+        WFO_CUDA(cudaMemcpyAsync(flags.data(), d_flags, flags.size(), cudaMemcpyDeviceToHost, st));
+        WFO_CUDA(cudaStreamSynchronize(st));
+        std::vector<int> redo;   // every member of a super-block with a flagged ket block: the whole rows again
+        for (int sb = 0; sb < n_super; sb++) {
+            bool bad = false;
+            for (int k = 0; k < nk && !bad; k++) bad = flags[(size_t)sb * nk + k] != 0;
+            if (bad)
+                for (int m = mem_off[sb]; m < mem_off[sb + 1]; m++) redo.push_back(mem_block[m]);
+        }
+        stats[2] = (int)redo.size();
+        WFO_TRY(brute(redo));
+    }
+    return WFO_OK;
+}
+
+}  // namespace
+
+int wfo_overlap_from_lists_host(wfo_ctx *ctx, const double *s_mo, int n_rows, int n_cols, int n_alpha,
+                                const int32_t *ba_blocks, int nba, const int32_t *ka_blocks, int nka, int n_beta,
+                                const int32_t *bb_blocks, int nbb, const int32_t *kb_blocks, int nkb, int nd_b,
+                                const int32_t *ba_of, const int32_t *bb_of, const double *bc, int ns_b, int nd_k,
+                                const int32_t *ka_of, const int32_t *kb_of, const double *kc, int ns_k, double *out,
+                                int32_t *info) {
+    if (!ctx || !s_mo || !bc || !kc || !out) return set_err(WFO_ERR_ARG, "overlap_from_lists: NULL argument");
+    if (n_rows < 1 || n_cols < 1 || n_alpha < 0 || n_beta < 0 || nd_b < 0 || nd_k < 0 || ns_b < 1 || ns_k < 1)
+        return set_err(WFO_ERR_ARG, "overlap_from_lists: bad sizes");
+    if (n_alpha > 128 || n_beta > 128) return set_err(WFO_ERR_ARG, "overlap_from_lists: at most 128 electrons per spin");
+    if ((n_alpha > 0 && (!ba_blocks || !ka_blocks || !ba_of || !ka_of)) || (n_beta > 0 && (!bb_blocks || !kb_blocks || !bb_of || !kb_of)))
+        return set_err(WFO_ERR_ARG, "overlap_from_lists: block lists / maps missing");
+    auto in_range = [](const int32_t *v, size_t cnt, int hi) {
+        for (size_t i = 0; i < cnt; i++)
+            if (v[i] < 0 || v[i] >= hi) return false;
+        return true;
+    };
+    if (n_alpha > 0 && !(in_range(ba_blocks, (size_t)nba * n_alpha, n_rows) && in_range(ka_blocks, (size_t)nka * n_alpha, n_cols) &&
+                         in_range(ba_of, nd_b, nba) && in_range(ka_of, nd_k, nka)))
+        return set_err(WFO_ERR_ARG, "overlap_from_lists: alpha index out of range");
+    if (n_beta > 0 && !(in_range(bb_blocks, (size_t)nbb * n_beta, n_rows) && in_range(kb_blocks, (size_t)nkb * n_beta, n_cols) &&
+                        in_range(bb_of, nd_b, nbb) && in_range(kb_of, nd_k, nkb)))
+        return set_err(WFO_ERR_ARG, "overlap_from_lists: beta index out of range");
+    if (info) info[0] = info[1] = info[2] = info[3] = 0;
+    if (nd_b == 0 || nd_k == 0) {
+        memset(out, 0, (size_t)ns_b * ns_k * sizeof(double));
+        return WFO_OK;
+    }
+    WFO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    // arena: inputs, tables, temporaries of the brute-force / cofactor paths (generous upper bound)
+    const size_t nS = (size_t)n_rows * n_cols;
+    size_t bytes = 0;
+    auto add = [&](size_t b) { bytes += align_up(b, 256); };
+    add(nS * 8);
+    for (int spin = 0; spin < 2; spin++) {
+        const int ne = spin ? n_beta : n_alpha, nb = spin ? nbb : nba, nk = spin ? nkb : nka;
+        if (ne == 0) continue;
+        add((size_t)nb * ne * 4); add((size_t)nk * ne * 4); add((size_t)nb * nk * 8);
+        add((size_t)nd_b * 4); add((size_t)nd_k * 4);
+        // brute (twice: solo + redo): lists, row map, temp table; cofactor: representatives, members, flags
+        add((size_t)nb * ne * 4); add((size_t)nb * 4); add((size_t)nb * nk * 8);
+        add((size_t)nb * ne * 4); add((size_t)nb * 4); add((size_t)nb * nk * 8);
+        add((size_t)nb * ne * 4); add((size_t)(nb + 1) * 4); add((size_t)nb * 4); add((size_t)nb * 4); add((size_t)nb * nk);
+    }
+    add((size_t)nd_b * ns_b * 8); add((size_t)nd_k * ns_k * 8); add((size_t)nd_k * ns_b * 8); add((size_t)ns_b * ns_k * 8);
+    WFO_TRY(ensure_scratch(ctx, bytes + 4096));
+    Arena ar{ctx->scratch, ctx->scratch_bytes, 0};
+    double *d_S = ar.take<double>(nS);
+    WFO_CUDA(cudaMemcpyAsync(d_S, s_mo, nS * 8, cudaMemcpyHostToDevice, st));
+    double *d_tab[2] = {nullptr, nullptr};
+    int32_t *d_bof[2] = {nullptr, nullptr}, *d_kof[2] = {nullptr, nullptr};
+    int ld_tab[2] = {0, 0};
+    for (int spin = 0; spin < 2; spin++) {
+        const int ne = spin ? n_beta : n_alpha, nb = spin ? nbb : nba, nk = spin ? nkb : nka;
+        if (ne == 0) continue;
+        const int32_t *hb = spin ? bb_blocks : ba_blocks, *hk = spin ? kb_blocks : ka_blocks;
+        int32_t *d_b = ar.take<int32_t>((size_t)nb * ne), *d_k = ar.take<int32_t>((size_t)nk * ne);
+        d_tab[spin] = ar.take<double>((size_t)nb * nk);
+        ld_tab[spin] = nk;
+        d_bof[spin] = ar.take<int32_t>(nd_b);
+        d_kof[spin] = ar.take<int32_t>(nd_k);
+        WFO_CUDA(cudaMemcpyAsync(d_b, hb, (size_t)nb * ne * 4, cudaMemcpyHostToDevice, st));
+        WFO_CUDA(cudaMemcpyAsync(d_k, hk, (size_t)nk * ne * 4, cudaMemcpyHostToDevice, st));
+        WFO_CUDA(cudaMemcpyAsync(d_bof[spin], spin ? bb_of : ba_of, (size_t)nd_b * 4, cudaMemcpyHostToDevice, st));
+        WFO_CUDA(cudaMemcpyAsync(d_kof[spin], spin ? kb_of : ka_of, (size_t)nd_k * 4, cudaMemcpyHostToDevice, st));
+        int stats[3];
+        WFO_TRY(det_table_super(ctx, d_S, n_cols, ne, hb, nb, d_b, d_k, nk, d_tab[spin], ar, st, stats));
+        if (info) { info[0] += stats[0]; info[1] += stats[1]; info[2] += stats[2]; }
+    }
+    double *d_bc = ar.take<double>((size_t)nd_b * ns_b), *d_kc = ar.take<double>((size_t)nd_k * ns_k);
+    double *d_tmp = ar.take<double>((size_t)nd_k * ns_b), *d_out = ar.take<double>((size_t)ns_b * ns_k);
+    WFO_CUDA(cudaMemcpyAsync(d_bc, bc, (size_t)nd_b * ns_b * 8, cudaMemcpyHostToDevice, st));
+    WFO_CUDA(cudaMemcpyAsync(d_kc, kc, (size_t)nd_k * ns_k * 8, cudaMemcpyHostToDevice, st));
+    lists_contract_kernel<<<nd_k, 256, 0, st>>>(d_tab[0], ld_tab[0], d_tab[1], ld_tab[1], d_bof[0], d_bof[1], nd_b, d_kof[0],
+                                                d_kof[1], d_bc, ns_b, d_tmp);
+    WFO_LAUNCH_CHECK(ctx);
+    // out (ns_b x ns_k) = tmp^T (ns_b x nd_k) kc (nd_k x ns_k)
+    WFO_TRY(gemm(ctx, true, false, ns_b, ns_k, nd_k, 1.0, d_tmp, ns_b, d_kc, ns_k, 0.0, d_out, ns_k, 0, 0, st));
+    WFO_CUDA(cudaMemcpyAsync(out, d_out, (size_t)ns_b * ns_k * 8, cudaMemcpyDeviceToHost, st));
+    WFO_CUDA(cudaStreamSynchronize(st));
     return WFO_OK;
 }
 

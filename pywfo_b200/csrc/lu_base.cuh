@@ -48,10 +48,11 @@ inline size_t lub_smem_bytes(int n) { return (size_t)n * LUB_LDS * sizeof(double
 //     per elimination step, and the warp that owns the next column updates that column first,
 //     searches its pivot and publishes it while the other warps still work on the current step;
 //   * det / min / max pivot are accumulated by the owning warps and combined at the end.
-__global__ void __launch_bounds__(LUB_THREADS)
-base_inverse_kernel(const double *__restrict__ A_src, int ld_src, int n, double *__restrict__ Ai_out, int ld_out,
-                    BaseInfo *__restrict__ info) {
-    extern __shared__ __align__(16) double lub_tile[];    // n x LUB_LDS
+// The factorisation itself: lub_tile (n x n, row stride LUB_LDS, shared memory) holds A on entry and, unless
+// the matrix is singular, A^-1 on return (all threads synchronised).  Every thread returns det(A), min/max |pivot|
+// and the singular flag.  Shared by base_inverse_kernel (one matrix) and cofactor_rows_kernel (a batch).
+__device__ __forceinline__ void lub_invert_tile(double *lub_tile, int n, double &det_out, double &min_out, double &max_out,
+                                                int &sing_out) {
     __shared__ __align__(16) double mcol[2][LUB_MAXN];    // multiplier column, double buffered by step parity
     __shared__ __align__(16) double prow[LUB_WARPS][LUB_CS];   // warp-private: this warp's part of the pivot row
     __shared__ double prd[2];                             // reciprocal of the pivot
@@ -66,13 +67,6 @@ base_inverse_kernel(const double *__restrict__ A_src, int ld_src, int n, double 
     long long t_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long t_prev = clock64();
 #endif
-
-    // coalesced load through the staging tile
-    for (int idx = tid; idx < n * n; idx += LUB_THREADS) {
-        const int r = idx / n, c = idx - r * n;
-        lub_tile[r * LUB_LDS + c] = A_src[(size_t)r * ld_src + c];
-    }
-    __syncthreads();
     double a[LUB_RS][LUB_CS];
     unsigned donemask = 0;   // bit s: row 4 lane + s is a used pivot row or beyond n
 #pragma unroll
@@ -240,21 +234,94 @@ base_inverse_kernel(const double *__restrict__ A_src, int ld_src, int n, double 
     int inv = 0;
     if (!tsing && tid < n)
         for (int k = tid + 1; k < n; k++) inv += piv_of_col[k] < piv_of_col[tid];
-    const int par = __syncthreads_count(inv & 1) & 1;
-    if (!tsing)
-        for (int idx = tid; idx < n * n; idx += LUB_THREADS) {
-            const int r = idx / n, c = idx - r * n;
-            Ai_out[(size_t)r * ld_out + c] = lub_tile[r * LUB_LDS + c];
-        }
+    const int par = __syncthreads_count(inv & 1) & 1;   // also: the permuted inverse in lub_tile is complete
     LUB_T(9);
 #ifdef WFO_LUB_CLOCKS
     if (tid == 32) for (int i = 0; i < 10; i++) g_lub_clk[i] = t_acc[i];
 #endif
+    det_out = tsing ? 0.0 : (par ? -tdet : tdet);
+    min_out = tmin;
+    max_out = tmax;
+    sing_out = tsing;
+}
+
+// A_src: n x n block with leading dimension ld_src.  Ai_out: n x n, leading dimension ld_out.
+// Dynamic shared memory: lub_smem_bytes(n) (staging tile for coalesced load / store).
+__global__ void __launch_bounds__(LUB_THREADS)
+base_inverse_kernel(const double *__restrict__ A_src, int ld_src, int n, double *__restrict__ Ai_out, int ld_out,
+                    BaseInfo *__restrict__ info) {
+    extern __shared__ __align__(16) double lub_tile[];    // n x LUB_LDS
+    const int tid = threadIdx.x;
+    // coalesced load through the staging tile
+    for (int idx = tid; idx < n * n; idx += LUB_THREADS) {
+        const int r = idx / n, c = idx - r * n;
+        lub_tile[r * LUB_LDS + c] = A_src[(size_t)r * ld_src + c];
+    }
+    __syncthreads();
+    double det, minp, maxp;
+    int sing;
+    lub_invert_tile(lub_tile, n, det, minp, maxp, sing);
+    if (!sing)
+        for (int idx = tid; idx < n * n; idx += LUB_THREADS) {
+            const int r = idx / n, c = idx - r * n;
+            Ai_out[(size_t)r * ld_out + c] = lub_tile[r * LUB_LDS + c];
+        }
     if (tid == 0) {
-        info->det = tsing ? 0.0 : (par ? -tdet : tdet);
-        info->min_piv = tmin;
-        info->max_piv = tmax;
-        info->singular = tsing;
+        info->det = det;
+        info->min_piv = minp;
+        info->max_piv = maxp;
+        info->singular = sing;
+    }
+}
+
+// Super-blocks of a general determinant list (pywfo/dets.py:119-156: blocks that are equal up to the LAST
+// orbital; the reference prepares `super_map` and counts the super-blocks, dets.py:233-236, but then takes one
+// np.linalg.det per block pair): the n - 1 shared rows are factored ONCE per (super-block, ket block) and
+// every member costs one dot product -- the Laplace expansion along the last row that laplace.py sketches,
+//     det([A; r_m]) = sum_j r_m[j] C_j,   C_j = cofactor of (n, j) = det(M) (M^-1)[j][n]   for M = [A; r_rep],
+// with the cofactors taken from the pivoted Gauss-Jordan inverse of the representative member's matrix
+// (the cofactors of the last row do not depend on that row).
+// One CTA per (super-block, ket block).  rows_rep: (n_super x n) index lists of the representatives;
+// mem_off (n_super + 1), mem_block / mem_row: member block ids and their last-row indices; cols: (n_kblk x n).
+// D (n_bblk x n_kblk, row stride ld_d) gets the members' determinants; flags (n_super x n_kblk) is set
+// when the representative's matrix is singular or ill conditioned (pivot ratio below 1e-6): the caller
+// recomputes those members by brute force.
+__global__ void __launch_bounds__(LUB_THREADS)
+cofactor_rows_kernel(const double *__restrict__ S, int ld_s, int n, const int32_t *__restrict__ rows_rep, int n_super,
+                     const int32_t *__restrict__ mem_off, const int32_t *__restrict__ mem_block,
+                     const int32_t *__restrict__ mem_row, const int32_t *__restrict__ cols, int n_kblk,
+                     double *__restrict__ D, int ld_d, unsigned char *__restrict__ flags) {
+    extern __shared__ __align__(16) double lub_tile[];    // n x LUB_LDS
+    __shared__ double cof[LUB_MAXN];
+    __shared__ int colv[LUB_MAXN];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (long long pair = blockIdx.x; pair < (long long)n_super * n_kblk; pair += gridDim.x) {
+        const int sb = (int)(pair / n_kblk), kb = (int)(pair - (long long)sb * n_kblk);
+        const int32_t *rl = rows_rep + (size_t)sb * n, *cl = cols + (size_t)kb * n;
+        __syncthreads();   // the previous pair is done with the tile
+        for (int idx = tid; idx < n * n; idx += LUB_THREADS) {
+            const int r = idx / n, c = idx - r * n;
+            lub_tile[r * LUB_LDS + c] = __ldg(S + (size_t)rl[r] * ld_s + cl[c]);
+        }
+        if (tid < n) colv[tid] = cl[tid];
+        __syncthreads();
+        double det, minp, maxp;
+        int sing;
+        lub_invert_tile(lub_tile, n, det, minp, maxp, sing);
+        const bool bad = sing || !(minp > 1e-6 * maxp);
+        if (tid == 0) flags[pair] = bad ? 1 : 0;
+        if (bad) continue;   // uniform
+        if (tid < n) cof[tid] = det * lub_tile[tid * LUB_LDS + (n - 1)];
+        __syncthreads();
+        // members: one warp per member, dot product of its last row with the cofactors
+        for (int m = mem_off[sb] + warp; m < mem_off[sb + 1]; m += LUB_WARPS) {
+            const double *srow = S + (size_t)mem_row[m] * ld_s;
+            double acc = 0.0;
+            for (int j = lane; j < n; j += 32) acc = fma(__ldg(srow + colv[j]), cof[j], acc);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) D[(size_t)mem_block[m] * ld_d + kb] = acc;
+        }
     }
 }
 

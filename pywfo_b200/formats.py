@@ -175,7 +175,8 @@ def _blocks(index_lists):
     return np.array(list(uniq.keys()), dtype=np.int32).reshape(len(uniq), -1), which
 
 
-def overlap_from_determinants(bra_mos, ket_mos, S_AO, bra_dets, bra_coeffs, ket_dets, ket_coeffs, device=None):
+def overlap_from_determinants(bra_mos, ket_mos, S_AO, bra_dets, bra_coeffs, ket_dets, ket_coeffs, device=None,
+                              return_info=False):
     """State overlaps ``<bra_i|ket_j>`` of two determinant lists (strings + (ndets, nstates)
     coefficients).  Closed- or open-shell: alpha and beta blocks are treated separately."""
     from . import _lib
@@ -193,10 +194,15 @@ def overlap_from_determinants(bra_mos, ket_mos, S_AO, bra_dets, bra_coeffs, ket_
     bc, (ba_blk, ba_of), (bb_blk, bb_of) = prep(bra_dets, bra_coeffs)
     kc, (ka_blk, ka_of), (kb_blk, kb_of) = prep(ket_dets, ket_coeffs)
     s_mo = ctx.smo_host(bra_mos, S_AO, ket_mos)                       # dets.py:264
-    alpha = ctx.det_table_host(s_mo, ba_blk, ka_blk) if n_alpha else np.ones((len(ba_blk), len(ka_blk)))
-    beta = ctx.det_table_host(s_mo, bb_blk, kb_blk) if n_beta else np.ones((len(bb_blk), len(kb_blk)))
-    SS = alpha[np.ix_(ba_of, ka_of)] * beta[np.ix_(bb_of, kb_of)]      # dets.py:280
-    return bc.T @ SS @ kc                                              # dets.py:279-283
+    # block determinants (dets.py:191-198, with super-block reuse: dets.py:119-156) and the contraction
+    # (dets.py:279-283) in one library call: neither table nor the determinant x determinant matrix
+    # of dets.py:280 comes back to the host
+    alpha = (ba_blk, ka_blk, ba_of, ka_of) if n_alpha else None
+    beta = (bb_blk, kb_blk, bb_of, kb_of) if n_beta else None
+    out, info = ctx.overlap_from_lists_host(s_mo, alpha, beta, bc, kc)
+    if return_info:
+        return out, {"super_blocks": int(info[0]), "blocks_via_super": int(info[1]), "blocks_redone": int(info[2])}
+    return out
 
 
 def overlap_from_deck(directory, a_mo="a_mo", b_mo="b_mo", ao_ovlp="ao_ovlp", a_det="dets_a_spin_adapted",

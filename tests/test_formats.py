@@ -88,3 +88,94 @@ def test_general_determinant_lists_reproduce_wfoverlap(name):
     got = fm.overlap_from_determinants(g["bra_mos"], g["ket_mos"], S_AO, bd, bc, kd, kc)
     want = g["ref_wfoverlap"]
     np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-12 * np.abs(want).max())
+
+
+CYT = os.path.join(GOLDEN, "ref_cytosin")
+
+
+def test_read_cytosine_deck():
+    deck = fm.read_ciovl_input(os.path.join(CYT, "ciovl_no_gs_loose_zeroed.in"))
+    assert deck["a_mo"] == "mos.1" and deck["b_det"] == "dets_no_gs_loose_zeroed.2" and deck["mix_aoovl"] == "ao_ovl"
+    mos = fm.read_turbomole_mos(os.path.join(CYT, deck["a_mo"]))
+    S = fm.read_ao_overlap(os.path.join(CYT, deck["mix_aoovl"]))
+    assert mos.shape == (137, 137) and S.shape == (137, 137)
+    dets, coeffs = fm.read_dets(os.path.join(CYT, deck["a_det"]))
+    assert len(dets) == 6 and coeffs.shape == (6, 2) and all(len(d) == 137 for d in dets)
+    # MOs are orthonormal in the AO metric of their own geometry only approximately for a mixed overlap
+    assert np.isfinite(mos).all() and np.isfinite(S).all()
+
+
+@pytest.mark.gpu
+def test_cytosine_deck_from_disk_on_gpu():
+    """pywfo/tests/ref_cytosin/ciovl_no_gs_loose_zeroed.in end to end from disk: 137 MOs, 29 electrons per spin,
+    open-shell strings.  Checker: oracle (LAPACK determinants per block pair) on the same parsed inputs."""
+    deck = fm.read_ciovl_input(os.path.join(CYT, "ciovl_no_gs_loose_zeroed.in"))
+    got = fm.overlap_from_deck(CYT, a_mo=deck["a_mo"], b_mo=deck["b_mo"], ao_ovlp=deck["mix_aoovl"],
+                               a_det=deck["a_det"], b_det=deck["b_det"])
+    a, b = fm.read_turbomole_mos(os.path.join(CYT, deck["a_mo"])), fm.read_turbomole_mos(os.path.join(CYT, deck["b_mo"]))
+    S = fm.read_ao_overlap(os.path.join(CYT, deck["mix_aoovl"]))
+    bd, bc = fm.read_dets(os.path.join(CYT, deck["a_det"]))
+    kd, kc = fm.read_dets(os.path.join(CYT, deck["b_det"]))
+    n_alpha = bd[0].count("a") + bd[0].count("d")
+    Smo = orc.mo_overlap(a, b, S)
+    pb, ba, bb = zip(*(fm.expand_det_string(d, n_alpha) for d in bd))
+    pk, ka, kb = zip(*(fm.expand_det_string(d, n_alpha) for d in kd))
+    want = orc.ref_overlap_from_determinants(Smo, ba, bb, bc * np.array(pb)[:, None], ka, kb, kc * np.array(pk)[:, None])
+    assert got.shape == (2, 2)
+    np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-12 * np.abs(want).max())
+    assert np.abs(want).max() > 0.1   # neighbouring geometries: the states overlap strongly
+
+
+def _cis_strings(n_mo, occ, excitations):
+    """Closed-shell reference with single alpha excitations (f -> occ + t) as occupation strings."""
+    out = []
+    for f, t in excitations:
+        s = ["d"] * occ + ["e"] * (n_mo - occ)
+        s[f] = "b"
+        s[occ + t] = "a"
+        out.append("".join(s))
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("occ,n_mo", [(4, 30), (9, 40), (33, 60), (64, 90), (100, 125), (128, 150)])
+def test_super_blocks_share_one_factorisation(occ, n_mo):
+    """Lists whose blocks differ only in the LAST orbital (pywfo/dets.py:119-156): the bra excitations out of the
+    two highest occupied orbitals into every virtual give two super-blocks of n_virt members each; they must
+    be served by the shared factorisation and equal the brute-force / LAPACK values."""
+    from pywfo_b200 import helpers
+    np.random.seed(occ)
+    _, bra_mos, ket_mos = helpers.get_bra_ket_dummy_mos(n_mo, occ)
+    S_AO = orc.get_S_AO(bra_mos, ket_mos, "ket")
+    virt = n_mo - occ
+    rng = np.random.default_rng(occ)
+    bra_exc = [(occ - 1, t) for t in range(virt)] + [(occ - 2, t) for t in range(virt)] + [(0, 1), (1, 0)]
+    ket_exc = [(int(rng.integers(occ)), int(rng.integers(virt))) for _ in range(9)]
+    ket_exc = list(dict.fromkeys(ket_exc))
+    bd, kd = _cis_strings(n_mo, occ, bra_exc), _cis_strings(n_mo, occ, ket_exc)
+    bc, kc = rng.standard_normal((len(bd), 3)), rng.standard_normal((len(kd), 2))
+    got, info = fm.overlap_from_determinants(bra_mos, ket_mos, S_AO, bd, bc, kd, kc, return_info=True)
+    want = _oracle_from_strings(bra_mos, ket_mos, S_AO, bd, bc, kd, kc)
+    np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-12 * np.abs(want).max())
+    assert info["super_blocks"] >= 2 and info["blocks_via_super"] >= 2 * virt and info["blocks_redone"] == 0
+
+
+@pytest.mark.gpu
+def test_super_block_with_singular_representative_is_redone():
+    """The shared factorisation uses the first member's matrix; when that one is singular (here: its last row
+    equals one of the shared rows) the super-block is recomputed by brute force, members stay correct."""
+    occ, n_mo = 6, 20
+    rng = np.random.default_rng(5)
+    q, _ = np.linalg.qr(rng.standard_normal((n_mo, n_mo)))
+    S = q + 0.05 * rng.standard_normal((n_mo, n_mo))
+    S[occ + 0] = S[1]                     # virtual 0 == occupied 1: every determinant holding both is zero
+    virt = n_mo - occ
+    bra_exc = [(occ - 1, t) for t in range(virt)]     # alpha block: [0..occ-2, occ+t]: representative t = 0
+    ket_exc = [(2, 3), (0, 0), (5, 7)]
+    bd, kd = _cis_strings(n_mo, occ, bra_exc), _cis_strings(n_mo, occ, ket_exc)
+    bc, kc = rng.standard_normal((len(bd), 2)), rng.standard_normal((len(kd), 2))
+    eye = np.eye(n_mo)
+    got, info = fm.overlap_from_determinants(eye, eye, S, bd, bc, kd, kc, return_info=True)   # S_MO = S
+    want = _oracle_from_strings(eye, eye, S, bd, bc, kd, kc)
+    np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-12 * np.abs(want).max())
+    assert info["super_blocks"] >= 1 and info["blocks_redone"] >= virt
