@@ -362,7 +362,8 @@ def run_ours(args, w):
         kname = "t1_fused_kernel (rank-1 update pair determinants + DMMA CI contraction)"
     else:
         flops_pair = f_det(n) + 2 * w["n_ket"]
-        kname = "t0_fused_kernel (pivoted LU per pair + CI contraction)"
+        kname = ("t0_fused_warp_kernel" if n <= 32 else "t0_fused_ll_kernel" if n <= 64 else "t0_fused_wpm_kernel") + \
+            " (pivoted LU per pair + CI contraction)"
     achieved = pairs_shard * flops_pair / (k_ms * 1e-3) / 1e12
     # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this
     # exact configuration (profiles/traffic.json, written from the capture by scratch/make_profiles.py);
@@ -405,6 +406,8 @@ def run_ours(args, w):
             "pairs": ks * kl, "kernel_ms": t0m, "pairs_per_s": ks * kl / (t0m * 1e-3),
             "achieved_tflops": fl / (t0m * 1e-3) / 1e12, "frac_of_fp64_peak": fl / (t0m * 1e-3) / 1e12 / peak,
             "flops_per_pair": f_det(n) + 2 * w["n_ket"],
+            "kernel": ("t0_fused_warp_kernel (register-resident, n <= 32)" if n <= 32 else
+                       "t0_fused_ll_kernel (left-looking, on chip)" if n <= 64 else "t0_fused_wpm_kernel (right-looking, L2 scratch)"),
             "note": "brute-force tier on a sample of the same workload; full workload at this rate: "
                     f"{n_pairs / (ks * kl / (t0m * 1e-3)):.1f} s"}
 
@@ -514,6 +517,73 @@ def run_ours(args, w):
     return 0
 
 
+def run_traj(args):
+    """--workload traj: the reference's own trajectory fixture (cytosine, 137 MOs, 29 occupied, 2 states; 4 cycles of
+    pywfo/tests/ref_cytosin as committed in tests/golden/cytosin_traj.npz), all 12 ordered pairs of cycles in ONE
+    library call from host arrays (wfo_trajectory_ci_host: cycles uploaded once, one inverse per cycle, the pairs
+    dealt over concurrent lanes), against one overlaps_cache call per pair of the unmodified reference."""
+    import contextlib
+    import io
+    import torch
+    from pywfo_b200 import trajectory as wtraj, _lib
+    g = np.load(os.path.join(ROOT, "tests", "golden", "cytosin_traj.npz"))
+    mo, ci, occ, thr = g["mo_coeffs"], g["ci_coeffs"], int(g["occ"]), float(g["ci_thresh"])
+    n_cyc = mo.shape[0]
+    gp = [tuple(int(x) for x in p) for p in g["pairs"]]   # the fixture's own pairs first, then every other ordered pair
+    pairs = np.array(gp + [(i, j) for i in range(n_cyc) for j in range(n_cyc) if i != j and (i, j) not in gp], dtype=np.int32)
+    ctx = _lib.context(0)
+
+    def timed(lanes):
+        os.environ["WFO_TRAJ_LANES"] = str(lanes)
+        ts = []
+        for i in range(args.warmup + args.steps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = wtraj.trajectory_overlaps(mo, ci, occ, ci_thresh=thr, ao_ovlps="ket", pairs=pairs)
+            if i >= args.warmup:
+                ts.append(time.perf_counter() - t0)
+        return float(np.mean(ts)), out
+
+    l0 = ctx.launch_count()
+    t1, out1 = timed(1)
+    launches_per_call = (ctx.launch_count() - l0) / (args.warmup + args.steps)
+    t4, out4 = timed(4)
+    os.environ.pop("WFO_TRAJ_LANES", None)
+    # parity: the fixture's own pairs against the unmodified reference's output stored with it
+    want = g["ref_overlaps_cache"]
+    err = float(np.abs(out4[:len(gp)] - want).max() / np.abs(want).max())
+    same = bool(np.array_equal(out1, out4))
+    cpu = None
+    ref = _load_reference()
+    if ref is not None and args.cpu_budget > 0:
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            for i, j in pairs:
+                ref.overlaps_cache(mo[i], mo[j], ci[i], ci[j], occ, ci_thresh=thr, ao_ovlps="ket")
+        dt = time.perf_counter() - t0
+        cpu = {"value": len(pairs) / dt, "unit": "matrices/s", "cores": blas_threads(), "kind": "reference",
+               "sample": f"unmodified pywfo.main.overlaps_cache, one call per pair, {len(pairs)} pairs: {dt:.2f} s"}
+    n_pairs = len(pairs)
+    line = {
+        "metric": "trajectory state-overlap matrices/sec", "value": n_pairs / t4, "unit": "matrices/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t4 * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "reference fixture (pywfo/tests/ref_cytosin, 4 cycles)",
+        "config": {"workload": f"traj: cytosine n_mo=137 n_occ=29 2x2 states, {n_pairs} pairs of 4 cycles, ci_thresh={thr}",
+                   "lanes": 4},
+        "e2e": {"value": n_pairs / t4, "unit": "matrices/s", "ms_per_call": t4 * 1e3, "ms_per_pair": t4 * 1e3 / n_pairs,
+                "h2d_bytes_per_step": int(mo.nbytes + ci.nbytes), "d2h_bytes_per_step": int(out4.nbytes),
+                "call": "pywfo_b200.trajectory.trajectory_overlaps(host numpy arrays), all pairs in one library call"},
+        "one_lane": {"ms_per_call": t1 * 1e3, "ms_per_pair": t1 * 1e3 / n_pairs, "bitwise_equal_to_4_lanes": same},
+        "gpu_launches": int(launches_per_call),
+        "cpu_baseline": cpu,
+        "speedup_vs_cpu_same_workload": (None if cpu is None else (n_pairs / t4) / cpu["value"]),
+        "parity": {"max_rel_err_vs_reference_golden": err},
+        "host_cores": os.cpu_count(),
+    }
+    print(json.dumps(line))
+    return 0
+
+
 def hbm_peak():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -532,7 +602,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS) + ["traj"])
     ap.add_argument("--tier", default="auto", choices=["auto", "lu", "update"])
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="N > 1: in-library one-shot peer-memory all-reduce (default) or torch.distributed/NCCL")
@@ -544,6 +614,8 @@ def main():
     ap.add_argument("--k-exc", type=int, default=None,
                     help="c5 only: excitations per side (BASELINE sweep 32/100/316/1000 -> 1e3..1e6 pairs)")
     args = ap.parse_args()
+    if args.workload == "traj":
+        return run_traj(args)
     w = dict(WORKLOADS[args.workload])
     if args.k_exc is not None and args.workload == "c5":
         w["K"] = args.k_exc

@@ -83,7 +83,8 @@ int wfo_sao_dev(wfo_ctx *ctx, const double *c_inv, int n, double *s_ao, void *st
 int wfo_smo_inv_dev(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos, const double *c_inv, int n,
                     double *s_mo, double *work, void *stream);
 /* a_inv = a^-1 (n x n), replaces np.linalg.inv in pywfo/main.py:303 (98, 212).
- * Fast path: Newton-Schulz iteration X <- X (2I - A X) from X0 = A^T / |A^T A|_inf, i.e. nothing but
+ * n <= 128: one launch of the register-resident Gauss-Jordan inverse with partial pivoting (csrc/lu_base.cuh).
+ * n > 128, fast path: Newton-Schulz iteration X <- X (2I - A X) from X0 = A^T / |A^T A|_inf, i.e. nothing but
  * FP64 tensor-core GEMMs; quadratically convergent, about 2 log2(cond) + 6 iterations (orthonormal
  * MOs: the first iterate is already the inverse); the stream is synchronised every 3 iterations to
  * read the residual max|A X - I|.

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <map>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -482,6 +483,8 @@ int wfo_destroy(wfo_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     wfo_comm_destroy(ctx);
+    for (int l = 1; l < TRAJ_MAX_LANES; l++)
+        if (ctx->lanes[l]) { wfo_destroy(ctx->lanes[l]); ctx->lanes[l] = nullptr; }
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->gscratch) cudaFree(ctx->gscratch);
     if (ctx->gj_buf) cudaFree(ctx->gj_buf);
@@ -916,6 +919,22 @@ int wfo_inverse_dev(wfo_ctx *ctx, const double *a, int n, double *a_inv, double 
         WFO_TRY(ensure_scratch(ctx, 2 * align_up(nn * sizeof(double), 256)));
         work = reinterpret_cast<double *>(ctx->scratch);
     }
+    ctx->last_inverse_iters = 0;
+    ctx->last_inverse_pivoted = 0;
+    if (n <= LUB_MAXN) {
+        // small matrices: ONE launch of the register-resident Gauss-Jordan inverse with partial pivoting (the
+        // kernel behind the base block of the rank-update tier) instead of a dozen launches of Newton-Schulz:
+        // these sizes are launch-latency bound (bundled pywfo tests: n_mo = 24 ... 38)
+        BaseInfo *d_info = reinterpret_cast<BaseInfo *>(ctx->ns_slots);
+        base_inverse_kernel<<<1, LUB_THREADS, lub_smem_bytes(n), st>>>(a, n, n, a_inv, n, d_info);
+        WFO_LAUNCH_CHECK(ctx);
+        WFO_CUDA(cudaMemcpyAsync(ctx->h_slots, d_info, sizeof(BaseInfo), cudaMemcpyDeviceToHost, st));
+        WFO_CUDA(cudaStreamSynchronize(st));
+        ctx->last_inverse_pivoted = 1;
+        if (reinterpret_cast<const BaseInfo *>(ctx->h_slots)->singular)
+            return set_err(WFO_ERR_NOCONV, "inverse: singular matrix (zero pivot column)");
+        return WFO_OK;
+    }
     double *T = work, *Xb = work + align_up(nn * sizeof(double), 256) / sizeof(double);
     double *X = a_inv, *Xn = Xb;   // ping-pong; the result must end in a_inv
     double *slots = ctx->ns_slots;
@@ -931,8 +950,6 @@ int wfo_inverse_dev(wfo_ctx *ctx, const double *a, int n, double *a_inv, double 
     int it = 0, checked = 0;
     bool converged = false, give_up = false;
     double prev = 1e300;
-    ctx->last_inverse_iters = 0;
-    ctx->last_inverse_pivoted = 0;
     while (it < NS_MAX_ITERS && !converged && !give_up) {
         const int batch = 3;   // iterations between two looks at the residuals
         for (int b = 0; b < batch && it < NS_MAX_ITERS; b++, it++) {
@@ -1825,37 +1842,120 @@ int wfo_trajectory_ci_host(wfo_ctx *ctx, const double *mos, const double *ci, in
         memset(out, 0, (size_t)n_pairs * nout * sizeof(double));
         return WFO_OK;
     }
-    CiWork w;
+    // Pairs of a trajectory are independent and, at the sizes of real trajectories (cytosine: 137 MOs, 2 states),
+    // each is a chain of ~40 small launches with two host synchronisations: launch latency, not the GPU, sets the
+    // pace.  So small problems run on several LANES -- worker contexts on the same device with their own streams
+    // and arenas, one host thread each -- whose kernels overlap on the GPU; the cycles (MOs, CI, inverses) are
+    // shared and resident.  Large problems (one pair fills the GPU) keep one lane.
+    int n_lanes = 1;
+    if ((long long)n_states * count <= 200000 && n_mo <= 512) n_lanes = n_pairs < TRAJ_MAX_LANES ? n_pairs : TRAJ_MAX_LANES;
+    {
+        const char *e = getenv("WFO_TRAJ_LANES");
+        if (e && atoi(e) >= 1) n_lanes = atoi(e) < TRAJ_MAX_LANES ? atoi(e) : TRAJ_MAX_LANES;
+        if (n_lanes > n_pairs) n_lanes = n_pairs;
+    }
+    for (int l = 1; l < n_lanes; l++)
+        if (!ctx->lanes[l]) WFO_TRY(wfo_create(ctx->device, &ctx->lanes[l]));
+    ctx->lanes[0] = ctx;
     Sizer sz;
     sz.take<double>(nsq * n_cycles); sz.take<double>(ncc * n_cycles); sz.take<double>(nsq * n_cycles);
     sz.take<double>(nout * n_pairs);
-    carve_ciwork(sz, w, nsq, count, n_states, n_states);
+    const size_t shared_bytes = sz.off;
+    {
+        CiWork w0;
+        carve_ciwork(sz, w0, nsq, count, n_states, n_states);
+    }
+    const size_t work_bytes = sz.off - shared_bytes;
     WFO_TRY(ensure_resident(ctx, sz.off));
+    for (int l = 1; l < n_lanes; l++) WFO_TRY(ensure_resident(ctx->lanes[l], work_bytes));
     Arena ar{ctx->resident, ctx->resident_bytes, 0};
     double *d_mos = ar.take<double>(nsq * n_cycles), *d_ci = ar.take<double>(ncc * n_cycles);
     double *d_inv = ar.take<double>(nsq * n_cycles), *d_outs = ar.take<double>(nout * n_pairs);
-    carve_ciwork(ar, w, nsq, count, n_states, n_states);
+    std::vector<CiWork> works(n_lanes);
+    carve_ciwork(ar, works[0], nsq, count, n_states, n_states);
+    for (int l = 1; l < n_lanes; l++) {
+        Arena al{ctx->lanes[l]->resident, ctx->lanes[l]->resident_bytes, 0};
+        carve_ciwork(al, works[l], nsq, count, n_states, n_states);
+    }
     WFO_CUDA(cudaMemcpyAsync(d_mos, mos, nsq * n_cycles * 8, cudaMemcpyHostToDevice, st));
     WFO_CUDA(cudaMemcpyAsync(d_ci, ci, ncc * n_cycles * 8, cudaMemcpyHostToDevice, st));
-    std::vector<char> have_inv(n_cycles, 0);
-    for (int p = 0; p < n_pairs; p++) {
-        const int cb = pairs[2 * p], ck = pairs[2 * p + 1];
-        const int ci_c = ao_side == WFO_AO_BRA ? cb : ck;   // the cycle whose MO matrix defines S_AO
-        if (!have_inv[ci_c]) {   // once per cycle; ordered after the uploads and after earlier users of the scratch
-            WFO_CUDA(cudaEventRecord(ctx->ev_fork, st));
-            WFO_CUDA(cudaStreamWaitEvent(s2, ctx->ev_fork, 0));
-            WFO_TRY(wfo_inverse_dev(ctx, d_mos + nsq * ci_c, n_mo, d_inv + nsq * ci_c, w.work, s2));
-            have_inv[ci_c] = 1;
+    WFO_CUDA(cudaStreamSynchronize(st));   // the lanes read the cycles from their own streams
+    // the cycles whose MO matrix defines an S_AO, in order of first use
+    std::vector<int> inv_cycles;
+    {
+        std::vector<char> seen(n_cycles, 0);
+        for (int p = 0; p < n_pairs; p++) {
+            const int c = ao_side == WFO_AO_BRA ? pairs[2 * p] : pairs[2 * p + 1];
+            if (!seen[c]) { seen[c] = 1; inv_cycles.push_back(c); }
         }
-        bool zero = false;
-        int32_t pinfo[4];
-        WFO_TRY(overlaps_ci_core(ctx, w, d_mos + nsq * cb, d_mos + nsq * ck, d_inv + nsq * ci_c, WFO_AO_GIVEN, n_mo, n_occ,
-                                 d_ci + ncc * cb, n_states, d_ci + ncc * ck, n_states, ci_thresh, semantics, tier, rank,
-                                 world, true, pinfo, &zero, st));
-        if (info) { info[0] = pinfo[0] > info[0] ? pinfo[0] : info[0]; info[1] = pinfo[1] > info[1] ? pinfo[1] : info[1]; info[3] = pinfo[3]; }
-        if (zero) WFO_CUDA(cudaMemsetAsync(d_outs + nout * p, 0, nout * 8, st));
-        else WFO_CUDA(cudaMemcpyAsync(d_outs + nout * p, w.out, nout * 8, cudaMemcpyDeviceToDevice, st));
     }
+    struct LaneResult { int rc; char msg[512]; int32_t info[4]; };
+    std::vector<LaneResult> res(n_lanes);
+    auto run_lanes = [&](auto &&body) {   // body(lane) -> rc, on the lane's own host thread
+        auto wrapped = [&](int l) {
+            cudaSetDevice(ctx->device);
+            res[l].rc = body(l);
+            if (res[l].rc != WFO_OK) snprintf(res[l].msg, sizeof(res[l].msg), "%s", g_err);
+        };
+        std::vector<std::thread> th;
+        for (int l = 1; l < n_lanes; l++) th.emplace_back(wrapped, l);
+        wrapped(0);
+        for (auto &t : th) t.join();
+        for (int l = 0; l < n_lanes; l++)
+            if (res[l].rc != WFO_OK) {
+                snprintf(g_err, sizeof(g_err), "%s", res[l].msg);
+                return res[l].rc;
+            }
+        return (int)WFO_OK;
+    };
+    // phase 1: one inverse per cycle, dealt over the lanes
+    WFO_TRY(run_lanes([&](int l) -> int {
+        wfo_ctx *lc = ctx->lanes[l];
+        for (size_t i = l; i < inv_cycles.size(); i += n_lanes) {
+            const int c = inv_cycles[i];
+            WFO_TRY(wfo_inverse_dev(lc, d_mos + nsq * c, n_mo, d_inv + nsq * c, works[l].work, lc->stream));
+        }
+        WFO_CUDA(cudaStreamSynchronize(lc->stream));
+        return WFO_OK;
+    }));
+    // phase 2: the pairs, dealt over the lanes
+    for (int l = 0; l < n_lanes; l++) { res[l].info[0] = res[l].info[1] = 0; res[l].info[2] = 0; res[l].info[3] = -1; }
+    const int rc2 = run_lanes([&](int l) -> int {
+        wfo_ctx *lc = ctx->lanes[l];
+        cudaStream_t ls = lc->stream;
+        for (int p = l; p < n_pairs; p += n_lanes) {
+            const int cb = pairs[2 * p], ck = pairs[2 * p + 1];
+            const int ci_c = ao_side == WFO_AO_BRA ? cb : ck;
+            bool zero = false;
+            int32_t pinfo[4];
+            WFO_TRY(overlaps_ci_core(lc, works[l], d_mos + nsq * cb, d_mos + nsq * ck, d_inv + nsq * ci_c, WFO_AO_GIVEN, n_mo,
+                                     n_occ, d_ci + ncc * cb, n_states, d_ci + ncc * ck, n_states, ci_thresh, semantics, tier,
+                                     rank, world, true, pinfo, &zero, ls));
+            int32_t *li = res[l].info;
+            li[0] = pinfo[0] > li[0] ? pinfo[0] : li[0];
+            li[1] = pinfo[1] > li[1] ? pinfo[1] : li[1];
+            li[3] = pinfo[3];
+            if (zero) WFO_CUDA(cudaMemsetAsync(d_outs + nout * p, 0, nout * 8, ls));
+            else WFO_CUDA(cudaMemcpyAsync(d_outs + nout * p, works[l].out, nout * 8, cudaMemcpyDeviceToDevice, ls));
+        }
+        WFO_CUDA(cudaStreamSynchronize(ls));
+        return WFO_OK;
+    });
+    for (int l = 1; l < n_lanes; l++) {   // bookkeeping of the worker contexts belongs to the caller's context
+        ctx->launches += ctx->lanes[l]->launches;
+        ctx->lanes[l]->launches = 0;
+    }
+    if (rc2 != WFO_OK) {
+        if (info && rc2 == WFO_ERR_EMPTY_STATE) info[2] = 1;
+        return rc2;
+    }
+    if (info)
+        for (int l = 0; l < n_lanes; l++) {
+            info[0] = res[l].info[0] > info[0] ? res[l].info[0] : info[0];
+            info[1] = res[l].info[1] > info[1] ? res[l].info[1] : info[1];
+            if (res[l].info[3] >= 0) info[3] = res[l].info[3];
+        }
+    ctx->last_lanes = n_lanes;
     WFO_CUDA(cudaMemcpyAsync(out, d_outs, nout * n_pairs * 8, cudaMemcpyDeviceToHost, st));
     WFO_CUDA(cudaStreamSynchronize(st));
     return WFO_OK;

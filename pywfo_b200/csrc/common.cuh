@@ -71,6 +71,8 @@ __device__ __forceinline__ unsigned hi_abs(double x) {
 
 namespace wfo { struct BaseInfo; struct Comm; }
 
+constexpr int TRAJ_MAX_LANES = 4;   // worker contexts of the trajectory driver
+
 struct wfo_ctx {
     int device;
     int sm_count;
@@ -95,6 +97,8 @@ struct wfo_ctx {
     long long launches;
     int last_tier;
     wfo::Comm *comm;       // in-library collective over peer memory (wfo_comm_init), NULL = single rank
+    wfo_ctx *lanes[TRAJ_MAX_LANES];   // [0] = this context, others created on demand (wfo_trajectory_ci_host)
+    int last_lanes;
     int lu_variant;        // WFO_LU_*: which brute-force kernel serves 32 < n <= 128
     int timing;
     float last_ms;
