@@ -362,7 +362,7 @@ def run_ours(args, w):
         kname = "t1_fused_kernel (rank-1 update pair determinants + DMMA CI contraction)"
     else:
         flops_pair = f_det(n) + 2 * w["n_ket"]
-        kname = ("t0_fused_warp_kernel" if n <= 32 else "t0_fused_ll_kernel" if n <= 64 else "t0_fused_wpm_kernel") + \
+        kname = ("t0_fused_warp_kernel" if n <= 32 else "t0_fused_ll_kernel") + \
             " (pivoted LU per pair + CI contraction)"
     achieved = pairs_shard * flops_pair / (k_ms * 1e-3) / 1e12
     # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this
@@ -407,7 +407,8 @@ def run_ours(args, w):
             "achieved_tflops": fl / (t0m * 1e-3) / 1e12, "frac_of_fp64_peak": fl / (t0m * 1e-3) / 1e12 / peak,
             "flops_per_pair": f_det(n) + 2 * w["n_ket"],
             "kernel": ("t0_fused_warp_kernel (register-resident, n <= 32)" if n <= 32 else
-                       "t0_fused_ll_kernel (left-looking, on chip)" if n <= 64 else "t0_fused_wpm_kernel (right-looking, L2 scratch)"),
+                       "t0_fused_ll_kernel (left-looking, on chip)" if n <= 64 else
+                       "t0_fused_ll_kernel (left-looking, L2 scratch)"),
             "note": "brute-force tier on a sample of the same workload; full workload at this rate: "
                     f"{n_pairs / (ks * kl / (t0m * 1e-3)):.1f} s"}
 

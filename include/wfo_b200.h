@@ -215,8 +215,8 @@ int wfo_allreduce_dev(wfo_ctx *ctx, double *buf, long long count, void *stream);
 int wfo_comm_status(wfo_ctx *ctx);        /* after a stream sync: WFO_ERR_COMM if a wait timed out */
 
 /* Brute-force tier, 32 < n_occ <= 128: which of the two warp-per-determinant LU kernels runs.
- * AUTO = left-looking, all on chip (csrc/det_lu_ll.cuh) up to n_occ = 64, right-looking with an
- * L2-resident scratch (csrc/det_lu_wpm.cuh) above.  Both compute the same partially pivoted LU
+ * AUTO = LEFT = left-looking (csrc/det_lu_ll.cuh: panels in shared memory up to n_occ = 64, in an
+ * L2-resident scratch above); RIGHT = right-looking with an L2-resident scratch (csrc/det_lu_wpm.cuh).  Both compute the same partially pivoted LU
  * (pywfo/main.py:583-584); the switch exists so that tests and benchmarks can run either one. */
 #define WFO_LU_AUTO 0
 #define WFO_LU_LEFT 1

@@ -180,26 +180,27 @@ static int ensure_gscratch(wfo_ctx *ctx, size_t bytes) {
 }
 
 // Brute-force tier, 32 < n <= 128: two warp-per-matrix kernels.
-//   left-looking, all on chip (det_lu_ll.cuh): faster up to n = 64 (20 % of the FP64 peak at n = 64 against 15 %),
-//     no DRAM traffic at any n; at n = 100 only five matrices fit an SM and it falls behind;
-//   right-looking with an L2-resident scratch (det_lu_wpm.cuh): eight matrices per SM at any n.
+//   left-looking (det_lu_ll.cuh), the default: M panels in shared memory up to n = 64 (21 % of the FP64 peak at
+//     n = 64 against 15 %), in an L2-resident scratch above (eight matrices per SM: 16-17 % at n = 120-128
+//     against 14-16 %, level at n = 100);
+//   right-looking with an L2-resident scratch (det_lu_wpm.cuh): round 1's kernel, kept as the cross-check.
 // wfo_set_lu_variant() pins one of them (tests run both at every size).
 static bool use_ll_kernels(const wfo_ctx *ctx, int n) {
     if (n <= 32 || n > 128) return false;
     if (ctx->lu_variant == WFO_LU_LEFT) return true;
     if (ctx->lu_variant == WFO_LU_RIGHT) return false;
-    return n <= 64;
+    return true;
 }
-#define WFO_LL_DISPATCH(n, CALL)                                             \
-    do {                                                                     \
-        switch (((n) + 7) / 8) {                                             \
-            case 5: CALL(5); break;   case 6: CALL(6); break;                \
-            case 7: CALL(7); break;   case 8: CALL(8); break;                \
-            case 9: CALL(9); break;   case 10: CALL(10); break;              \
-            case 11: CALL(11); break; case 12: CALL(12); break;              \
-            case 13: CALL(13); break; case 14: CALL(14); break;              \
-            case 15: CALL(15); break; default: CALL(16); break;              \
-        }                                                                    \
+#define WFO_LL_DISPATCH(n, CALL)                                                         \
+    do {                                                                                 \
+        switch (((n) + 7) / 8) {                                                         \
+            case 5: CALL(5, false); break;   case 6: CALL(6, false); break;              \
+            case 7: CALL(7, false); break;   case 8: CALL(8, false); break;              \
+            case 9: CALL(9, true); break;    case 10: CALL(10, true); break;             \
+            case 11: CALL(11, true); break;  case 12: CALL(12, true); break;             \
+            case 13: CALL(13, true); break;  case 14: CALL(14, true); break;             \
+            case 15: CALL(15, true); break;  default: CALL(16, true); break;             \
+        }                                                                                \
     } while (0)
 #define WFO_WPM_DISPATCH(n, CALL)            \
     do {                                     \
@@ -236,11 +237,13 @@ static int det_table(wfo_ctx *ctx, const double *S, int ld_s, int n, const int32
         return set_err(WFO_ERR_ARG, "det_table: n_occ=%lld outside the supported range 1..128", n);
     unsigned grid = 1;
     if (use_ll_kernels(ctx, n)) {
-#define CALL_DL(NT_)                                                                                           \
-    WFO_TRY(persistent_grid(ctx, det_table_ll_kernel<NT_>, LLWarps<NT_>::W * 32, LLWarps<NT_>::W * LLCfg<NT_>::BYTES, \
-                            (npairs + LLWarps<NT_>::W - 1) / LLWarps<NT_>::W, &grid));                         \
-    det_table_ll_kernel<NT_><<<grid, LLWarps<NT_>::W * 32, LLWarps<NT_>::W * LLCfg<NT_>::BYTES, st>>>(S, ld_s, n, rows, kb, \
-                                                                                                      cols, kk, D)
+#define CALL_DL(NT_, MG_)                                                                                       \
+    WFO_TRY(persistent_grid(ctx, det_table_ll_kernel<NT_, MG_>, LLWarps<NT_, MG_>::W * 32,                           \
+                            LLWarps<NT_, MG_>::W * LLCfg<NT_, MG_>::BYTES,                                           \
+                            (npairs + LLWarps<NT_, MG_>::W - 1) / LLWarps<NT_, MG_>::W, &grid));                     \
+    if (MG_) WFO_TRY(ensure_gscratch(ctx, (size_t)grid * LLWarps<NT_, MG_>::W * ll_scratch_doubles(NT_) * 8));       \
+    det_table_ll_kernel<NT_, MG_><<<grid, LLWarps<NT_, MG_>::W * 32, LLWarps<NT_, MG_>::W * LLCfg<NT_, MG_>::BYTES, st>>>( \
+        S, ld_s, n, rows, kb, cols, kk, D, ctx->gscratch)
         WFO_LL_DISPATCH(n, CALL_DL);
 #undef CALL_DL
     } else if (n > 32) {
@@ -1354,12 +1357,14 @@ static int state_overlaps_block(wfo_ctx *ctx, size_t arena_off, const double *s_
         const long long items = (long long)ksh * t0_chunks;
         unsigned grid = 1;
         if (use_ll_kernels(ctx, n)) {
-#define CALL_FL(NT_)                                                                                              \
-    WFO_TRY(persistent_grid(ctx, t0_fused_ll_kernel<NT_>, LLWarps<NT_>::W * 32, LLWarps<NT_>::W * LLCfg<NT_>::BYTES, \
-                            (items + LLWarps<NT_>::W - 1) / LLWarps<NT_>::W, &grid));                             \
-    if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev0, st));                                                     \
-    t0_fused_ll_kernel<NT_><<<grid, LLWarps<NT_>::W * 32, LLWarps<NT_>::W * LLCfg<NT_>::BYTES, st>>>(             \
-        s_mo, n_mo, n, p.bra_lists, ksh, p.ket_lists, kk, p.ckt, ldg, chunk_len, t0_chunks, p.gpart)
+#define CALL_FL(NT_, MG_)                                                                                         \
+    WFO_TRY(persistent_grid(ctx, t0_fused_ll_kernel<NT_, MG_>, LLWarps<NT_, MG_>::W * 32,                             \
+                            LLWarps<NT_, MG_>::W * LLCfg<NT_, MG_>::BYTES,                                            \
+                            (items + LLWarps<NT_, MG_>::W - 1) / LLWarps<NT_, MG_>::W, &grid));                       \
+    if (MG_) WFO_TRY(ensure_gscratch(ctx, (size_t)grid * LLWarps<NT_, MG_>::W * ll_scratch_doubles(NT_) * 8));        \
+    if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev0, st));                                                         \
+    t0_fused_ll_kernel<NT_, MG_><<<grid, LLWarps<NT_, MG_>::W * 32, LLWarps<NT_, MG_>::W * LLCfg<NT_, MG_>::BYTES, st>>>( \
+        s_mo, n_mo, n, p.bra_lists, ksh, p.ket_lists, kk, p.ckt, ldg, chunk_len, t0_chunks, p.gpart, ctx->gscratch)
             WFO_LL_DISPATCH(n, CALL_FL);
 #undef CALL_FL
         } else if (n > 32) {

@@ -42,7 +42,9 @@ struct LLClk {};
 #define LL_T(i)
 #endif
 
-template <int NT>
+// MG: the M panels live in a per-warp GLOBAL scratch that stays L2 resident (n > 64: more matrices in flight per SM
+// than shared memory could hold); shared memory then holds only the staging area of one panel.
+template <int NT, bool MG = false>
 struct LLCfg {
     static constexpr int ROWS = 8 * NT;
     static constexpr int M_TILES = NT * (NT - 1) / 2;
@@ -55,11 +57,17 @@ struct LLCfg {
     static constexpr int OFF_ROFFB = OFF_ROFF + 4 * ROWS;  // ... as they were when the next panel was prefetched
     static constexpr int OFF_COFF = OFF_ROFFB + 4 * ROWS;  // column offsets
     static constexpr int OFF_M = (OFF_COFF + 4 * ROWS + 15) / 16 * 16;
-    static constexpr int BYTES = OFF_M + 512 * M_TILES;
+    static constexpr int BYTES = OFF_M + 512 * (MG ? NT : M_TILES);
 };
 
 __device__ __forceinline__ double2 lds128(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 __device__ __forceinline__ void sts128(double *p, double x, double y) { *reinterpret_cast<double2 *>(p) = make_double2(x, y); }
+// a 16-byte chunk of an M panel: shared memory, or the L2-resident global scratch (L1 bypassed; prefetching the
+// next panel into L1 while the current one is applied was measured: 5 % slower)
+template <bool MG>
+__device__ __forceinline__ double2 ldM(const double *p) {
+    return MG ? __ldcg(reinterpret_cast<const double2 *>(p)) : *reinterpret_cast<const double2 *>(p);
+}
 
 // element (row position, column c) of the padded minor; roff < 0 marks pad row -(roff+1), coff < 0 a pad column
 __device__ __forceinline__ double ll_elem(const double *__restrict__ S, int roff, int coff, int c) {
@@ -91,16 +99,18 @@ __device__ __forceinline__ void ll_load_panel(const double *__restrict__ S, cons
 // cache level.  (Measured: with every loop unrolled and four slot counts, 125 KB of code, the warps
 // spent 6 of 10 cycles per instruction in 'no instruction' stalls.)
 // Returns 0 for a singular minor, 1 when no row changed position, 2 when rows moved.
-template <int NT, int SL>
-__device__ __forceinline__ int ll_factor(char *sm, int p, int n, int lane, double &det, unsigned &par, LLClk &clk) {
-    using C = LLCfg<NT>;
+template <int NT, int SL, bool MG>
+__device__ __forceinline__ int ll_factor(char *sm, double *gM, int p, int n, int lane, double &det, unsigned &par, LLClk &clk) {
+    using C = LLCfg<NT, MG>;
     const unsigned FULL = 0xffffffffu;
     const int L = 8 * (NT - p);   // live rows
     double *smd = reinterpret_cast<double *>(sm);
     double *recs = reinterpret_cast<double *>(sm + C::OFF_REC);
     unsigned char *moves = reinterpret_cast<unsigned char *>(sm + C::OFF_MOVES);
     int *roff = reinterpret_cast<int *>(sm + C::OFF_ROFF);
-    const int mp_off = C::OFF_M / 8 + (p * (NT - 1) - p * (p - 1) / 2) * 64;   // M_p, in doubles from sm
+    // staging rows of the live block below the top tile: the future M_p (shared-memory variant) or the staging area
+    const int mp_off = MG ? C::OFF_M / 8 : C::OFF_M / 8 + (p * (NT - 1) - p * (p - 1) / 2) * 64;
+    double *Mp_dst = MG ? gM + (size_t)(p * (NT - 1) - p * (p - 1) / 2) * 64 : smd + mp_off;
 
     double a[SL][8];
     int rpos[SL], myroff[SL], rowoff[SL];
@@ -197,7 +207,7 @@ __device__ __forceinline__ int ll_factor(char *sm, int p, int n, int lane, doubl
     for (int s = 0; s < SL; s++) {
         const int lam = lane + 32 * s;
         if (alive[s]) {
-            double *dst = smd + mp_off + (rpos[s] - 8) * 8;
+            double *dst = Mp_dst + (rpos[s] - 8) * 8;
             const int sw = (rpos[s] >> 1) & 3;
 #pragma unroll
             for (int c = 0; c < 4; c++) sts128(dst + ((c ^ sw) << 1), -a[s][c], -a[s][c + 4]);
@@ -230,17 +240,18 @@ __device__ __forceinline__ int ll_factor(char *sm, int p, int n, int lane, doubl
 
 // whole factorisation by one warp; returns det to every lane.  sm: LLCfg<NT>::BYTES of shared memory
 // owned by this warp.
-template <int NT>
+template <int NT, bool MG>
 __device__ __forceinline__ double ll_lu_det(const double *__restrict__ S, int ld_s, const int32_t *__restrict__ rows,
-                                            const int32_t *__restrict__ cols, int n, char *sm, int lane) {
-    using C = LLCfg<NT>;
+                                            const int32_t *__restrict__ cols, int n, char *sm, double *gM, int lane) {
+    using C = LLCfg<NT, MG>;
     double *top = reinterpret_cast<double *>(sm + C::OFF_TOP);
     double *rbuf = reinterpret_cast<double *>(sm + C::OFF_RBUF);
     const unsigned char *moves = reinterpret_cast<const unsigned char *>(sm + C::OFF_MOVES);
     int *roff = reinterpret_cast<int *>(sm + C::OFF_ROFF);
     int *roffb = reinterpret_cast<int *>(sm + C::OFF_ROFFB);
     int *coff = reinterpret_cast<int *>(sm + C::OFF_COFF);
-    double *Mall = reinterpret_cast<double *>(sm + C::OFF_M);
+    double *Mall = MG ? gM : reinterpret_cast<double *>(sm + C::OFF_M);
+    double *stage = reinterpret_cast<double *>(sm + C::OFF_M);   // MG only
     const int g = lane >> 2, tq = lane & 3;
     const int swz = (g >> 1) & 3;
     LLClk clk;
@@ -287,7 +298,8 @@ __device__ __forceinline__ double ll_lu_det(const double *__restrict__ S, int ld
             const double *Mq = Mall + (q * (NT - 1) - q * (q - 1) / 2) * 64 + g * 8 + ((tq ^ swz) << 1);
             double2 af[NT];
 #pragma unroll
-            for (int t = q + 1; t < NT; t++) af[t] = lds128(Mq + (t - q - 1) * 64);
+            for (int t = q + 1; t < NT; t++)
+                af[t] = ldM<MG>(Mq + (t - q - 1) * 64);
 #pragma unroll
             for (int t = q + 1; t < NT; t++) dmma884(acc[t][0], acc[t][1], af[t].x, b0);
 #pragma unroll
@@ -296,7 +308,7 @@ __device__ __forceinline__ double ll_lu_det(const double *__restrict__ S, int ld
         LL_T(1);
         // ---- live rows to the row-per-lane layout through the staging area (top tile + future M_p)
         {
-            double *Mp = Mall + (size_t)(p * (NT - 1) - p * (p - 1) / 2 - p - 1) * 64;
+            double *Mp = MG ? stage - (size_t)(p + 1) * 64 : Mall + (size_t)(p * (NT - 1) - p * (p - 1) / 2 - p - 1) * 64;
 #pragma unroll
             for (int t = 0; t < NT; t++) {
                 if (t >= p) {
@@ -309,8 +321,8 @@ __device__ __forceinline__ double ll_lu_det(const double *__restrict__ S, int ld
         LL_T(2);
         const int L = 8 * (NT - p);
         constexpr int SLMAX = (8 * NT + 31) / 32, SLLO = (SLMAX + 1) / 2;
-        if (L > 32 * SLLO) ok = ll_factor<NT, SLMAX>(sm, p, n, lane, det, par, clk);
-        else ok = ll_factor<NT, SLLO>(sm, p, n, lane, det, par, clk);
+        if (L > 32 * SLLO) ok = ll_factor<NT, SLMAX, MG>(sm, gM, p, n, lane, det, par, clk);
+        else ok = ll_factor<NT, SLLO, MG>(sm, gM, p, n, lane, det, par, clk);
         if (ok == 0) break;
         if (ok >= 2) {
             // rows moved: the same moves in the finished panels M_0 .. M_{p-1} ...
@@ -323,12 +335,12 @@ __device__ __forceinline__ double ll_lu_det(const double *__restrict__ S, int ld
                 if (m0 < nm) {
                     const int from = moves[2 * m0];
                     d0 = moves[2 * m0 + 1];
-                    v0 = lds128(Mq + from * 8 + ((c ^ ((from >> 1) & 3)) << 1));
+                    v0 = ldM<MG>(Mq + from * 8 + ((c ^ ((from >> 1) & 3)) << 1));
                 }
                 if (m0 + 8 < nm) {
                     const int from = moves[2 * (m0 + 8)];
                     d1 = moves[2 * (m0 + 8) + 1];
-                    v1 = lds128(Mq + from * 8 + ((c ^ ((from >> 1) & 3)) << 1));
+                    v1 = ldM<MG>(Mq + from * 8 + ((c ^ ((from >> 1) & 3)) << 1));
                 }
                 __syncwarp();
                 if (m0 < nm) sts128(Mq + d0 * 8 + ((c ^ ((d0 >> 1) & 3)) << 1), v0.x, v0.y);
@@ -363,50 +375,51 @@ __device__ __forceinline__ double ll_lu_det(const double *__restrict__ S, int ld
 // Warps per CTA.  The warps are independent of each other, but the hardware maps warp w of a CTA to
 // scheduler w % 4: single-warp CTAs would all sit on scheduler 0 (measured: 4-5x slower).  So ONE
 // persistent CTA per SM with as many warps as shared memory (227 KB) and registers allow.
-template <int NT>
+template <int NT, bool MG = false>
 struct LLWarps {
-    static constexpr int SMEM = (227 * 1024) / LLCfg<NT>::BYTES;
+    static constexpr int SMEM = (227 * 1024) / LLCfg<NT, MG>::BYTES;
     static constexpr int REG = NT >= 13 ? 8 : (NT >= 9 ? 10 : (NT >= 7 ? 12 : 16));   // register budget 65536 / (32 w)
     static constexpr int W = SMEM < REG ? SMEM : REG;
 };
-template <int NT>
-constexpr int ll_warps() { return LLWarps<NT>::W; }
+inline size_t ll_scratch_doubles(int nt) { return (size_t)nt * (nt - 1) / 2 * 64; }   // per warp, MG variant
 
-template <int NT>
-__global__ void __launch_bounds__(LLWarps<NT>::W * 32, 1)
+template <int NT, bool MG>
+__global__ void __launch_bounds__(LLWarps<NT, MG>::W * 32, 1)
 det_table_ll_kernel(const double *__restrict__ S, int ld_s, int n, const int32_t *__restrict__ rows, int kb,
-                    const int32_t *__restrict__ cols, int kk, double *__restrict__ D) {
+                    const int32_t *__restrict__ cols, int kk, double *__restrict__ D, double *gscratch) {
     extern __shared__ __align__(16) char ll_smem[];
-    constexpr int W = LLWarps<NT>::W;
+    constexpr int W = LLWarps<NT, MG>::W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    char *sm = ll_smem + (size_t)warp * LLCfg<NT>::BYTES;
+    char *sm = ll_smem + (size_t)warp * LLCfg<NT, MG>::BYTES;
     const long long gw = (long long)blockIdx.x * W + warp, nw = (long long)gridDim.x * W;
+    double *gM = MG ? gscratch + (size_t)gw * (NT * (NT - 1) / 2 * 64) : nullptr;
     const long long npairs = (long long)kb * kk;
     for (long long pair = gw; pair < npairs; pair += nw) {
         const int k = (int)(pair / kk), l = (int)(pair - (long long)k * kk);
-        const double det = ll_lu_det<NT>(S, ld_s, rows + (size_t)k * n, cols + (size_t)l * n, n, sm, lane);
+        const double det = ll_lu_det<NT, MG>(S, ld_s, rows + (size_t)k * n, cols + (size_t)l * n, n, sm, gM, lane);
         if (lane == 0) D[pair] = det;
     }
 }
 
 // one work item per warp = (bra determinant k, chunk of ket determinants); g[j] += D(k,l) CkT[l][j]
-template <int NT>
-__global__ void __launch_bounds__(LLWarps<NT>::W * 32, 1)
+template <int NT, bool MG>
+__global__ void __launch_bounds__(LLWarps<NT, MG>::W * 32, 1)
 t0_fused_ll_kernel(const double *__restrict__ S, int ld_s, int n, const int32_t *__restrict__ rows, int ksh,
                    const int32_t *__restrict__ cols, int kk, const double *__restrict__ ckt, int ldg, int chunk_len,
-                   int n_chunks, double *__restrict__ gpart) {
+                   int n_chunks, double *__restrict__ gpart, double *gscratch) {
     extern __shared__ __align__(16) char ll_smem[];
-    constexpr int W = LLWarps<NT>::W;
+    constexpr int W = LLWarps<NT, MG>::W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    char *sm = ll_smem + (size_t)warp * LLCfg<NT>::BYTES;
+    char *sm = ll_smem + (size_t)warp * LLCfg<NT, MG>::BYTES;
     const long long gw = (long long)blockIdx.x * W + warp, nw = (long long)gridDim.x * W;
+    double *gM = MG ? gscratch + (size_t)gw * (NT * (NT - 1) / 2 * 64) : nullptr;
     const long long nitems = (long long)ksh * n_chunks;
     for (long long item = gw; item < nitems; item += nw) {
         const int k = (int)(item / n_chunks), ch = (int)(item - (long long)k * n_chunks);
         const int l0 = ch * chunk_len, l1 = min(kk, l0 + chunk_len);
         double g0 = 0.0, g1 = 0.0;
         for (int l = l0; l < l1; l++) {
-            const double det = ll_lu_det<NT>(S, ld_s, rows + (size_t)k * n, cols + (size_t)l * n, n, sm, lane);
+            const double det = ll_lu_det<NT, MG>(S, ld_s, rows + (size_t)k * n, cols + (size_t)l * n, n, sm, gM, lane);
             if (lane < ldg) g0 = fma(det, __ldg(ckt + (size_t)l * ldg + lane), g0);
             if (lane + 32 < ldg) g1 = fma(det, __ldg(ckt + (size_t)l * ldg + lane + 32), g1);
         }

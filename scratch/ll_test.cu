@@ -57,13 +57,18 @@ int main(int argc, char **argv) {
     cudaMemcpy(dS, S.data(), S.size() * 8, cudaMemcpyHostToDevice);
     cudaMemcpy(dr, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(dc, cols.data(), cols.size() * 4, cudaMemcpyHostToDevice);
-    auto kern = det_table_ll_kernel<NTV>;
-    constexpr int LL_WARPS = LLWarps<NTV>::W;
-    const int smem = LL_WARPS * LLCfg<NTV>::BYTES;
+    #ifndef MGV
+#define MGV false
+#endif
+    auto kern = det_table_ll_kernel<NTV, MGV>;
+    constexpr int LL_WARPS = LLWarps<NTV, MGV>::W;
+    const int smem = LL_WARPS * LLCfg<NTV, MGV>::BYTES;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     int per_sm = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LL_WARPS * 32, smem);
     int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     const int grid = sms * per_sm;
+    double *dG = nullptr;
+    if (MGV) cudaMalloc(&dG, (size_t)grid * LL_WARPS * ll_scratch_doubles(NTV) * 8);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e30f, sum = 0; const int reps = 10;
     for (int r = 0; r < reps + 5; r++) {
@@ -71,7 +76,7 @@ int main(int argc, char **argv) {
         long long z[8] = {0}; cudaMemcpyToSymbol(g_ll_clk, z, sizeof(z));
 #endif
         cudaEventRecord(e0);
-        kern<<<grid, LL_WARPS * 32, smem>>>(dS, n_mo, n, dr, kb, dc, kk, dD);
+        kern<<<grid, LL_WARPS * 32, smem>>>(dS, n_mo, n, dr, kb, dc, kk, dD, dG);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         if (r >= 5) { best = std::min(best, ms); sum += ms; }
@@ -90,7 +95,7 @@ int main(int argc, char **argv) {
     const double fdet = n * (n - 1) / 2.0 + n * (n - 1) * (2.0 * n - 1) / 3.0 + n - 1;
     const double ms = sum / reps, tf = kb * (double)kk * fdet / ms / 1e9;
     const double clk_mat = ms * 1e-3 * 1.965e9 / (kb * (double)kk / (grid * LL_WARPS));
-    printf("n=%d NT=%d mode=%d pairs=%d warps/SM=%d ms=%.3f (best %.3f) TF/s=%.2f frac=%.3f clk/matrix/warp=%.0f max_rel_err=%.2e bad=%d\n", n, NTV, mode,
+    printf("MG=%d n=%d NT=%d mode=%d pairs=%d warps/SM=%d ms=%.3f (best %.3f) TF/s=%.2f frac=%.3f clk/matrix/warp=%.0f max_rel_err=%.2e bad=%d\n", (int)MGV, n, NTV, mode,
            kb * kk, per_sm * LL_WARPS, ms, best, tf, tf / 37.17, clk_mat, worst, bad);
 #ifdef WFO_LL_CLOCKS
     long long c[8]; cudaMemcpyFromSymbol(c, g_ll_clk, sizeof(c));
