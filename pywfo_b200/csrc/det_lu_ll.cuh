@@ -378,7 +378,9 @@ __device__ __forceinline__ double ll_lu_det(const double *__restrict__ S, int ld
 template <int NT, bool MG = false>
 struct LLWarps {
     static constexpr int SMEM = (227 * 1024) / LLCfg<NT, MG>::BYTES;
-    static constexpr int REG = NT >= 13 ? 8 : (NT >= 9 ? 10 : (NT >= 7 ? 12 : 16));   // register budget 65536 / (32 w)
+    // register budget 65536 / (32 w).  L2-scratch variant: 12 warps (168 registers, a few spilled) beat 8 up to
+    // n = 104 (n = 72: 5.6 -> 6.9 TFLOP/s, n = 88: 5.9 -> 7.2, n = 100: 5.0 -> 5.4), 8 warps win at n = 128
+    static constexpr int REG = MG ? (NT <= 13 ? 12 : 8) : (NT >= 13 ? 8 : (NT >= 9 ? 10 : (NT >= 7 ? 12 : 16)));
     static constexpr int W = SMEM < REG ? SMEM : REG;
 };
 inline size_t ll_scratch_doubles(int nt) { return (size_t)nt * (nt - 1) / 2 * 64; }   // per warp, MG variant
