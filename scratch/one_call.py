@@ -21,7 +21,7 @@ d_be = torch.tensor(bt.exc, dtype=torch.int32, device="cuda"); d_ke = torch.tens
 d_cb, d_ck = torch.tensor(bt.coeff, **f64), torch.tensor(kt.coeff, **f64)
 d_out = torch.empty((d_cb.shape[0], d_ck.shape[0]), **f64)
 lo, hi = ex.shard_bounds(bt.K, world, 0)
-if tier == "lu":
+if tier == "lu":   # 4096 pairs: what the round-1 captures used (the DRAM traffic is compared per 4096 pairs)
     hi = min(hi, 64); d_ke = d_ke[:64].contiguous(); d_ck = d_ck[:, :64].contiguous()
 for _ in range(3):
     ctx.state_overlaps_dev(d_smo, n, d_be, d_cb, d_ke, d_ck, d_out, tier=tier, k_begin=lo, k_end=hi,
