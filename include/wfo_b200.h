@@ -82,6 +82,13 @@ int wfo_sao_dev(wfo_ctx *ctx, const double *c_inv, int n, double *s_ao, void *st
  * pywfo/main.py:304 + :532, associated so that S_AO is never materialised (work: 2 n*n doubles or NULL). */
 int wfo_smo_inv_dev(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos, const double *c_inv, int n,
                     double *s_mo, double *work, void *stream);
+/* Optional: tell the context how many occupied orbitals the next state-overlap call will use (0 = off, the default).
+ * wfo_smo_inv_dev then forms the base block S_MO[:n_occ,:n_occ] (pywfo/main.py:548) first and inverts it on a side
+ * stream while the rest of S_MO is still being multiplied; the next wfo_state_overlaps_dev call on THAT s_mo buffer
+ * with that n_occ (same stream, s_mo untouched in between) picks the inverse up instead of computing it behind
+ * S_MO.  Only n_occ <= 128 is started early; results agree with the unhinted path to rounding (the base block is
+ * multiplied with another tile shape).  The raw-CI entry points do this on their own. */
+int wfo_set_occ_hint(wfo_ctx *ctx, int n_occ);
 /* a_inv = a^-1 (n x n), replaces np.linalg.inv in pywfo/main.py:303 (98, 212).
  * n <= 128: one launch of the register-resident Gauss-Jordan inverse with partial pivoting (csrc/lu_base.cuh).
  * n > 128, fast path: Newton-Schulz iteration X <- X (2I - A X) from X0 = A^T / |A^T A|_inf, i.e. nothing but

@@ -65,6 +65,7 @@ SIGNATURES = {
     "wfo_comm_status": (C.c_int, [c_vp]),
     "wfo_set_lu_variant": (C.c_int, [c_vp, C.c_int]),
     "wfo_last_tier": (C.c_int, [c_vp]),
+    "wfo_set_occ_hint": (C.c_int, [c_vp, C.c_int]),
     "wfo_set_timing": (C.c_int, [c_vp, C.c_int]),
     "wfo_last_kernel_ms": (C.c_double, [c_vp]),
     "wfo_last_phases": (C.c_int, [c_vp, c_dp, C.c_char_p, C.c_int]),
@@ -309,6 +310,10 @@ class Context:
             raise ValueError("work must hold 2 n*n doubles")
         check(self.lib.wfo_smo_inv_dev(self.handle, bra.data_ptr(), ket.data_ptr(), c_inv.data_ptr(), bra.shape[0],
                                        out.data_ptr(), work.data_ptr(), stream))
+
+    def set_occ_hint(self, n_occ):
+        """smo_inv_dev starts the inverse of S_MO[:n_occ,:n_occ] early for the next state-overlap call (0 = off)."""
+        check(self.lib.wfo_set_occ_hint(self.handle, int(n_occ)))
 
     def sao_dev(self, c_inv, out, stream=0):
         self._dev(c_inv, out)

@@ -466,6 +466,13 @@ int wfo_create(int device, wfo_ctx **out) {
     c->lu_variant = WFO_LU_AUTO;
     WFO_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     WFO_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    {   // the early base block is a short dependent chain next to wide GEMMs: its CTAs go first
+        int prio_lo = 0, prio_hi = 0;
+        WFO_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        WFO_CUDA(cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, prio_hi));
+    }
+    WFO_CUDA(cudaEventCreateWithFlags(&c->ev_pre_in, cudaEventDisableTiming));
+    WFO_CUDA(cudaEventCreateWithFlags(&c->ev_pre, cudaEventDisableTiming));
     WFO_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     WFO_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     WFO_CUDA(cudaEventCreate(&c->ev0));
@@ -501,6 +508,10 @@ int wfo_destroy(wfo_ctx *ctx) {
     for (int i = 0; i < 24; i++) cudaEventDestroy(ctx->pev[i]);
     cudaEventDestroy(ctx->ev_fork);
     cudaEventDestroy(ctx->ev_join);
+    if (ctx->pre_buf) cudaFree(ctx->pre_buf);
+    cudaEventDestroy(ctx->ev_pre_in);
+    cudaEventDestroy(ctx->ev_pre);
+    cudaStreamDestroy(ctx->stream3);
     cudaStreamDestroy(ctx->stream2);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -848,6 +859,13 @@ int wfo_set_lu_variant(wfo_ctx *ctx, int variant) {
 }
 
 int wfo_last_tier(const wfo_ctx *ctx) { return ctx ? ctx->last_tier : -1; }
+int wfo_set_occ_hint(wfo_ctx *ctx, int n_occ) {
+    if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL");
+    if (n_occ < 0) return set_err(WFO_ERR_ARG, "wfo_set_occ_hint: n_occ must be >= 0");
+    ctx->occ_hint = n_occ;
+    ctx->pre_smo = nullptr;
+    return WFO_OK;
+}
 int wfo_set_timing(wfo_ctx *ctx, int on) {
     if (!ctx) return set_err(WFO_ERR_ARG, "ctx is NULL");
     ctx->timing = on;
@@ -1051,6 +1069,41 @@ int wfo_smo_inv_dev(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos, 
     }
     double *P = work, *Q = work + nn;
     const ptrdiff_t dbytes = reinterpret_cast<const char *>(ket_mos) - reinterpret_cast<const char *>(bra_mos);
+    ctx->pre_smo = nullptr;
+    const int h = ctx->occ_hint;
+    if (h >= 1 && h <= LUB_MAXN && h <= n) {
+        // the base block first, on its own stream: A = (bra[:h] Cinv)(ket[:h] Cinv)^T, then its inverse (one CTA for
+        // ~0.8 us per column) next to the full products below instead of behind them
+        const size_t hn = (size_t)h * n, hh = (size_t)h * h;
+        const size_t want = (2 * hn + 2 * hh) * sizeof(double) + 256;
+        if (want > ctx->pre_bytes) {
+            WFO_CUDA(cudaDeviceSynchronize());
+            if (ctx->pre_buf) WFO_CUDA(cudaFree(ctx->pre_buf));
+            ctx->pre_buf = nullptr;
+            ctx->pre_bytes = 0;
+            WFO_CUDA(cudaMalloc(&ctx->pre_buf, want + want / 4));
+            ctx->pre_bytes = want + want / 4;
+        }
+        double *Ls = reinterpret_cast<double *>(ctx->pre_buf), *Rs = Ls + hn, *A = Rs + hn, *Ai = A + hh;
+        BaseInfo *info = reinterpret_cast<BaseInfo *>(Ai + hh);
+        cudaStream_t s3 = ctx->stream3;
+        WFO_CUDA(cudaEventRecord(ctx->ev_pre_in, st));
+        WFO_CUDA(cudaStreamWaitEvent(s3, ctx->ev_pre_in, 0));
+        if (bra_mos != ket_mos && dbytes % (ptrdiff_t)sizeof(double) == 0) {
+            WFO_TRY(gemm(ctx, false, false, h, n, n, 1.0, bra_mos, n, c_inv, n, 0.0, Ls, n, 0, (long long)hn, s3, 2,
+                         (long long)(dbytes / (ptrdiff_t)sizeof(double)), 0));
+        } else {
+            WFO_TRY(gemm(ctx, false, false, h, n, n, 1.0, bra_mos, n, c_inv, n, 0.0, Ls, n, 0, 0, s3));
+            WFO_TRY(gemm(ctx, false, false, h, n, n, 1.0, ket_mos, n, c_inv, n, 0.0, Rs, n, 0, 0, s3));
+        }
+        WFO_TRY(gemm(ctx, false, true, h, h, n, 1.0, Ls, n, Rs, n, 0.0, A, h, 0, 0, s3));
+        WFO_TRY(base_factor(ctx, A, h, h, Ai, h, info, nullptr, s3));
+        WFO_CUDA(cudaEventRecord(ctx->ev_pre, s3));
+        ctx->pre_smo = s_mo;
+        ctx->pre_n = h;
+        ctx->pre_Ai = Ai;
+        ctx->pre_info = info;
+    }
     if (bra_mos == ket_mos) {
         WFO_TRY(gemm(ctx, false, false, n, n, n, 1.0, bra_mos, n, c_inv, n, 0.0, P, n, 0, 0, st));
         Q = P;
@@ -1287,8 +1340,15 @@ static int state_overlaps_block(wfo_ctx *ctx, size_t arena_off, const double *s_
             WFO_LAUNCH_CHECK(ctx);
         }
         WFO_CUDA(cudaEventRecord(ctx->ev_join, s2));
-        // ---- one base factorisation, then the three block products
-        WFO_TRY(base_factor(ctx, s_mo, n_mo, n, p.Ai, n, p.info, p.bwork, st));
+        // ---- one base factorisation (or the one wfo_smo_inv_dev started early for this S_MO), then the three block products
+        if (ctx->pre_smo == s_mo && ctx->pre_n == n) {
+            p.Ai = ctx->pre_Ai;
+            p.info = ctx->pre_info;
+            WFO_CUDA(cudaStreamWaitEvent(st, ctx->ev_pre, 0));
+        } else {
+            WFO_TRY(base_factor(ctx, s_mo, n_mo, n, p.Ai, n, p.info, p.bwork, st));
+        }
+        ctx->pre_smo = nullptr;   // consumed (or not ours): never reused
         // the conditioning of the base block decides whether the rank-update tier is usable.  The
         // 32-byte verdict travels to pinned host memory behind the kernel; the rank-update kernels
         // are queued right away (speculatively) and the host looks at the verdict after queueing
@@ -1623,7 +1683,13 @@ static int overlaps_ci_core(wfo_ctx *ctx, const CiWork &w, const double *d_bra, 
         WFO_TRY(wfo_inverse_dev(ctx, ao_side == WFO_AO_BRA ? d_bra : d_ket, n_mo, w.inv, w.work, s2));
         d_inv = w.inv;
     }
-    WFO_TRY(wfo_smo_inv_dev(ctx, d_bra, d_ket, d_inv, n_mo, w.smo, w.work, s2));   // work, work2 contiguous
+    {   // the base block early (the rank-update tier will want it), whatever hint the caller has set
+        const int hint0 = ctx->occ_hint;
+        ctx->occ_hint = (tier == WFO_TIER_AUTO || tier == WFO_TIER_UPDATE) ? n : 0;
+        const int rc_ = wfo_smo_inv_dev(ctx, d_bra, d_ket, d_inv, n_mo, w.smo, w.work, s2);   // work, work2 contiguous
+        ctx->occ_hint = hint0;
+        if (rc_ != WFO_OK) return rc_;
+    }
     WFO_CUDA(cudaEventRecord(ctx->ev_join, s2));
     WFO_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     // ---- the table sizes (and per-state counts) come back: 2 small copies, one sync

@@ -79,6 +79,17 @@ struct wfo_ctx {
     size_t smem_optin;
     cudaStream_t stream;   // private stream of the *_host entry points
     cudaStream_t stream2;  // side stream: work that overlaps the single-CTA base factorisation
+    // early base block (wfo_set_occ_hint): wfo_smo_inv_dev forms S_MO[:occ,:occ] first and inverts it on stream3
+    // while the rest of S_MO is still being multiplied; the next state-overlap call on that S_MO picks it up
+    cudaStream_t stream3;
+    cudaEvent_t ev_pre_in, ev_pre;
+    int occ_hint;
+    char *pre_buf;
+    size_t pre_bytes;
+    const double *pre_smo;   // the S_MO buffer the stashed inverse belongs to (valid until consumed)
+    int pre_n;
+    double *pre_Ai;
+    wfo::BaseInfo *pre_info;
     cudaEvent_t ev_fork, ev_join;
     double *ns_slots;      // device: norms + per-iteration residuals of the Newton-Schulz inverse (128 doubles)
     double *h_slots;       // pinned host mirror

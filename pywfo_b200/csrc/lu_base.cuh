@@ -1,8 +1,8 @@
 // Base-block factorisation for the rank-update tiers: in-place Gauss-Jordan inverse with
-// partial (row) pivoting of A = S_MO[:n,:n] (n <= 128) in ONE CTA of 512 threads, REGISTER
-// resident (32 matrix elements per thread).  Pivoting is implicit (rows never move), the
-// row/column permutation is undone when the inverse is written out.
-// Produces Ai = A^-1, det(A) and min/max |pivot| as a conditioning indicator.
+// partial (row) pivoting of A = S_MO[:n,:n] (n <= 128) in ONE CTA, REGISTER resident (32 matrix
+// elements per thread), blocked by panels of 8 columns and pipelined over the warps WITHOUT block
+// barriers.  Pivoting is implicit (rows never move), the row/column permutation is undone when the
+// inverse is written out.  Produces Ai = A^-1, det(A) and min/max |pivot| as a conditioning indicator.
 //
 // This is the "one base LU" that north_star's rank-1 (Sherman-Morrison / cofactor) updates
 // reuse; upstream the same numbers would come from np.linalg.det / np.linalg.inv of
@@ -29,182 +29,259 @@ __device__ long long g_lub_clk[16];
 constexpr int LUB_MAXN = 128;
 constexpr int LUB_THREADS = 512;
 constexpr int LUB_WARPS = LUB_THREADS / 32;   // 16
-constexpr int LUB_CS = LUB_MAXN / LUB_WARPS;  // 8 column slots per thread (columns warp + 16 c)
+constexpr int LUB_CS = LUB_MAXN / LUB_WARPS;  // 8 columns per warp = one panel (columns 8 warp + c)
 constexpr int LUB_RS = 4;                     // 4 row slots per thread (rows 4 lane + s)
 constexpr int LUB_LDS = LUB_MAXN + 1;         // row stride of the staging tile
-inline size_t lub_smem_bytes(int n) { return (size_t)n * LUB_LDS * sizeof(double); }
+// staging tile (n x LUB_LDS) on entry / exit; in between the same memory holds the multiplier panels
+// (ceil(n/8) panels x 8 columns x row stride 4 ceil(n/4))
+inline size_t lub_smem_bytes(int n) {
+    const size_t tile = (size_t)n * LUB_LDS, panels = (size_t)((n + 7) / 8) * 8 * ((n + 3) & ~3);
+    return (tile > panels ? tile : panels) * sizeof(double);
+}
 
-// A_src: n x n block with leading dimension ld_src.  Ai_out: n x n, leading dimension ld_out.
-// Dynamic shared memory: lub_smem_bytes(n) (staging tile for coalesced load / store).
-//
-// Ownership: lane l holds rows 4l..4l+3, warp w holds columns w, w+16, ..., w+112, so
-//   * column j lives entirely in ONE warp (j mod 16): the pivot search is 4 compares per lane and
-//     one REDUX inside that warp -- no shared memory, no barrier;
-//   * row p lives in lane p/4 of EVERY warp: each warp passes its part of the pivot row through a
-//     warp-private shared buffer (one lane writes, the warp reads it back) -- no block barrier;
+// Ownership: lane l holds rows 4l..4l+3, warp w holds columns 8w..8w+7 (= panel w), so
+//   * a panel is factored by ONE warp on its own: per column 4 compares per lane and one REDUX, the
+//     pivot row is exchanged inside the warp, no block barrier; the reciprocal of the pivot is computed
+//     speculatively by every lane for its own best candidate while the reduction is in flight;
 //   * the update is branch- and select-free: the pivot row's own multiplier is published as d - 1,
 //     so that a_p - (d-1) (a_p / d) = a_p / d comes out of the same multiply-add as every other row;
-//   * only the multiplier column (and p, 1/pivot) goes through block-shared memory: ONE block barrier
-//     per elimination step, and the warp that owns the next column updates that column first,
-//     searches its pivot and publishes it while the other warps still work on the current step;
+//   * the panel's multiplier columns M_k (n x 8), pivot rows and reciprocals are PUBLISHED to shared memory
+//     and a flag is raised; every other warp applies the panel to its own 8 columns when it gets there:
+//       raw_s = its part of pivot row s (as it was before the panel), s = 0..7
+//       pr_s  = (raw_s - sum_{s'<s} M_k[p_s][s'] pr_s') / d_s          (8 x 8 triangular recurrence)
+//       a    -= sum_s M_k[:, s] pr_s                                    (rank-8 update, 256 FMA per thread)
+//     Each panel has its own shared-memory region (the staging tile is free once the registers are
+//     loaded), so nothing is ever overwritten and no warp waits for a slower consumer: warp k+1 applies
+//     panel k and factors panel k+1 while the other warps are still busy with older panels;
 //   * det / min / max pivot are accumulated by the owning warps and combined at the end.
-// The factorisation itself: lub_tile (n x n, row stride LUB_LDS, shared memory) holds A on entry and, unless
-// the matrix is singular, A^-1 on return (all threads synchronised).  Every thread returns det(A), min/max |pivot|
-// and the singular flag.  Shared by base_inverse_kernel (one matrix) and cofactor_rows_kernel (a batch).
+// The factorisation itself: lub_tile (n x n, row stride LUB_LDS, shared memory, lub_smem_bytes(n) bytes) holds A
+// on entry and, unless the matrix is singular, A^-1 on return (all threads synchronised).  Every thread returns
+// det(A), min/max |pivot| and the singular flag.  Shared by base_inverse_kernel (one matrix) and
+// cofactor_rows_kernel (a batch).  (Round 1's version took one block barrier per COLUMN: 81 us at n = 100.)
 __device__ __forceinline__ void lub_invert_tile(double *lub_tile, int n, double &det_out, double &min_out, double &max_out,
                                                 int &sing_out) {
-    __shared__ __align__(16) double mcol[2][LUB_MAXN];    // multiplier column, double buffered by step parity
-    __shared__ __align__(16) double prow[LUB_WARPS][LUB_CS];   // warp-private: this warp's part of the pivot row
-    __shared__ double prd[2];                             // reciprocal of the pivot
-    __shared__ int pp[2];                                 // pivot row (-1: no candidate left)
-    __shared__ int piv_of_col[LUB_MAXN];                  // p_j: pivot row chosen for column j
-    __shared__ int col_of_piv[LUB_MAXN];                  // inverse map
+    __shared__ __align__(16) double rowbuf[LUB_WARPS][8][LUB_CS];   // warp-private: pivot rows in this warp's columns, then pr
+    __shared__ __align__(16) double2 prec[LUB_MAXN];                // per column step: (1 / pivot, pivot row in the low word)
+    __shared__ __align__(8) unsigned long long pbar[LUB_MAXN];       // mbarrier j completes when column step j has been published
+    __shared__ int piv_of_col[LUB_MAXN];                            // p_j: pivot row chosen for column j
+    __shared__ int col_of_piv[LUB_MAXN];                            // inverse map
     __shared__ double wdet[LUB_WARPS], wmin[LUB_WARPS], wmax[LUB_WARPS];
     __shared__ int wsing[LUB_WARPS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
+    const int np = (n + 7) >> 3;          // panels = active warps
+    const int rs = (n + 3) & ~3;          // row stride of one multiplier column
+    double a[LUB_RS][LUB_CS];
+    unsigned kmask[LUB_RS];   // 0 once row 4 lane + s is a used pivot row (or beyond n), else the key mask
+#pragma unroll
+    for (int s = 0; s < LUB_RS; s++) {
+        const int r = 4 * lane + s;
+        kmask[s] = (r < n) ? 0x7fffff00u : 0u;
+#pragma unroll
+        for (int c = 0; c < LUB_CS; c++) {
+            const int col = LUB_CS * warp + c;
+            a[s][c] = (r < n && col < n) ? lub_tile[r * LUB_LDS + col] : 0.0;
+        }
+    }
+    if (tid < LUB_MAXN) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"((unsigned)__cvta_generic_to_shared(&pbar[tid])));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    double det = 1.0, minp = 1e300, maxp = 0.0;   // over the columns this warp owns
+    int singular = 0;
+    __syncthreads();   // the tile is free: it now holds M_k[s][i] at lub_tile[(8 k + s) rs + i]
+
+#define LUB_STS_PRED(PTR_, X_, Y_, PRED_)                                                        \
+    asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %3, 0;\n@q st.shared.v2.f64 [%0], {%1, %2};\n}\n" ::     \
+                 "r"((unsigned)__cvta_generic_to_shared(PTR_)), "d"(X_), "d"(Y_), "r"((int)(PRED_)) : "memory")
+#define LUB_ROW_OUT(S_, DST_)                                                                   \
+    _Pragma("unroll") for (int c = 0; c < LUB_CS; c += 2)                                       \
+        *reinterpret_cast<double2 *>((DST_) + c) = make_double2(a[S_][c], a[S_][c + 1]);
+#define LUB_ROW_SWITCH(PS_, DST_)                                                               \
+    switch (PS_) {   /* static register indices */                                              \
+        case 0: LUB_ROW_OUT(0, DST_) break;                                                     \
+        case 1: LUB_ROW_OUT(1, DST_) break;                                                     \
+        case 2: LUB_ROW_OUT(2, DST_) break;                                                     \
+        default: LUB_ROW_OUT(3, DST_) break;                                                    \
+    }
+
 #ifdef WFO_LUB_CLOCKS
     long long t_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long t_prev = clock64();
 #endif
-    double a[LUB_RS][LUB_CS];
-    unsigned donemask = 0;   // bit s: row 4 lane + s is a used pivot row or beyond n
-#pragma unroll
-    for (int s = 0; s < LUB_RS; s++) {
-        const int r = 4 * lane + s;
-        if (!(r < n)) donemask |= 1u << s;
-#pragma unroll
-        for (int c = 0; c < LUB_CS; c++) {
-            const int col = warp + LUB_WARPS * c;
-            a[s][c] = (r < n && col < n) ? lub_tile[r * LUB_LDS + col] : 0.0;
-        }
-    }
-    double det = 1.0, minp = 1e300, maxp = 0.0;   // over the columns this warp owns
-    int singular = 0;
-
-    // pivot search in column slot C of this warp + publication (multipliers, pivot row index,
-    // reciprocal) for step J; then the slot restarts as the unit column e_p (in-place Gauss-Jordan)
-#define LUB_PUBLISH(C, B, J)                                                                               \
-    do {                                                                                                   \
-        unsigned key = 0;                                                                                  \
-        _Pragma("unroll") for (int s = 0; s < LUB_RS; s++) {                                               \
-            const unsigned k = (hi_abs(a[s][C]) & 0xffffff00u) | 0x80u | (unsigned)(4 * lane + s);         \
-            key = max(key, ((donemask >> s) & 1u) ? 0u : k);                                               \
-        }                                                                                                  \
-        const unsigned kmax = __reduce_max_sync(FULL, key);                                                \
-        const int p_ = (kmax != 0u) ? (int)(kmax & 0x7fu) : -1;                                            \
-        const int ps_ = p_ & 3, pl_ = (p_ >> 2) & 31;                                                      \
-        double cand = a[0][C];                                                                             \
-        cand = (ps_ == 1) ? a[1][C] : cand;                                                                \
-        cand = (ps_ == 2) ? a[2][C] : cand;                                                                \
-        cand = (ps_ == 3) ? a[3][C] : cand;                                                                \
-        const double d_ = __shfl_sync(FULL, cand, pl_);                                                    \
-        /* multipliers; the pivot row's own entry is d - 1, so that a_p - (d-1) (a_p/d) = a_p/d */        \
-        double m_[LUB_RS];                                                                                 \
-        _Pragma("unroll") for (int s = 0; s < LUB_RS; s++) m_[s] = (4 * lane + s == p_) ? d_ - 1.0 : a[s][C]; \
-        *reinterpret_cast<double2 *>(&mcol[B][4 * lane]) = make_double2(m_[0], m_[1]);                     \
-        *reinterpret_cast<double2 *>(&mcol[B][4 * lane + 2]) = make_double2(m_[2], m_[3]);                 \
-        if (lane == 0) {                                                                                   \
-            prd[B] = fast_rcp(d_);                                                                         \
-            pp[B] = p_;                                                                                    \
-            piv_of_col[J] = p_;                                                                            \
-            col_of_piv[p_ & 127] = J;                                                                      \
-        }                                                                                                  \
-        const double ad_ = fabs(d_);                                                                       \
-        singular |= (p_ < 0 || !(ad_ > 0.0) || !(ad_ < 1e300)) ? 1 : 0;                                    \
-        det *= d_;                                                                                         \
-        minp = fmin(minp, ad_);                                                                            \
-        maxp = fmax(maxp, ad_);                                                                            \
-        _Pragma("unroll") for (int s = 0; s < LUB_RS; s++) a[s][C] = (4 * lane + s == p_) ? 1.0 : 0.0;    \
+    if (warp < np) {
+        for (int k = 0; k < np; k++) {
+            double *Mk = lub_tile + (size_t)k * 8 * rs;
+            const int ns = min(8, n - 8 * k);
+            if (warp == k) {
+                LUB_T(5);
+                // ---- factor this warp's own panel: column slot s is column 8 k + s.
+                // Software pipelined by hand: the dependent chain of a step is only
+                //     keys of column s -> REDUX -> three shuffles (pivot, its reciprocal, the pivot row's entry in
+                //     column s+1) -> multipliers -> update of column s+1 -> keys of column s+1;
+                // the rest of step s (pivot row through shared memory, the other 28 multiply-adds per thread, the
+                // multiplier column, bookkeeping) is issued behind the NEXT step's reduction, in its latency shadow.
+                double m_prev[LUB_RS] = {0.0, 0.0, 0.0, 0.0};
+                double rd_prev = 0.0;
+                int p_prev = 0;
+                unsigned kbad = 0;  // a step found no candidate
+                // the deferred part of step S_ (static)
+#define LUB_DEFERRED(S_)                                                                                      \
+    do {                                                                                                      \
+        __syncwarp();   /* the pivot row of step S_ is in rowbuf */                                           \
+        double pr_[LUB_CS];                                                                                   \
+        _Pragma("unroll") for (int c = 0; c < LUB_CS; c += 2) {                                               \
+            const double2 v = *reinterpret_cast<const double2 *>(&rowbuf[warp][S_][c]);                       \
+            pr_[c] = v.x * rd_prev;                                                                           \
+            pr_[c + 1] = v.y * rd_prev;                                                                       \
+        }                                                                                                     \
+        pr_[S_] = rd_prev;   /* column S_ of the pivot row is the unit column's 1 */                          \
+        _Pragma("unroll") for (int c = 0; c < LUB_CS; c++) {                                                  \
+            if (c == (S_) + 1) continue;   /* done ahead of time */                                           \
+            _Pragma("unroll") for (int r = 0; r < LUB_RS; r++) a[r][c] = fma(-m_prev[r], pr_[c], a[r][c]);    \
+        }                                                                                                     \
+        if (4 * lane < rs) {                                                                                  \
+            *reinterpret_cast<double2 *>(Mk + (S_) * rs + 4 * lane) = make_double2(m_prev[0], m_prev[1]);     \
+            *reinterpret_cast<double2 *>(Mk + (S_) * rs + 4 * lane + 2) = make_double2(m_prev[2], m_prev[3]); \
+        }                                                                                                     \
+        if (lane == 0) *reinterpret_cast<double2 *>(&prec[8 * k + (S_)]) = make_double2(rd_prev, __hiloint2double(0, p_prev)); \
+        __syncwarp();   /* orders the other lanes' stores before lane 0's release */                          \
+        if (lane == 0)   /* column step 8 k + S_ is published */                                              \
+            asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];\n" ::"r"(                      \
+                (unsigned)__cvta_generic_to_shared(&pbar[8 * k + (S_)])) : "memory");                         \
     } while (0)
-
-    LUB_T(0);
-    if (warp == 0 && n > 0) LUB_PUBLISH(0, 0, 0);
-    __syncthreads();
-    LUB_T(1);
-
 #pragma unroll
-    for (int cj = 0; cj < LUB_CS; cj++) {           // column slot of the current step (static register index)
-        const int nsteps = min(LUB_WARPS, n - LUB_WARPS * cj);
-        for (int wj = 0; wj < nsteps; wj++) {       // owning warp
-            const int j = wj + LUB_WARPS * cj;
-            const int b = j & 1;
-            LUB_T(2);
-            const int p = pp[b];
-            const double rd = prd[b];
-            const int ps = p & 3, pl = (p >> 2) & 31;
-            // this warp's part of the pivot row: lane pl writes it (slot ps), everybody reads it back
-            if (lane == pl) {
-                switch (ps) {   // static register indices
-#define LUB_ROW(S_)                                                                              \
-    _Pragma("unroll") for (int c = 0; c < LUB_CS; c += 2)                                        \
-        *reinterpret_cast<double2 *>(&prow[warp][c]) = make_double2(a[S_][c], a[S_][c + 1]);
-                    case 0: LUB_ROW(0) break;
-                    case 1: LUB_ROW(1) break;
-                    case 2: LUB_ROW(2) break;
-                    default: LUB_ROW(3) break;
-#undef LUB_ROW
+                for (int s = 0; s < 8; s++) {
+                    if (s < ns) {   // uniform
+                        unsigned key = 0;
+#pragma unroll
+                        for (int r = 0; r < LUB_RS; r++)   // kmask: 0x7fffff00 for a free row, 0 for a used one
+                            key = max(key, ((unsigned)__double2hiint(a[r][s]) & kmask[r]) | (0x80u + (unsigned)(4 * lane + r)));
+                        const unsigned kmax = __reduce_max_sync(FULL, key);
+                        // this lane's own best candidate and its reciprocal: if this lane wins, these ARE the pivot
+                        // and 1/pivot (computed in the shadow of the reduction)
+                        const int bs = key & 3;
+                        double cand = a[0][s];
+                        cand = (bs == 1) ? a[1][s] : cand;
+                        cand = (bs == 2) ? a[2][s] : cand;
+                        cand = (bs == 3) ? a[3][s] : cand;
+                        const double rc_own = fast_rcp(cand);
+                        if (s > 0) LUB_DEFERRED(s - 1);
+                        // (after the deferred update of column s+1) the candidate's neighbour in the next column
+                        double nxt = a[0][(s + 1) & 7];
+                        nxt = (bs == 1) ? a[1][(s + 1) & 7] : nxt;
+                        nxt = (bs == 2) ? a[2][(s + 1) & 7] : nxt;
+                        nxt = (bs == 3) ? a[3][(s + 1) & 7] : nxt;
+                        kbad |= (kmax < 0x100u) ? 1u : 0u;
+                        const int p = (int)(kmax & 0x7fu);
+                        const int pl = p >> 2;
+                        const double d = __shfl_sync(FULL, cand, pl);
+                        const double rd = __shfl_sync(FULL, rc_own, pl);
+                        const double v1 = __shfl_sync(FULL, nxt, pl);
+                        const double pr1 = v1 * rd;
+                        // multipliers = the column itself; the slot restarts as the unit column e_p (in-place Gauss-Jordan);
+                        // the pivot row's own multiplier is d - 1, so that a_p - (d-1) (a_p/d) = a_p/d
+                        double m[LUB_RS];
+#pragma unroll
+                        for (int r = 0; r < LUB_RS; r++) m[r] = a[r][s];
+                        {   // the winner's row goes out, its slot is marked used: predicated, no branch
+                            const double dm1 = d - 1.0;
+                            double *dst = &rowbuf[warp][s][0];
+#pragma unroll
+                            for (int r = 0; r < LUB_RS; r++) {
+                                const bool isp = (4 * lane + r == p);
+#pragma unroll
+                                for (int c = 0; c < LUB_CS; c += 2) LUB_STS_PRED(dst + c, a[r][c], a[r][c + 1], isp);
+                                m[r] = isp ? dm1 : m[r];
+                                a[r][s] = isp ? 1.0 : 0.0;
+                                kmask[r] = isp ? 0u : kmask[r];
+                            }
+                        }
+#pragma unroll
+                        for (int r = 0; r < LUB_RS; r++) {
+                            if (s + 1 < 8) a[r][(s + 1) & 7] = fma(-m[r], pr1, a[r][(s + 1) & 7]);   // the next pivot column first
+                            m_prev[r] = m[r];
+                        }
+                        rd_prev = rd;
+                        p_prev = p;
+                        {   // statistics and the permutation tables: nobody waits for these
+                            const double ad = fabs(d);
+                            singular |= (!(ad > 0.0) || !(ad < 1e300)) ? 1 : 0;
+                            det *= d;
+                            minp = fmin(minp, ad);
+                            maxp = fmax(maxp, ad);
+                            if (lane == 0) {
+                                piv_of_col[8 * k + s] = p;
+                                col_of_piv[p] = 8 * k + s;
+                            }
+                        }
+                    }
+                }
+                // the last step's deferred part (ns is 8 except in a ragged last panel)
+                switch (ns) {
+                    case 1: LUB_DEFERRED(0); break;
+                    case 2: LUB_DEFERRED(1); break;
+                    case 3: LUB_DEFERRED(2); break;
+                    case 4: LUB_DEFERRED(3); break;
+                    case 5: LUB_DEFERRED(4); break;
+                    case 6: LUB_DEFERRED(5); break;
+                    case 7: LUB_DEFERRED(6); break;
+                    default: LUB_DEFERRED(7); break;
+                }
+                singular |= (int)kbad;
+#undef LUB_DEFERRED
+                LUB_T(4);
+            } else {
+                // ---- apply the column steps of panel k to this warp's columns, one by one as they are published
+#pragma unroll 1
+                for (int sj = 0; sj < ns; sj++) {
+                    // (a hardware-suspended wait: polling a flag from 15 warps starved the factoring warp of issue slots and LSU)
+                    asm volatile(
+                        "{\n.reg .pred p;\nLUB_WAIT:\n"
+                        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], 0;\n"
+                        "@p bra LUB_DONE;\nbra LUB_WAIT;\nLUB_DONE:\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(&pbar[8 * k + sj])) : "memory");
+                    const double2 rec = prec[8 * k + sj];
+                    const double rdj = rec.x;
+                    const int pj = __double2loint(rec.y);
+                    double *rb = &rowbuf[warp][sj][0];
+#pragma unroll
+                    for (int r = 0; r < LUB_RS; r++) {   // predicated, no branch; a used pivot row leaves the search
+                        const bool isp = (4 * lane + r == pj);
+#pragma unroll
+                        for (int c = 0; c < LUB_CS; c += 2) LUB_STS_PRED(rb + c, a[r][c], a[r][c + 1], isp);
+                        kmask[r] = isp ? 0u : kmask[r];
+                    }
+                    double2 m01 = make_double2(0.0, 0.0), m23 = m01;
+                    if (4 * lane < rs) {
+                        m01 = *reinterpret_cast<const double2 *>(Mk + sj * rs + 4 * lane);
+                        m23 = *reinterpret_cast<const double2 *>(Mk + sj * rs + 4 * lane + 2);
+                    }
+                    const double m[LUB_RS] = {m01.x, m01.y, m23.x, m23.y};
+                    __syncwarp();
+                    double pr[LUB_CS];
+#pragma unroll
+                    for (int c = 0; c < LUB_CS; c += 2) {
+                        const double2 v = *reinterpret_cast<const double2 *>(rb + c);
+                        pr[c] = v.x * rdj;
+                        pr[c + 1] = v.y * rdj;
+                    }
+#pragma unroll
+                    for (int c = 0; c < LUB_CS; c++)
+#pragma unroll
+                        for (int r = 0; r < LUB_RS; r++) a[r][c] = fma(-m[r], pr[c], a[r][c]);
                 }
             }
-            __syncwarp();
-            double pr[LUB_CS];
-#pragma unroll
-            for (int c = 0; c < LUB_CS; c += 2) {
-                const double2 v = *reinterpret_cast<const double2 *>(&prow[warp][c]);
-                pr[c] = v.x * rd;
-                pr[c + 1] = v.y * rd;
-            }
-            LUB_T(3);
-            // multipliers of this lane's rows
-            const double2 f01 = *reinterpret_cast<const double2 *>(&mcol[b][4 * lane]);
-            const double2 f23 = *reinterpret_cast<const double2 *>(&mcol[b][4 * lane + 2]);
-            const double f[LUB_RS] = {f01.x, f01.y, f23.x, f23.y};
-            donemask |= (lane == pl) ? (1u << ps) : 0u;
-            LUB_T(4);
-            // look-ahead: the owner of the next column updates it first and publishes its pivot
-            const int jn = j + 1;
-            const bool own_next = (jn < n) && (warp == (jn & (LUB_WARPS - 1)));
-            if (jn < n) {
-                if (wj + 1 < LUB_WARPS) {           // next column is in the same slot cj
-                    if (own_next) {
-#pragma unroll
-                        for (int s = 0; s < LUB_RS; s++) a[s][cj] = fma(-f[s], pr[cj], a[s][cj]);
-                        LUB_PUBLISH(cj, b ^ 1, jn);
-                    }
-                } else if (cj + 1 < LUB_CS) {       // next column is slot cj + 1 of warp 0
-                    if (own_next) {
-#pragma unroll
-                        for (int s = 0; s < LUB_RS; s++)
-                            a[s][(cj + 1) % LUB_CS] = fma(-f[s], pr[(cj + 1) % LUB_CS], a[s][(cj + 1) % LUB_CS]);
-                        LUB_PUBLISH((cj + 1) % LUB_CS, b ^ 1, jn);
-                    }
-                }
-            }
-            LUB_T(5);
-            // the rest of the update (the column handled by the look-ahead is skipped by its owner)
-            const int skip = !own_next ? -1 : ((wj + 1 < LUB_WARPS) ? cj : cj + 1);
-#pragma unroll
-            for (int c = 0; c < LUB_CS; c++) {
-                if (c == skip) continue;
-#pragma unroll
-                for (int s = 0; s < LUB_RS; s++) a[s][c] = fma(-f[s], pr[c], a[s][c]);
-            }
-            // keep the bulk update on this side of the barrier: sunk into the next step it would sit in
-            // front of that step's critical path (pivot row exchange -> look-ahead publish)
-#pragma unroll
-            for (int c = 0; c < LUB_CS; c++)
-#pragma unroll
-                for (int s = 0; s < LUB_RS; s++) asm volatile("" : "+d"(a[s][c]));
-            LUB_T(6);
-            __syncthreads();
-            LUB_T(7);
         }
     }
-#undef LUB_PUBLISH
-    LUB_T(8);
+#undef LUB_ROW_SWITCH
+#undef LUB_ROW_OUT
+#ifdef WFO_LUB_CLOCKS
+    if (tid == 32 * (np > 1 ? np / 2 : 0)) for (int i = 0; i < 10; i++) g_lub_clk[i] = t_acc[i];
+#endif
     // ---- combine the per-warp pivot statistics
     if (lane == 0) { wdet[warp] = det; wmin[warp] = minp; wmax[warp] = maxp; wsing[warp] = singular; }
-    __syncthreads();
+    __syncthreads();   // also: every panel has been applied everywhere, the panel memory is free again
+    if (tid < LUB_MAXN) asm volatile("mbarrier.inval.shared::cta.b64 [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(&pbar[tid])) : "memory");
     double tdet = 1.0, tmin = 1e300, tmax = 0.0;
     int tsing = 0;
 #pragma unroll
@@ -224,7 +301,7 @@ __device__ __forceinline__ void lub_invert_tile(double *lub_tile, int n, double 
                 const int orow = col_of_piv[r];
 #pragma unroll
                 for (int c = 0; c < LUB_CS; c++) {
-                    const int col = warp + LUB_WARPS * c;
+                    const int col = LUB_CS * warp + c;
                     if (col < n) lub_tile[orow * LUB_LDS + piv_of_col[col]] = a[s][c];
                 }
             }
@@ -235,10 +312,6 @@ __device__ __forceinline__ void lub_invert_tile(double *lub_tile, int n, double 
     if (!tsing && tid < n)
         for (int k = tid + 1; k < n; k++) inv += piv_of_col[k] < piv_of_col[tid];
     const int par = __syncthreads_count(inv & 1) & 1;   // also: the permuted inverse in lub_tile is complete
-    LUB_T(9);
-#ifdef WFO_LUB_CLOCKS
-    if (tid == 32) for (int i = 0; i < 10; i++) g_lub_clk[i] = t_acc[i];
-#endif
     det_out = tsing ? 0.0 : (par ? -tdet : tdet);
     min_out = tmin;
     max_out = tmax;

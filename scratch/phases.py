@@ -33,7 +33,8 @@ stream = torch.cuda.current_stream().cuda_stream
 ctx.set_timing(2)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-for world in (1, 8):
+for world, hint in ((1, 0), (1, n), (8, 0), (8, n)):
+    ctx.set_occ_hint(hint)
     lo, hi = ex.shard_bounds(bt.K, world, 0)
     acc = {}
     order = []
@@ -58,6 +59,6 @@ for world in (1, 8):
                 acc[name] = []
                 order.append(name)
             acc[name].append(ms)
-    print(f"--- {wname} shard 1/{world}: step {np.mean(tot)*1e3:.1f} us, sao+smo {np.mean(pre)*1e3:.1f} us")
+    print(f"--- {wname} shard 1/{world} occ_hint={hint}: step {np.mean(tot)*1e3:.1f} us, sao+smo {np.mean(pre)*1e3:.1f} us")
     for name in order:
         print(f"   {name:16s} {np.mean(acc[name])*1e3:9.1f} us")
