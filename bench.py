@@ -248,6 +248,7 @@ def run_ours(args, w):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     stream = torch.cuda.current_stream().cuda_stream
     ctx.set_timing(True)
+    ctx.set_occ_hint(n if tier in ("auto", "update") else 0)   # smo_inv_dev starts the base-block inverse early
     peer_collective = world > 1 and wdist.has_comm(ctx)
 
     def step():

@@ -139,9 +139,9 @@ static int copy2d(wfo_ctx *ctx, const double *src, int ld_src, double *dst, int 
     return WFO_OK;
 }
 static int base_factor(wfo_ctx *ctx, const double *A, int lda, int n, double *Ai, int ldo, BaseInfo *info, double *work,
-                       cudaStream_t st) {
+                       cudaStream_t st, int n_slabs = 1, long long slab_stride = 0) {
     if (n <= LUB_MAXN) {
-        base_inverse_kernel<<<1, LUB_THREADS, lub_smem_bytes(n), st>>>(A, lda, n, Ai, ldo, info);
+        base_inverse_kernel<<<1, LUB_THREADS, lub_smem_bytes(n), st>>>(A, lda, n, Ai, ldo, info, n_slabs, slab_stride, nullptr, 0);
         WFO_LAUNCH_CHECK(ctx);
         return WFO_OK;
     }
@@ -470,6 +470,9 @@ int wfo_create(int device, wfo_ctx **out) {
         int prio_lo = 0, prio_hi = 0;
         WFO_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         WFO_CUDA(cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, prio_hi));
+        WFO_CUDA(cudaStreamCreateWithPriority(&c->stream4, cudaStreamNonBlocking, prio_hi));
+        WFO_CUDA(cudaMalloc(&c->pre_flag, sizeof(int)));
+        WFO_CUDA(cudaMemset(c->pre_flag, 0, sizeof(int)));
     }
     WFO_CUDA(cudaEventCreateWithFlags(&c->ev_pre_in, cudaEventDisableTiming));
     WFO_CUDA(cudaEventCreateWithFlags(&c->ev_pre, cudaEventDisableTiming));
@@ -479,7 +482,7 @@ int wfo_create(int device, wfo_ctx **out) {
     WFO_CUDA(cudaEventCreate(&c->ev1));
     for (int i = 0; i < 24; i++) WFO_CUDA(cudaEventCreate(&c->pev[i]));
     WFO_CUDA(cudaFuncSetAttribute(base_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)lub_smem_bytes(LUB_MAXN)));
+                                  (int)(LUB_EXCL_SMEM > lub_smem_bytes(LUB_MAXN) ? LUB_EXCL_SMEM : lub_smem_bytes(LUB_MAXN))));
     WFO_CUDA(cudaMalloc(&c->ns_slots, 128 * sizeof(double)));
     WFO_CUDA(cudaMallocHost(&c->h_slots, 128 * sizeof(double)));
     WFO_CUDA(cudaMallocHost(&c->h_info, sizeof(BaseInfo)));
@@ -512,6 +515,8 @@ int wfo_destroy(wfo_ctx *ctx) {
     cudaEventDestroy(ctx->ev_pre_in);
     cudaEventDestroy(ctx->ev_pre);
     cudaStreamDestroy(ctx->stream3);
+    cudaStreamDestroy(ctx->stream4);
+    if (ctx->pre_flag) cudaFree(ctx->pre_flag);
     cudaStreamDestroy(ctx->stream2);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -947,7 +952,7 @@ int wfo_inverse_dev(wfo_ctx *ctx, const double *a, int n, double *a_inv, double 
         // kernel behind the base block of the rank-update tier) instead of a dozen launches of Newton-Schulz:
         // these sizes are launch-latency bound (bundled pywfo tests: n_mo = 24 ... 38)
         BaseInfo *d_info = reinterpret_cast<BaseInfo *>(ctx->ns_slots);
-        base_inverse_kernel<<<1, LUB_THREADS, lub_smem_bytes(n), st>>>(a, n, n, a_inv, n, d_info);
+        base_inverse_kernel<<<1, LUB_THREADS, lub_smem_bytes(n), st>>>(a, n, n, a_inv, n, d_info, 1, 0, nullptr, 0);
         WFO_LAUNCH_CHECK(ctx);
         WFO_CUDA(cudaMemcpyAsync(ctx->h_slots, d_info, sizeof(BaseInfo), cudaMemcpyDeviceToHost, st));
         WFO_CUDA(cudaStreamSynchronize(st));
@@ -1057,6 +1062,13 @@ int wfo_inverse_host(wfo_ctx *ctx, const double *a, int n, double *a_inv) {
  * Same product as pywfo/main.py:304 + :532 with the matrix chain associated the other way: two
  * launches (the two left factors as one batched GEMM, then P Q^T) instead of three dependent ones,
  * and S_AO is never materialised.  work: 2 n*n doubles. */
+#ifdef WFO_DEBUG_PRE   // scratch builds: timeline of the early base-block chain against the main products
+static cudaEvent_t g_dbg[8];
+static bool g_dbg_init = false;
+#define DBG_EV(i, s) do { if (!g_dbg_init) { for (auto &e_ : g_dbg) cudaEventCreate(&e_); g_dbg_init = true; } cudaEventRecord(g_dbg[i], s); } while (0)
+#else
+#define DBG_EV(i, s)
+#endif
 int wfo_smo_inv_dev(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos, const double *c_inv, int n,
                     double *s_mo, double *work, void *stream) {
     if (!ctx || !bra_mos || !ket_mos || !c_inv || !s_mo) return set_err(WFO_ERR_ARG, "smo_inv: NULL argument");
@@ -1071,11 +1083,13 @@ int wfo_smo_inv_dev(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos, 
     const ptrdiff_t dbytes = reinterpret_cast<const char *>(ket_mos) - reinterpret_cast<const char *>(bra_mos);
     ctx->pre_smo = nullptr;
     const int h = ctx->occ_hint;
-    if (h >= 1 && h <= LUB_MAXN && h <= n) {
+    if (h >= 1 && h <= LUB_MAXN && h <= n && n >= 96) {   // (tiny matrices: the five extra launches cost more than they hide)
         // the base block first, on its own stream: A = (bra[:h] Cinv)(ket[:h] Cinv)^T, then its inverse (one CTA for
         // ~0.8 us per column) next to the full products below instead of behind them
         const size_t hn = (size_t)h * n, hh = (size_t)h * h;
-        const size_t want = (2 * hn + 2 * hh) * sizeof(double) + 256;
+        // the base block as a split-K product (its K loop is the latency): at most 8 slabs, summed by the inverse kernel
+        const int kslab = n <= 512 ? 64 : (int)align_up((size_t)cdiv(n, 8), 32), nslab = cdiv(n, kslab);
+        const size_t want = (2 * hn + (size_t)(nslab + 1) * hh) * sizeof(double) + 256;
         if (want > ctx->pre_bytes) {
             WFO_CUDA(cudaDeviceSynchronize());
             if (ctx->pre_buf) WFO_CUDA(cudaFree(ctx->pre_buf));
@@ -1084,11 +1098,20 @@ int wfo_smo_inv_dev(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos, 
             WFO_CUDA(cudaMalloc(&ctx->pre_buf, want + want / 4));
             ctx->pre_bytes = want + want / 4;
         }
-        double *Ls = reinterpret_cast<double *>(ctx->pre_buf), *Rs = Ls + hn, *A = Rs + hn, *Ai = A + hh;
+        double *Ls = reinterpret_cast<double *>(ctx->pre_buf), *Rs = Ls + hn, *A = Rs + hn, *Ai = A + (size_t)nslab * hh;
         BaseInfo *info = reinterpret_cast<BaseInfo *>(Ai + hh);
-        cudaStream_t s3 = ctx->stream3;
+        cudaStream_t s3 = ctx->stream3, s4 = ctx->stream4;
+        DBG_EV(0, st);
         WFO_CUDA(cudaEventRecord(ctx->ev_pre_in, st));
         WFO_CUDA(cudaStreamWaitEvent(s3, ctx->ev_pre_in, 0));
+        WFO_CUDA(cudaStreamWaitEvent(s4, ctx->ev_pre_in, 0));
+        // the inverse kernel goes FIRST: it takes an SM for itself and waits there for the flag
+        const int epoch = ++ctx->pre_epoch;
+        base_inverse_kernel<<<1, LUB_THREADS, LUB_EXCL_SMEM > lub_smem_bytes(h) ? LUB_EXCL_SMEM : lub_smem_bytes(h), s4>>>(
+            A, h, h, Ai, h, info, nslab, (long long)hh, ctx->pre_flag, epoch);
+        WFO_LAUNCH_CHECK(ctx);
+        DBG_EV(3, s4);
+        WFO_CUDA(cudaEventRecord(ctx->ev_pre, s4));
         if (bra_mos != ket_mos && dbytes % (ptrdiff_t)sizeof(double) == 0) {
             WFO_TRY(gemm(ctx, false, false, h, n, n, 1.0, bra_mos, n, c_inv, n, 0.0, Ls, n, 0, (long long)hn, s3, 2,
                          (long long)(dbytes / (ptrdiff_t)sizeof(double)), 0));
@@ -1096,9 +1119,15 @@ int wfo_smo_inv_dev(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos, 
             WFO_TRY(gemm(ctx, false, false, h, n, n, 1.0, bra_mos, n, c_inv, n, 0.0, Ls, n, 0, 0, s3));
             WFO_TRY(gemm(ctx, false, false, h, n, n, 1.0, ket_mos, n, c_inv, n, 0.0, Rs, n, 0, 0, s3));
         }
-        WFO_TRY(gemm(ctx, false, true, h, h, n, 1.0, Ls, n, Rs, n, 0.0, A, h, 0, 0, s3));
-        WFO_TRY(base_factor(ctx, A, h, h, Ai, h, info, nullptr, s3));
-        WFO_CUDA(cudaEventRecord(ctx->ev_pre, s3));
+        DBG_EV(1, s3);
+        WFO_TRY(gemm(ctx, false, true, h, h, n, 1.0, Ls, n, Rs, n, 0.0, A, h, kslab, (long long)hh, s3));
+        set_flag_kernel<<<1, 32, 0, s3>>>(ctx->pre_flag, epoch);
+        WFO_LAUNCH_CHECK(ctx);
+        DBG_EV(2, s3);
+        // the wide products below would fill every SM and leave this short dependent chain waiting for CTA slots
+        // (measured: base block ready after 56 us instead of 12): they start behind it
+        WFO_CUDA(cudaEventRecord(ctx->ev_pre_in, s3));
+        WFO_CUDA(cudaStreamWaitEvent(st, ctx->ev_pre_in, 0));
         ctx->pre_smo = s_mo;
         ctx->pre_n = h;
         ctx->pre_Ai = Ai;
@@ -1115,7 +1144,19 @@ int wfo_smo_inv_dev(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos, 
         WFO_TRY(gemm(ctx, false, false, n, n, n, 1.0, bra_mos, n, c_inv, n, 0.0, P, n, 0, 0, st));
         WFO_TRY(gemm(ctx, false, false, n, n, n, 1.0, ket_mos, n, c_inv, n, 0.0, Q, n, 0, 0, st));
     }
-    return gemm(ctx, false, true, n, n, n, 1.0, P, n, Q, n, 0.0, s_mo, n, 0, 0, st);
+    DBG_EV(4, st);
+    const int rc_s = gemm(ctx, false, true, n, n, n, 1.0, P, n, Q, n, 0.0, s_mo, n, 0, 0, st);
+#ifdef WFO_DEBUG_PRE
+    DBG_EV(5, st);
+    if (ctx->pre_smo) {
+        cudaDeviceSynchronize();
+        float t[6] = {0};
+        for (int i = 1; i < 6; i++) cudaEventElapsedTime(&t[i], g_dbg[0], g_dbg[i]);
+        fprintf(stderr, "[pre] small LR done %.1f us, S_oo done %.1f, base done %.1f | main LR done %.1f, S done %.1f\n",
+                t[1] * 1e3, t[2] * 1e3, t[3] * 1e3, t[4] * 1e3, t[5] * 1e3);
+    }
+#endif
+    return rc_s;
 }
 
 int wfo_smo_host(wfo_ctx *ctx, const double *bra_mos, const double *s_ao, const double *ket_mos, int p, int u,
@@ -1364,9 +1405,12 @@ static int state_overlaps_block(wfo_ctx *ctx, size_t arena_off, const double *s_
             const double *Bblk = s_mo + n;                    // occ  x virt
             const double *Cblk = s_mo + (size_t)n * n_mo;     // virt x occ
             if (v > 0) {
-                WFO_TRY(gemm(ctx, false, false, v, n, n, 1.0, Cblk, n_mo, p.Ai, n, 0.0, p.X, n, 0, 0, st));
+                // X = C Ai on the side stream (behind the verdict copy) next to Y = Ai B -> W = D - C Y
+                WFO_TRY(gemm(ctx, false, false, v, n, n, 1.0, Cblk, n_mo, p.Ai, n, 0.0, p.X, n, 0, 0, s2));
+                WFO_CUDA(cudaEventRecord(ctx->ev_join, s2));
                 WFO_TRY(gemm(ctx, false, false, n, v, n, 1.0, p.Ai, n, Bblk, n_mo, 0.0, p.Y, v, 0, 0, st));
                 WFO_TRY(gemm(ctx, false, false, v, v, n, -1.0, Cblk, n_mo, p.Y, v, 1.0, p.Wb, v + 1, 0, 0, st));
+                WFO_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
             }
             WFO_PHASE(ctx, st, "xyw_gemms");
             t1_prep_kernel<<<cdiv(ksh + 1, 256) + cdiv(kk_pad, 256), 256, 0, st>>>(bra_sh, ksh, ket_exc, kk, kk_pad, n, v, p.X, p.Y, p.info,

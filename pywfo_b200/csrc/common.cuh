@@ -81,7 +81,9 @@ struct wfo_ctx {
     cudaStream_t stream2;  // side stream: work that overlaps the single-CTA base factorisation
     // early base block (wfo_set_occ_hint): wfo_smo_inv_dev forms S_MO[:occ,:occ] first and inverts it on stream3
     // while the rest of S_MO is still being multiplied; the next state-overlap call on that S_MO picks it up
-    cudaStream_t stream3;
+    cudaStream_t stream3, stream4;
+    int *pre_flag;           // device: raised (to pre_epoch) when the base block is ready for the waiting inverse kernel
+    int pre_epoch;
     cudaEvent_t ev_pre_in, ev_pre;
     int occ_hint;
     char *pre_buf;

@@ -32,6 +32,7 @@ constexpr int LUB_WARPS = LUB_THREADS / 32;   // 16
 constexpr int LUB_CS = LUB_MAXN / LUB_WARPS;  // 8 columns per warp = one panel (columns 8 warp + c)
 constexpr int LUB_RS = 4;                     // 4 row slots per thread (rows 4 lane + s)
 constexpr int LUB_LDS = LUB_MAXN + 1;         // row stride of the staging tile
+constexpr size_t LUB_EXCL_SMEM = 200 * 1024;  // dynamic shared memory request that leaves no room for another CTA on the SM
 // staging tile (n x LUB_LDS) on entry / exit; in between the same memory holds the multiplier panels
 // (ceil(n/8) panels x 8 columns x row stride 4 ceil(n/4))
 inline size_t lub_smem_bytes(int n) {
@@ -322,13 +323,34 @@ __device__ __forceinline__ void lub_invert_tile(double *lub_tile, int n, double 
 // Dynamic shared memory: lub_smem_bytes(n) (staging tile for coalesced load / store).
 __global__ void __launch_bounds__(LUB_THREADS)
 base_inverse_kernel(const double *__restrict__ A_src, int ld_src, int n, double *__restrict__ Ai_out, int ld_out,
-                    BaseInfo *__restrict__ info) {
+                    BaseInfo *__restrict__ info, int n_slabs, long long slab_stride, const int *wait_flag, int wait_value) {
     extern __shared__ __align__(16) double lub_tile[];    // n x LUB_LDS
     const int tid = threadIdx.x;
-    // coalesced load through the staging tile
+    if (wait_flag) {
+        // launched AHEAD of its input (wfo_smo_inv_dev's early base block): the CTA sits on an SM of its own
+        // (its shared-memory request keeps the GEMM CTAs away, whose FP64 traffic would slow this latency-bound
+        // kernel by half) and waits until the producer stream raises the flag.  Bounded: ~2 s, then it runs
+        // on whatever is there and the consumer's verdict check (non-finite pivots) rejects the result.
+        if (tid == 0) {
+            int seen = 0;
+            for (long long spin = 0; spin < (1ll << 24); spin++) {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(seen) : "l"(wait_flag) : "memory");
+                if (seen == wait_value) break;
+                __nanosleep(100);
+            }
+        }
+        __syncthreads();
+    }
+    // coalesced load through the staging tile; A may arrive as the K slabs of a split-K product (summed in fixed order)
     for (int idx = tid; idx < n * n; idx += LUB_THREADS) {
         const int r = idx / n, c = idx - r * n;
-        lub_tile[r * LUB_LDS + c] = A_src[(size_t)r * ld_src + c];
+        double vz[8];   // at most 8 slabs, all loads in flight together
+#pragma unroll
+        for (int z = 0; z < 8; z++) vz[z] = (z < n_slabs) ? A_src[(size_t)z * slab_stride + (size_t)r * ld_src + c] : 0.0;
+        double v = vz[0];
+#pragma unroll
+        for (int z = 1; z < 8; z++) v += vz[z];
+        lub_tile[r * LUB_LDS + c] = v;
     }
     __syncthreads();
     double det, minp, maxp;
@@ -395,6 +417,13 @@ cofactor_rows_kernel(const double *__restrict__ S, int ld_s, int n, const int32_
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (lane == 0) D[(size_t)mem_block[m] * ld_d + kb] = acc;
         }
+    }
+}
+
+__global__ void set_flag_kernel(int *flag, int value) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        __threadfence();
+        asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(flag), "r"(value) : "memory");
     }
 }
 

@@ -55,14 +55,14 @@ int main(int argc, char **argv) {
         float warm = 0, cold = 0;
         for (int r = 0; r < 8; r++) {
             cudaEventRecord(e0);
-            base_inverse_kernel<<<1, LUB_THREADS, lub_smem_bytes(n)>>>(dA, n, n, dAi, n, dinfo);
+            base_inverse_kernel<<<1, LUB_THREADS, lub_smem_bytes(n)>>>(dA, n, n, dAi, n, dinfo, 1, 0, nullptr, 0);
             cudaEventRecord(e1); cudaEventSynchronize(e1);
             float ms; cudaEventElapsedTime(&ms, e0, e1); if (r >= 3) warm += ms / 5;
         }
         for (int r = 0; r < 5; r++) {
             flush_kernel<<<296, 1024>>>(fl, FB); cudaDeviceSynchronize();
             cudaEventRecord(e0);
-            base_inverse_kernel<<<1, LUB_THREADS, lub_smem_bytes(n)>>>(dA, n, n, dAi, n, dinfo);
+            base_inverse_kernel<<<1, LUB_THREADS, lub_smem_bytes(n)>>>(dA, n, n, dAi, n, dinfo, 1, 0, nullptr, 0);
             cudaEventRecord(e1); cudaEventSynchronize(e1);
             float ms; cudaEventElapsedTime(&ms, e0, e1); cold += ms / 5;
         }
