@@ -1729,7 +1729,8 @@ static int overlaps_ci_core(wfo_ctx *ctx, const CiWork &w, const double *d_bra, 
     }
     {   // the base block early (the rank-update tier will want it), whatever hint the caller has set
         const int hint0 = ctx->occ_hint;
-        ctx->occ_hint = (tier == WFO_TIER_AUTO || tier == WFO_TIER_UPDATE) ? n : 0;
+        static const bool no_early = getenv("WFO_NO_EARLY_BASE") != nullptr;   // tuning switch
+        ctx->occ_hint = (!no_early && (tier == WFO_TIER_AUTO || tier == WFO_TIER_UPDATE)) ? n : 0;
         const int rc_ = wfo_smo_inv_dev(ctx, d_bra, d_ket, d_inv, n_mo, w.smo, w.work, s2);   // work, work2 contiguous
         ctx->occ_hint = hint0;
         if (rc_ != WFO_OK) return rc_;
