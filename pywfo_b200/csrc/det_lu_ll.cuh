@@ -62,6 +62,19 @@ struct LLCfg {
 
 __device__ __forceinline__ double2 lds128(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 __device__ __forceinline__ void sts128(double *p, double x, double y) { *reinterpret_cast<double2 *>(p) = make_double2(x, y); }
+// predicated shared-memory stores without a branch (a branch ends the basic block the scheduler works in)
+__device__ __forceinline__ void sts128_if(double *p, double x, double y, bool pred) {
+    asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %3, 0;\n@q st.shared.v2.f64 [%0], {%1, %2};\n}\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(p)), "d"(x), "d"(y), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void sts64_if(double *p, double x, bool pred) {
+    asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %2, 0;\n@q st.shared.f64 [%0], %1;\n}\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(p)), "d"(x), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void sts32_if(int *p, int x, bool pred) {
+    asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %2, 0;\n@q st.shared.b32 [%0], %1;\n}\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(p)), "r"(x), "r"((int)pred) : "memory");
+}
 // a 16-byte chunk of an M panel: shared memory, or the L2-resident global scratch (L1 bypassed; prefetching the
 // next panel into L1 while the current one is applied was measured: 5 % slower)
 template <bool MG>
@@ -134,6 +147,7 @@ __device__ __forceinline__ int ll_factor(char *sm, double *gM, int p, int n, int
     LL_T(3);
 
     const int nsteps = n - 8 * p;   // < 8 in a ragged last panel: the identity padding needs no elimination
+    bool bad = false;
 #pragma unroll
     for (int jj = 0; jj < 8; jj++) {
         if (jj >= nsteps) break;
@@ -144,7 +158,7 @@ __device__ __forceinline__ int ll_factor(char *sm, double *gM, int p, int n, int
             key = max(key, alive[s] ? k : 0u);
         }
         const unsigned kmax = __reduce_max_sync(FULL, key);
-        if (kmax == 0u) return 0;   // uniform: no candidate left
+        bad |= (kmax == 0u);   // no candidate left (checked after the panel: no branch inside the steps)
         // reciprocal of this lane's own best candidate, computed in the shadow of the reduction
         const int bs = (key >> 5) & 3;
         double cand = a[0][jj];
@@ -153,24 +167,21 @@ __device__ __forceinline__ int ll_factor(char *sm, double *gM, int p, int n, int
         const double rc_own = fast_rcp(cand);
         const int wl = kmax & 31, ws = (kmax >> 5) & 3;
         double *rec = recs + 12 * jj;   // [0, jj): multipliers of the pivot row = row jj of L11; [jj, 8): the pivot row
-        if (lane == wl) {
 #pragma unroll
-            for (int s = 0; s < SL; s++) {
-                if (ws == s) {
+        for (int s = 0; s < SL; s++) {
+            const bool win = (lane == wl) && (ws == s);
 #pragma unroll
-                    for (int c = 0; c < 4; c++) sts128(rec + 2 * c, a[s][2 * c], a[s][2 * c + 1]);
-                    rec[8] = rc_own;
-                    reinterpret_cast<int *>(rec + 9)[0] = rpos[s];
-                }
-            }
+            for (int c = 0; c < 4; c++) sts128_if(rec + 2 * c, a[s][2 * c], a[s][2 * c + 1], win);
+            sts64_if(rec + 8, rc_own, win);
+            sts32_if(reinterpret_cast<int *>(rec + 9), rpos[s], win);
         }
         __syncwarp();
         double u[8];
 #pragma unroll
         for (int c = jj; c < 8; c++) u[c] = rec[c];
-        const double rcp = rec[8];
+        const double rcp = rec[8], nrcp = -rcp;
         const int pp = reinterpret_cast<const int *>(rec + 9)[0];
-        if (u[jj] == 0.0) return 0;   // uniform: the whole column is zero
+        bad |= (u[jj] == 0.0);   // the whole column is zero
         det *= u[jj];
         par ^= (pp != jj) ? 1u : 0u;
 #pragma unroll
@@ -179,24 +190,29 @@ __device__ __forceinline__ int ll_factor(char *sm, double *gM, int p, int n, int
             rpos[s] = (alive[s] && !win && rpos[s] == jj) ? pp : rpos[s];   // the row the pivot displaces
             rpos[s] = win ? jj : rpos[s];
             alive[s] = alive[s] && !win;
-            const double l = alive[s] ? a[s][jj] * rcp : 0.0;
-            a[s][jj] = alive[s] ? l : a[s][jj];
+            // the NEGATIVE multiplier -l is what every later use wants (the update, the recurrence for M below, the
+            // stored -M): a negation would cost an FP64 issue slot each time
+            const double nl = alive[s] ? a[s][jj] * nrcp : 0.0;
+            a[s][jj] = alive[s] ? nl : a[s][jj];
 #pragma unroll
-            for (int c = jj + 1; c < 8; c++) a[s][c] = fma(-l, u[c], a[s][c]);
+            for (int c = jj + 1; c < 8; c++) a[s][c] = fma(nl, u[c], a[s][c]);
         }
     }
     LL_T(4);
+    if (bad) return 0;           // uniform: singular minor
     if (p == NT - 1) return 1;   // last panel: nothing below it
 
     __syncwarp();   // the records are complete
-    // ---- M = L21 L11^-1 (axpy form of x L11 = l); L11[q][c] = recs[q][c], c < q; dead rows are modified too, harmlessly
+    // ---- -M = -L21 L11^-1 (axpy form of x L11 = l, linear, so it holds for the negated rows as they are kept);
+    // recs[q][c], c < q, is -L11[q][c] (the winner's row was recorded with its negative multipliers);
+    // dead rows are modified too, harmlessly
 #pragma unroll
     for (int q = 7; q >= 1; q--) {
 #pragma unroll
         for (int c = 0; c < q; c++) {
             const double lqc = recs[12 * q + c];
 #pragma unroll
-            for (int s = 0; s < SL; s++) a[s][c] = fma(-a[s][q], lqc, a[s][c]);
+            for (int s = 0; s < SL; s++) a[s][c] = fma(a[s][q], lqc, a[s][c]);
         }
     }
     __syncwarp();   // all staging rows consumed: M_p may now overwrite them
@@ -210,7 +226,7 @@ __device__ __forceinline__ int ll_factor(char *sm, double *gM, int p, int n, int
             double *dst = Mp_dst + (rpos[s] - 8) * 8;
             const int sw = (rpos[s] >> 1) & 3;
 #pragma unroll
-            for (int c = 0; c < 4; c++) sts128(dst + ((c ^ sw) << 1), -a[s][c], -a[s][c + 4]);
+            for (int c = 0; c < 4; c++) sts128(dst + ((c ^ sw) << 1), a[s][c], a[s][c + 4]);
         }
         moved[s] = lam < L && rpos[s] != lam;
         any = any || moved[s];
