@@ -733,3 +733,68 @@ def test_raw_ci_entry_point_from_device_buffers(ctx):
         s.synchronize()
         assert info[0] > 0 and info[1] > 0
         assert_parity(out.cpu().numpy(), g[key])
+
+
+@pytest.mark.parametrize("n_mo,occ", [(96, 20), (130, 37), (200, 100), (150, 128)])
+def test_early_base_block_hint(ctx, n_mo, occ):
+    """wfo_set_occ_hint: wfo_smo_inv_dev multiplies and inverts S_MO[:occ,:occ] (pywfo/main.py:548) on a side
+    stream ahead of the full S_MO; the state-overlap call on that buffer picks it up.  Same result as the
+    unhinted path (to rounding: the base block is multiplied with another tile shape), stale hints are ignored
+    (other n_occ, other buffer), and a hint that is never consumed does no harm."""
+    import torch
+    from pywfo_b200 import excitations as ex, helpers
+    bra_mos, ket_mos, bci, kci = helpers.synthetic_case(11 + occ, n_mo, occ, 3, 4, top_k=60)
+    bt, kt = ex.build_tables(bci, 1e-12, "cache"), ex.build_tables(kci, 1e-12, "cache", order="locality")
+    S = orc.mo_overlap(bra_mos, ket_mos, orc.get_S_AO(bra_mos, ket_mos, "ket"))
+    want = orc.state_overlaps_closed_form(S, occ, [tuple(e) for e in bt.exc], bt.coeff, [tuple(e) for e in kt.exc],
+                                          kt.coeff, 1.0)
+    f64 = dict(dtype=torch.float64, device="cuda")
+    d_bra, d_ket, d_inv = (torch.tensor(np.ascontiguousarray(x), **f64) for x in (bra_mos, ket_mos, np.linalg.inv(ket_mos)))
+    d_smo, d_work = torch.empty((n_mo, n_mo), **f64), torch.empty((2, n_mo, n_mo), **f64)
+    d_be, d_ke = (torch.tensor(t.exc, dtype=torch.int32, device="cuda") for t in (bt, kt))
+    d_cb, d_ck = torch.tensor(bt.coeff, **f64), torch.tensor(kt.coeff, **f64)
+    d_out = torch.empty((3, 4), **f64)
+
+    def run(hint, occ_call=occ):
+        ctx.set_occ_hint(hint)
+        ctx.smo_inv_dev(d_bra, d_ket, d_inv, d_smo, d_work)
+        ctx.state_overlaps_dev(d_smo, occ_call, d_be, d_cb, d_ke, d_ck, d_out, tier="update")
+        torch.cuda.synchronize()
+        return d_out.cpu().numpy().copy()
+
+    try:
+        plain = run(0)
+        assert_parity(plain, want)
+        hinted = run(occ)
+        assert_parity(hinted, want)
+        np.testing.assert_allclose(hinted, plain, rtol=1e-11, atol=1e-13 * np.abs(plain).max())
+        assert np.array_equal(run(occ), hinted)                 # and reproducible
+        stale = run(occ - 1)                                    # hint for another n_occ: ignored by the consumer
+        assert np.array_equal(stale, plain)
+        ctx.set_occ_hint(occ)                                   # a hint nobody consumes, then a fresh S_MO elsewhere
+        ctx.smo_inv_dev(d_bra, d_ket, d_inv, d_smo, d_work)
+        other = d_smo.clone()
+        ctx.state_overlaps_dev(other, occ, d_be, d_cb, d_ke, d_ck, d_out, tier="update")
+        torch.cuda.synchronize()
+        assert np.array_equal(d_out.cpu().numpy(), plain)
+    finally:
+        ctx.set_occ_hint(0)
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 8, 9, 16, 33, 63, 64, 65, 100, 121, 122, 127, 128])
+@pytest.mark.parametrize("kind", ["near_identity", "random", "permuted"])
+def test_base_inverse_every_panel_shape(ctx, n, kind):
+    """The pipelined Gauss-Jordan inverse behind the rank-update tier (csrc/lu_base.cuh: panels of 8 columns per
+    warp, ragged last panel, row pivoting across panels) against numpy.linalg.inv / det -- what the reference
+    takes from LAPACK (pywfo/main.py:303, 548)."""
+    rng = np.random.default_rng(300 + n)
+    if kind == "near_identity":
+        a = np.eye(n) + 0.05 * rng.standard_normal((n, n))
+    elif kind == "random":
+        a = rng.standard_normal((n, n))
+    else:   # every pivot far from the diagonal
+        a = (np.eye(n) + 0.01 * rng.standard_normal((n, n)))[rng.permutation(n)]
+    got = ctx.inverse_host(a)
+    resid = np.abs(a @ got - np.eye(n)).max()
+    assert resid < 1e-9 * max(1.0, np.linalg.cond(a)), (n, kind, resid)
+    np.testing.assert_allclose(got, np.linalg.inv(a), rtol=0, atol=1e-9 * np.abs(np.linalg.inv(a)).max() * max(1.0, np.linalg.cond(a) * 1e-3))
