@@ -1651,7 +1651,7 @@ static int build_tables_dev(wfo_ctx *ctx, const double *ci_dev, int n_states, in
     }
     scan_flags_kernel<<<1, 1024, 0, st>>>(flags, cnt, offs, totals);
     WFO_LAUNCH_CHECK(ctx);
-    if (cnt == count) {   // per-state totals only make sense (and are only needed) for the whole tensor
+    if (cnt == count && strict) {   // per-state totals: only pywfo.main.overlaps looks at them (main.py:186), whole tensor only
         state_counts_kernel<<<n_states, 256, 0, st>>>(ci_dev, n, v, thr, strict, totals + 1);
         WFO_LAUNCH_CHECK(ctx);
     }
