@@ -336,7 +336,10 @@ __device__ __forceinline__ double ll_lu_det(const double *__restrict__ S, int ld
         __syncwarp();
         LL_T(2);
         const int L = 8 * (NT - p);
-        constexpr int SLMAX = (8 * NT + 31) / 32, SLLO = (SLMAX + 1) / 2;
+        // NT >= 10: ONE slot count.  The kernel is instruction-fetch bound there (ncu, n = 100: 39 % of the stall
+        // samples are 'no instruction' with two instantiations, 92 KB of code); the late panels then carry idle row
+        // slots, and it is still 5-12 % faster (n = 80 ... 128).  Below, two slot counts fit (n = 64: 52 KB, 5 %).
+        constexpr int SLMAX = (8 * NT + 31) / 32, SLLO = (NT >= 10) ? SLMAX : (SLMAX + 1) / 2;
         if (L > 32 * SLLO) ok = ll_factor<NT, SLMAX, MG>(sm, gM, p, n, lane, det, par, clk);
         else ok = ll_factor<NT, SLLO, MG>(sm, gM, p, n, lane, det, par, clk);
         if (ok == 0) break;
@@ -397,7 +400,11 @@ struct LLWarps {
     // register budget 65536 / (32 w).  L2-scratch variant: 12 warps (168 registers, a few spilled) beat 8 up to
     // n = 104 (n = 72: 5.6 -> 6.9 TFLOP/s, n = 88: 5.9 -> 7.2, n = 100: 5.0 -> 5.4), 8 warps win at n = 128
     static constexpr int REG = MG ? (NT <= 13 ? 12 : 8) : (NT >= 13 ? 8 : (NT >= 9 ? 10 : (NT >= 7 ? 12 : 16)));
+#ifdef LL_WARPS_OVERRIDE
+    static constexpr int W = LL_WARPS_OVERRIDE;
+#else
     static constexpr int W = SMEM < REG ? SMEM : REG;
+#endif
 };
 inline size_t ll_scratch_doubles(int nt) { return (size_t)nt * (nt - 1) / 2 * 64; }   // per warp, MG variant
 
