@@ -125,6 +125,20 @@ def as_i32(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.int32)
 
 
+
+def _check_exc(name, exc, n_occ, n_virt):
+    """(from, to) tables index S_MO on the device: out-of-range entries must fail here, as the reference's own
+    indexing would (IndexError, pywfo/main.py:565-576), not read past the matrix.  (-1, -1) is the ground state."""
+    if exc.size == 0:
+        return
+    f, t = exc[:, 0], exc[:, 1]
+    gs = (f < 0) & (t < 0)
+    bad = ~gs & ((f < 0) | (f >= n_occ) | (t < 0) | (t >= n_virt))
+    if bad.any():
+        k = int(np.argmax(bad))
+        raise IndexError(f"{name} excitation {k} = ({int(f[k])}, {int(t[k])}) is outside occ={n_occ}, virt={n_virt}")
+
+
 class Context:
     """One per (process, device); owns the device scratch arena."""
 
@@ -172,6 +186,8 @@ class Context:
         if cb.shape[1] != kb or ck.shape[1] != kk:
             raise ValueError("coefficient matrices do not match the excitation tables")
         k_end = kb if k_end is None else k_end
+        _check_exc("bra", be, int(n_occ), s.shape[0] - int(n_occ))
+        _check_exc("ket", ke, int(n_occ), s.shape[0] - int(n_occ))
         out = np.empty((cb.shape[0], ck.shape[0]))
         check(self.lib.wfo_state_overlaps_host(self.handle, _hptr(s), s.shape[0], int(n_occ), _hptr(be), kb,
                                                _hptr(cb), cb.shape[0], _hptr(ke), kk, _hptr(ck), ck.shape[0],
@@ -190,6 +206,8 @@ class Context:
         if cb.shape[1] != kb or ck.shape[1] != kk:
             raise ValueError("coefficient matrices do not match the excitation tables")
         k_end = kb if k_end is None else k_end
+        _check_exc("bra", be, int(n_occ), n_mo - int(n_occ))
+        _check_exc("ket", ke, int(n_occ), n_mo - int(n_occ))
         if out is None:
             out = np.empty((cb.shape[0], ck.shape[0]))
         check(self.lib.wfo_overlaps_host(self.handle, _hptr(bra), _hptr(ket), _hptr(inv), n_mo, int(n_occ),

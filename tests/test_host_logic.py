@@ -108,3 +108,15 @@ def test_shard_bounds(K, world):
     assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
     sizes = [hi - lo for lo, hi in b]
     assert max(sizes) - min(sizes) <= 1
+
+
+def test_excitation_tables_are_range_checked():
+    """(from, to) entries outside the occupied / virtual ranges raise IndexError on the host
+    (what the reference's own indexing does, pywfo/main.py:565-576) instead of reaching the device."""
+    from pywfo_b200._lib import _check_exc
+    ok = np.array([[0, 0], [4, 18], [-1, -1]], dtype=np.int32)
+    _check_exc("bra", ok, 5, 19)
+    _check_exc("bra", ok[:0], 5, 19)
+    for bad in ([5, 0], [0, 19], [-1, 3], [2, -1], [7, 40]):
+        with pytest.raises(IndexError):
+            _check_exc("ket", np.array([[1, 1], bad], dtype=np.int32), 5, 19)
