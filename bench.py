@@ -609,7 +609,7 @@ def main():
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="N > 1: in-library one-shot peer-memory all-reduce (default) or torch.distributed/NCCL")
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--t0-sample", type=int, default=16384, help="pairs in the brute-force sample leg (0 = skip)")
+    ap.add_argument("--t0-sample", type=int, default=65536, help="pairs in the brute-force sample leg (0 = skip)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU baseline work (0 = skip)")
     ap.add_argument("--no-check", dest="check", action="store_false")
     ap.add_argument("--no-t2", dest="t2", action="store_false", help="skip the closed-form tier timing")

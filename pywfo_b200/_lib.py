@@ -129,7 +129,7 @@ def as_i32(a) -> np.ndarray:
 def _check_exc(name, exc, n_occ, n_virt):
     """(from, to) tables index S_MO on the device: out-of-range entries must fail here, as the reference's own
     indexing would (IndexError, pywfo/main.py:565-576), not read past the matrix.  (-1, -1) is the ground state."""
-    if exc.size == 0:
+    if exc.size == 0 or n_occ < 1 or n_virt < 0:   # (bad sizes: the library's own message)
         return
     f, t = exc[:, 0], exc[:, 1]
     gs = (f < 0) & (t < 0)

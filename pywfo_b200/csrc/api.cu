@@ -413,7 +413,8 @@ static int make_part(wfo_ctx *ctx, int ksh, int kk, int n_ket, bool may_t0, bool
         if (parts > q.n_parts) q.n_parts = parts;
     }
     // T0: items (k, chunk of l)
-    const int target_ctas = ctx->sm_count * 48;
+    // (about 16 items per resident warp: the items are handed out dynamically and a coarse last item is idle time)
+    const int target_ctas = ctx->sm_count * 192;
     int chunks = cdiv(target_ctas, ksh);
     if (chunks > kk) chunks = kk;
     if (chunks < 1) chunks = 1;
@@ -484,6 +485,7 @@ int wfo_create(int device, wfo_ctx **out) {
     WFO_CUDA(cudaFuncSetAttribute(base_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(LUB_EXCL_SMEM > lub_smem_bytes(LUB_MAXN) ? LUB_EXCL_SMEM : lub_smem_bytes(LUB_MAXN))));
     WFO_CUDA(cudaMalloc(&c->ns_slots, 128 * sizeof(double)));
+    WFO_CUDA(cudaMalloc(&c->t0_next, sizeof(unsigned long long)));
     WFO_CUDA(cudaMallocHost(&c->h_slots, 128 * sizeof(double)));
     WFO_CUDA(cudaMallocHost(&c->h_info, sizeof(BaseInfo)));
     WFO_CUDA(cudaEventCreateWithFlags(&c->ev_info, cudaEventDisableTiming));
@@ -503,6 +505,7 @@ int wfo_destroy(wfo_ctx *ctx) {
     if (ctx->gj_buf) cudaFree(ctx->gj_buf);
     if (ctx->resident) cudaFree(ctx->resident);
     if (ctx->ns_slots) cudaFree(ctx->ns_slots);
+    if (ctx->t0_next) cudaFree(ctx->t0_next);
     if (ctx->h_slots) cudaFreeHost(ctx->h_slots);
     if (ctx->h_info) cudaFreeHost(ctx->h_info);
     cudaEventDestroy(ctx->ev_info);
@@ -1466,9 +1469,10 @@ static int state_overlaps_block(wfo_ctx *ctx, size_t arena_off, const double *s_
                             LLWarps<NT_, MG_>::W * LLCfg<NT_, MG_>::BYTES,                                            \
                             (items + LLWarps<NT_, MG_>::W - 1) / LLWarps<NT_, MG_>::W, &grid));                       \
     if (MG_) WFO_TRY(ensure_gscratch(ctx, (size_t)grid * LLWarps<NT_, MG_>::W * ll_scratch_doubles(NT_) * 8));        \
+    WFO_CUDA(cudaMemsetAsync(ctx->t0_next, 0, sizeof(unsigned long long), st));                                       \
     if (ctx->timing) WFO_CUDA(cudaEventRecord(ctx->ev0, st));                                                         \
     t0_fused_ll_kernel<NT_, MG_><<<grid, LLWarps<NT_, MG_>::W * 32, LLWarps<NT_, MG_>::W * LLCfg<NT_, MG_>::BYTES, st>>>( \
-        s_mo, n_mo, n, p.bra_lists, ksh, p.ket_lists, kk, p.ckt, ldg, chunk_len, t0_chunks, p.gpart, ctx->gscratch)
+        s_mo, n_mo, n, p.bra_lists, ksh, p.ket_lists, kk, p.ckt, ldg, chunk_len, t0_chunks, p.gpart, ctx->gscratch, ctx->t0_next)
             WFO_LL_DISPATCH(n, CALL_FL);
 #undef CALL_FL
         } else if (n > 32) {

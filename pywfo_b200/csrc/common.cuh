@@ -104,6 +104,7 @@ struct wfo_ctx {
     char *scratch;         // device arena, grown on demand
     size_t scratch_bytes;
     double *gscratch;      // per-CTA LU working matrices (global-scratch variant of the T0 kernel)
+    unsigned long long *t0_next;   // device: work counter of the brute-force pair kernel (zeroed before each launch)
     size_t gscratch_bytes;
     char *resident;        // inputs + phase-1 workspace of the raw-CI / trajectory entry points
     size_t resident_bytes;

@@ -431,7 +431,7 @@ template <int NT, bool MG>
 __global__ void __launch_bounds__(LLWarps<NT, MG>::W * 32, 1)
 t0_fused_ll_kernel(const double *__restrict__ S, int ld_s, int n, const int32_t *__restrict__ rows, int ksh,
                    const int32_t *__restrict__ cols, int kk, const double *__restrict__ ckt, int ldg, int chunk_len,
-                   int n_chunks, double *__restrict__ gpart, double *gscratch) {
+                   int n_chunks, double *__restrict__ gpart, double *gscratch, unsigned long long *next_item) {
     extern __shared__ __align__(16) char ll_smem[];
     constexpr int W = LLWarps<NT, MG>::W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -439,7 +439,15 @@ t0_fused_ll_kernel(const double *__restrict__ S, int ld_s, int n, const int32_t 
     const long long gw = (long long)blockIdx.x * W + warp, nw = (long long)gridDim.x * W;
     double *gM = MG ? gscratch + (size_t)gw * (NT * (NT - 1) / 2 * 64) : nullptr;
     const long long nitems = (long long)ksh * n_chunks;
-    for (long long item = gw; item < nitems; item += nw) {
+    // the first item of a warp is its index, further ones come from a global counter (starts at 0 = the warps'
+    // first round): pivoting makes the determinants take different times, and a static round robin left the last
+    // round a quarter empty on small tables
+    auto fetch = [&]() -> long long {
+        unsigned long long v = 0;
+        if (lane == 0) v = atomicAdd(next_item, 1ull);
+        return nw + (long long)__shfl_sync(0xffffffffu, v, 0);
+    };
+    for (long long item = gw; item < nitems; item = fetch()) {
         const int k = (int)(item / n_chunks), ch = (int)(item - (long long)k * n_chunks);
         const int l0 = ch * chunk_len, l1 = min(kk, l0 + chunk_len);
         double g0 = 0.0, g1 = 0.0;

@@ -88,6 +88,18 @@ def _state_overlaps(semantics, sigma, bra_mos, ket_mos, bra_ci, ket_ci, occ, ci_
         raise ValueError("CI coefficients do not match occ")
     ctx = _lib.context(device)
     n_bra, n_ket = bra_ci.shape[0], ket_ci.shape[0]
+    # upstream only ever indexes S_MO with occ + to (main.py:565-576), so CI tensors that cover FEWER virtual
+    # orbitals than the MO matrices have (frozen / truncated virtual space, different widths on the two sides)
+    # are fine there: widen them with zero coefficients, which select nothing and weigh nothing.
+    n_virt = bra_mos.shape[0] - occ
+    if n_virt >= 0 and (bra_ci.shape[2] < n_virt or ket_ci.shape[2] < n_virt):
+        def widen(ci):
+            if ci.shape[2] >= n_virt:
+                return ci
+            wide = np.zeros((ci.shape[0], occ, n_virt))
+            wide[:, :, :ci.shape[2]] = ci
+            return wide
+        bra_ci, ket_ci = widen(bra_ci), widen(ket_ci)
     if isinstance(ao_ovlps, str):
         # everything on the device: the inverse behind S_AO (main.py:303), S_AO, S_MO, the selection
         # of excitations above the threshold, every determinant pair and the CI-weighted reduction.

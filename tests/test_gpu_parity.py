@@ -798,3 +798,21 @@ def test_base_inverse_every_panel_shape(ctx, n, kind):
     resid = np.abs(a @ got - np.eye(n)).max()
     assert resid < 1e-9 * max(1.0, np.linalg.cond(a)), (n, kind, resid)
     np.testing.assert_allclose(got, np.linalg.inv(a), rtol=0, atol=1e-9 * np.abs(np.linalg.inv(a)).max() * max(1.0, np.linalg.cond(a) * 1e-3))
+
+
+@pytest.mark.parametrize("fn_name,ref_name", [("overlaps_cache", "ref_overlaps_cache"), ("overlaps", "ref_overlaps_minus")])
+def test_ci_tensors_with_fewer_virtuals(ctx, fn_name, ref_name):
+    """the reference indexes S_MO with occ + to only (pywfo/main.py:565-576), so CI tensors that cover
+    fewer virtual orbitals than the MO matrices hold are accepted upstream; here too (zero-widened), string and
+    ndarray AO overlaps alike."""
+    from pywfo_b200 import helpers, main
+    n_mo, occ, vci = 40, 8, 20
+    bra_mos, ket_mos, bci, kci = helpers.synthetic_case(77, n_mo, occ, 3, 3)
+    bci, kci = np.ascontiguousarray(bci[:, :, :vci]), np.ascontiguousarray(kci[:, :, :vci])
+    want = getattr(orc, ref_name)(bra_mos, ket_mos, bci, kci, occ, ci_thresh=0.02)
+    want = want[0] if isinstance(want, tuple) else want
+    got = getattr(main, fn_name)(bra_mos, ket_mos, bci, kci, occ, ci_thresh=0.02)
+    assert_parity(got, want)
+    inv = np.linalg.inv(ket_mos)
+    got2 = getattr(main, fn_name)(bra_mos, ket_mos, bci, kci, occ, ci_thresh=0.02, ao_ovlps=inv @ inv.T)
+    assert_parity(got2, want)
