@@ -1,8 +1,10 @@
-// Standalone timing of base_inverse_kernel (scratch).  Round 2 measured two redesigns with it (panels of 8 columns
-// per warp, published through mbarriers per panel / per column, software-pipelined pivot steps): all land on the same
-// ~0.8 us per column as the shipped kernel -- a lone warp issues one dependent instruction every ~5 cycles and a pivot
-// step is ~140 of them -- so the shipped kernel stayed.
-//: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 [-DWFO_LUB_CLOCKS] scratch/lub_test.cu -o scratch/lub_test
+// Standalone timing of base_inverse_kernel (scratch): nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 scratch/lub_test.cu -o scratch/lub_test
+//   lub_test <mode>        table over n (warm / L2-flushed launches; mode 0 near-identity, 1 random)
+//   lub_test <mode> <n>    200 inversions inside ONE launch (per-inversion time without launch overhead; ncu sampling)
+// Round 2 went through four designs with it (us at n = 100): round 1's one block barrier per column 81; panels of 8
+// columns published per PANEL through mbarriers 97-100 (the next owner's apply sits on the critical path); published per
+// COLUMN 82; the same with predicated stores instead of branches and a software-pipelined pivot step 68 (shipped).
+// A lone warp issues one dependent instruction every ~5 cycles, a pivot step is ~140 of them: that is the floor here.
 #include <vector>
 #include <random>
 #include <cstdio>
