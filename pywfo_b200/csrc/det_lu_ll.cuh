@@ -28,6 +28,13 @@
 //      are moved in the older M_q as well (rare) and re-fetched for the prefetched panel.
 // The determinant is the signed product of the pivots = np.linalg.det(S_MO[rows][:, cols])
 // (pywfo/main.py:583-584).  The matrix is padded to 8 NT rows/columns with an identity block.
+//
+// Measured and rejected in round 2 (standalone driver scratch/ll_test.cu, n = 100 / 64): the A fragments of panel
+// q+1 requested into a second register set while panel q is applied (needs 8 warps at 255 registers: -10 %); four
+// unrolled column steps run twice over swapped register halves to halve the step code (runtime record addresses and a
+// uniform branch per step: -22 % / -5 %).  Kept: predicated winner records instead of branches (+11 %), negative
+// multipliers throughout, one row-slot instantiation for NT >= 10 (instruction fetch, see ll_lu_det), work items from a
+// global counter (t0_fused_ll_kernel).
 #pragma once
 #include "common.cuh"
 
