@@ -47,7 +47,9 @@ extern "C" {
 #define WFO_AO_KET 2   /* ao_ovlps="ket": ket_mos is inverted on the device */
 
 /* algorithm tiers (identical results to ~1e-13).  n_occ <= 128 for the brute-force tier,
- * n_occ <= 4096 for the rank-update and closed-form tiers (base block inverted blockwise above 128). */
+ * n_occ <= 4096 for the rank-update and closed-form tiers (base block inverted blockwise above 128; when that
+ * fails on a block LAPACK would invert -- pivoting is needed across the 128-blocks, e.g. occupied orbitals reordered
+ * between the geometries -- the rank-update tier falls back to a pivoted Gauss-Jordan inverse of the whole block). */
 #define WFO_TIER_LU 0      /* T0: one partially pivoted LU per determinant pair          */
 #define WFO_TIER_UPDATE 1  /* T1: one base LU + rank-1 row/column update per pair        */
 #define WFO_TIER_CLOSED 2  /* T2: closed-form contraction (GEMMs only), pair determinants never formed; opt-in */

@@ -313,7 +313,7 @@ struct Plan {   // everything wfo_state_overlaps needs from the arena
     // T0
     int32_t *bra_lists, *ket_lists, *gs_list;
     // T1
-    double *Abuf, *Ai, *X, *Y, *Wb, *bscale, *bwork;
+    double *Abuf, *Ai, *X, *Y, *Wb, *bscale, *bwork, *gjwork;
     BraMeta *bmeta;
     KetMeta *kmeta;
     BaseInfo *info;
@@ -346,6 +346,8 @@ static void carve(AR &ar, Plan &p, int n, int v, int ksh, int kk, int n_bra, int
         p.kmeta = ar.template take<KetMeta>(kk_pad);
         p.info = ar.template take<BaseInfo>(1);
         p.bwork = ar.template take<double>(base_work_doubles(n) + 1);
+        // base blocks above 128 (no brute-force tier behind them): work matrices of the pivoted fallback inverse
+        p.gjwork = (n > LUB_MAXN) ? ar.template take<double>(2 * (size_t)n * n) : nullptr;
     }
 }
 
@@ -939,6 +941,48 @@ int wfo_smo_dev(wfo_ctx *ctx, const double *bra_mos, const double *s_ao, const d
 
 /* Newton-Schulz inverse on the DMMA GEMM (replaces np.linalg.inv, pywfo/main.py:303) */
 constexpr int NS_MAX_ITERS = 51;   // enough for cond ~ 1e6; anything slower goes to the pivoted elimination
+}  // extern "C"
+
+// Pivoted Gauss-Jordan inverse of the n x n matrix a (leading dimension lda) on one cooperative grid (csrc/inverse_gj.cuh):
+// a_inv (n x n, contiguous), W and V n x n work matrices.  Queued on st, no synchronisation.  The pivot rows, pivot
+// values and the singular flag stay on the device (*piv_out, *dval_out, *state_out) for the caller to look at.
+static int gj_invert(wfo_ctx *ctx, const double *a, int lda, int n, double *a_inv, double *W, double *V, cudaStream_t st,
+                     int **piv_out, double **dval_out, GjState **state_out) {
+    WFO_CUDA(cudaMemcpy2DAsync(W, (size_t)n * sizeof(double), a, (size_t)lda * sizeof(double), (size_t)n * sizeof(double), n,
+                               cudaMemcpyDeviceToDevice, st));
+    int per_sm = 1;
+    WFO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gj_inverse_kernel, GJ_THREADS, 0));
+    int G = ctx->sm_count * (per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm));
+    if (G > n) G = n;
+    // bookkeeping: pivots, pivot values, candidates, used flags, state
+    const size_t bytes = align_up((size_t)n * 4, 16) + (size_t)n * 8 + (size_t)G * sizeof(GjCand) + align_up((size_t)n, 16) + 16;
+    if (bytes > ctx->gj_bytes) {
+        WFO_CUDA(cudaStreamSynchronize(st));
+        if (ctx->gj_buf) WFO_CUDA(cudaFree(ctx->gj_buf));
+        ctx->gj_buf = nullptr;
+        ctx->gj_bytes = 0;
+        WFO_CUDA(cudaMalloc(&ctx->gj_buf, bytes));
+        ctx->gj_bytes = bytes;
+    }
+    char *q = ctx->gj_buf;
+    int *piv = reinterpret_cast<int *>(q); q += align_up((size_t)n * 4, 16);
+    double *dval = reinterpret_cast<double *>(q); q += (size_t)n * 8;
+    GjCand *cand = reinterpret_cast<GjCand *>(q); q += (size_t)G * sizeof(GjCand);
+    unsigned char *used = reinterpret_cast<unsigned char *>(q); q += align_up((size_t)n, 16);
+    GjState *state = reinterpret_cast<GjState *>(q);
+    int nn_i = n;
+    double *outp = a_inv;
+    void *args[] = {&W, &V, &nn_i, &outp, &piv, &dval, &cand, &used, &state};
+    WFO_CUDA(cudaLaunchCooperativeKernel((void *)gj_inverse_kernel, dim3(G), dim3(GJ_THREADS), args, 0, st));
+    ctx->launches++;
+    if (piv_out) *piv_out = piv;
+    if (dval_out) *dval_out = dval;
+    if (state_out) *state_out = state;
+    return WFO_OK;
+}
+
+extern "C" {
+
 int wfo_inverse_dev(wfo_ctx *ctx, const double *a, int n, double *a_inv, double *work, void *stream) {
     if (!ctx || !a || !a_inv) return set_err(WFO_ERR_ARG, "inverse: NULL argument");
     if (n < 1) return set_err(WFO_ERR_ARG, "inverse: n=%lld", n);
@@ -1010,33 +1054,8 @@ int wfo_inverse_dev(wfo_ctx *ctx, const double *a, int n, double *a_inv, double 
     }
     // ---- fallback: Gauss-Jordan with partial pivoting (what LAPACK's inverse is to the reference)
     {
-        double *W = T, *V = Xb;
-        WFO_CUDA(cudaMemcpyAsync(W, a, nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
-        int per_sm = 1;
-        WFO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gj_inverse_kernel, GJ_THREADS, 0));
-        int G = ctx->sm_count * (per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm));
-        if (G > n) G = n;
-        // bookkeeping behind the Newton-Schulz slots: pivots, pivot values, candidates, used flags, state
-        const size_t bytes = align_up((size_t)n * 4, 16) + (size_t)n * 8 + (size_t)G * sizeof(GjCand) + align_up((size_t)n, 16) + 16;
-        if (bytes > ctx->gj_bytes) {
-            WFO_CUDA(cudaStreamSynchronize(st));
-            if (ctx->gj_buf) WFO_CUDA(cudaFree(ctx->gj_buf));
-            ctx->gj_buf = nullptr;
-            ctx->gj_bytes = 0;
-            WFO_CUDA(cudaMalloc(&ctx->gj_buf, bytes));
-            ctx->gj_bytes = bytes;
-        }
-        char *q = ctx->gj_buf;
-        int *piv = reinterpret_cast<int *>(q); q += align_up((size_t)n * 4, 16);
-        double *dval = reinterpret_cast<double *>(q); q += (size_t)n * 8;
-        GjCand *cand = reinterpret_cast<GjCand *>(q); q += (size_t)G * sizeof(GjCand);
-        unsigned char *used = reinterpret_cast<unsigned char *>(q); q += align_up((size_t)n, 16);
-        GjState *state = reinterpret_cast<GjState *>(q);
-        int nn_i = n;
-        double *outp = a_inv;
-        void *args[] = {&W, &V, &nn_i, &outp, &piv, &dval, &cand, &used, &state};
-        WFO_CUDA(cudaLaunchCooperativeKernel((void *)gj_inverse_kernel, dim3(G), dim3(GJ_THREADS), args, 0, st));
-        ctx->launches++;
+        GjState *state = nullptr;
+        WFO_TRY(gj_invert(ctx, a, n, n, a_inv, T, Xb, st, nullptr, nullptr, &state));
         GjState hs;
         WFO_CUDA(cudaMemcpyAsync(&hs, state, sizeof(hs), cudaMemcpyDeviceToHost, st));
         WFO_CUDA(cudaStreamSynchronize(st));
@@ -1404,8 +1423,8 @@ static int state_overlaps_block(wfo_ctx *ctx, size_t arena_off, const double *s_
         WFO_CUDA(cudaStreamWaitEvent(s2, ctx->ev_fork, 0));     // ... the copy rides on the side stream
         WFO_CUDA(cudaMemcpyAsync(ctx->h_info, p.info, sizeof(BaseInfo), cudaMemcpyDeviceToHost, s2));
         WFO_CUDA(cudaEventRecord(ctx->ev_info, s2));
-        const bool ok = true;   // speculation; checked below
-        if (ok) {
+        // everything behind the base inverse (queued speculatively; queued again if the pivoted fallback had to step in)
+        auto queue_t1 = [&]() -> int {
             const double *Bblk = s_mo + n;                    // occ  x virt
             const double *Cblk = s_mo + (size_t)n * n_mo;     // virt x occ
             if (v > 0) {
@@ -1438,10 +1457,36 @@ static int state_overlaps_block(wfo_ctx *ctx, size_t arena_off, const double *s_
             WFO_PHASE(ctx, st, "t1_fused");
             d00_ptr = &p.info->det;
             used = WFO_TIER_UPDATE;
-        }
+            return WFO_OK;
+        };
+        WFO_TRY(queue_t1());
         WFO_CUDA(cudaEventSynchronize(ctx->ev_info));
         const BaseInfo &hinfo = *ctx->h_info;
-        if (hinfo.singular || !(hinfo.min_piv > 1e-6 * hinfo.max_piv)) {
+        bool bad_base = hinfo.singular || !(hinfo.min_piv > 1e-6 * hinfo.max_piv);
+        if (bad_base && n > LUB_MAXN) {
+            // the blockwise (Schur) inverse pivots inside its 128-blocks only: a well-conditioned base block with a
+            // singular leading half (occupied orbitals reordered between the geometries) fails there although
+            // LAPACK, i.e. the reference, handles it.  Fall back to the pivoted Gauss-Jordan inverse of the whole
+            // block (csrc/inverse_gj.cuh) and queue the rank-update stages again.
+            int *piv = nullptr;
+            double *dval = nullptr;
+            GjState *state = nullptr;
+            WFO_TRY(gj_invert(ctx, s_mo, n_mo, n, p.Ai, p.gjwork, p.gjwork + (size_t)n * n, st, &piv, &dval, &state));
+            gj_info_kernel<<<1, 256, 0, st>>>(piv, dval, n, state, p.info);
+            WFO_LAUNCH_CHECK(ctx);
+            WFO_CUDA(cudaMemcpyAsync(ctx->h_info, p.info, sizeof(BaseInfo), cudaMemcpyDeviceToHost, st));
+            WFO_CUDA(cudaStreamSynchronize(st));
+            bad_base = hinfo.singular || !(hinfo.min_piv > 1e-6 * hinfo.max_piv);
+            if (!bad_base) {
+                if (v > 0) {   // W's D block again (the first pass subtracted garbage from it)
+                    long long wtot = (long long)(v + 1) * (v + 1);
+                    w_init_kernel<<<(unsigned)((wtot + 255) / 256), 256, 0, st>>>(s_mo, n_mo, n, v, p.Wb);
+                    WFO_LAUNCH_CHECK(ctx);
+                }
+                WFO_TRY(queue_t1());
+            }
+        }
+        if (bad_base) {
             used = -1;   // what was queued computes garbage into buffers the brute-force tier rewrites
             if (!may_t0)
                 return set_err(WFO_ERR_SINGULAR,

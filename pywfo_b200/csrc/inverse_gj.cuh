@@ -15,6 +15,7 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "lu_base.cuh"   // BaseInfo
 
 namespace wfo {
 
@@ -145,6 +146,47 @@ gj_inverse_kernel(double *W, double *V, int n, double *__restrict__ out, int *pi
         const int p = piv[k];
         const double rd = 1.0 / dval[k];
         for (int j = tid; j < n; j += GJ_THREADS) out[(size_t)k * n + j] = V[(size_t)p * n + j] * rd;
+    }
+}
+
+// verdict of a pivoted inverse in the form the rank-update tier wants (BaseInfo: det with the sign of the row
+// permutation k -> piv[k], min / max |pivot|, singular flag).  One CTA.
+__global__ void __launch_bounds__(256)
+gj_info_kernel(const int *__restrict__ piv, const double *__restrict__ dval, int n, const GjState *__restrict__ state,
+               BaseInfo *__restrict__ info) {
+    __shared__ double s_det[256], s_min[256], s_max[256];
+    __shared__ int s_inv[256];
+    const int tid = threadIdx.x;
+    const bool sing = state->singular != 0;
+    double det = 1.0, mn = 1e300, mx = 0.0;
+    int inv = 0;
+    if (!sing) {
+        for (int k = tid; k < n; k += 256) {
+            const double d = dval[k];
+            det *= d;
+            mn = fmin(mn, fabs(d));
+            mx = fmax(mx, fabs(d));
+            const int pk = piv[k];
+            for (int j = k + 1; j < n; j++) inv += piv[j] < pk;
+        }
+    }
+    s_det[tid] = det; s_min[tid] = mn; s_max[tid] = mx; s_inv[tid] = inv & 1;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) {
+            s_det[tid] *= s_det[tid + o];
+            s_min[tid] = fmin(s_min[tid], s_min[tid + o]);
+            s_max[tid] = fmax(s_max[tid], s_max[tid + o]);
+            s_inv[tid] ^= s_inv[tid + o];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        info->det = sing ? 0.0 : (s_inv[0] ? -s_det[0] : s_det[0]);
+        info->min_piv = s_min[0];
+        info->max_piv = s_max[0];
+        info->singular = sing ? 1 : 0;
+        info->pad = 0;
     }
 }
 

@@ -717,6 +717,38 @@ def test_base_blocks_larger_than_128(ctx, occ, n_mo):
     assert_parity(got1, one, rtol=1e-9)
 
 
+@pytest.mark.parametrize("occ,n_mo", [(150, 190), (260, 300)])
+def test_base_blocks_larger_than_128_with_reordered_orbitals(ctx, occ, n_mo):
+    """occupied orbitals reordered between the two geometries make the LEADING half of
+    S_MO[:occ,:occ] singular although the block itself is perfectly conditioned; LAPACK (the reference) does
+    not care.  The blockwise Schur inverse does (it pivots inside 128-blocks only), so the call falls back to
+    the pivoted Gauss-Jordan inverse of the whole block and still takes the rank-update tier."""
+    rng = np.random.default_rng(occ)
+    S = np.eye(n_mo) + 0.02 * rng.standard_normal((n_mo, n_mo))   # MO overlaps of two close geometries
+    perm = np.arange(n_mo)
+    perm[:occ] = np.roll(perm[:occ], occ // 2 + 3)       # ket occupied orbitals rotated: A = (near identity) x permutation
+    S = S[:, perm]
+    h = occ // 2
+    S[:h - 4, :h - 4] = 0.0                              # ... whose leading half is exactly rank deficient
+    assert np.linalg.cond(S[:occ, :occ]) < 50 and np.linalg.matrix_rank(S[:h, :h]) < h
+    bra, Cb, ket, Ck = _random_tables(rng, occ, n_mo - occ, 60, 40, 3, 4)
+    want = orc.state_overlaps_closed_form(S, occ, [tuple(e) for e in bra], Cb, [tuple(e) for e in ket], Ck, 1.0)
+    for tier in ("update", "auto"):
+        got = ctx.state_overlaps_host(S, occ, bra, Cb, ket, Ck, tier=tier)
+        assert ctx.last_tier() == 1
+        assert_parity(got, want, rtol=1e-9)
+    k, l = tuple(bra[2]), tuple(ket[7])                   # one pair directly against LAPACK's determinant
+    one = orc.state_overlaps_bruteforce(S, occ, [k], np.ones((1, 1)), [l], np.ones((1, 1)), 1.0)
+    got1 = ctx.state_overlaps_host(S, occ, bra[2:3], np.ones((1, 1)), ket[7:8], np.ones((1, 1)), tier="update")
+    assert_parity(got1, one, rtol=1e-9)
+    # a truly singular base block is still reported
+    from pywfo_b200 import _lib
+    S2 = S.copy()
+    S2[5, :occ] = S2[9, :occ]
+    with pytest.raises(_lib.WfoError):
+        ctx.state_overlaps_host(S2, occ, bra, Cb, ket, Ck, tier="update")
+
+
 def test_raw_ci_entry_point_from_device_buffers(ctx):
     """wfo_overlaps_ci_dev: orbitals and CI tensors already in HBM (torch tensors as plain memory)."""
     import torch
