@@ -1025,7 +1025,9 @@ int wfo_inverse_dev(wfo_ctx *ctx, const double *a, int n, double *a_inv, double 
     bool converged = false, give_up = false;
     double prev = 1e300;
     while (it < NS_MAX_ITERS && !converged && !give_up) {
-        const int batch = 3;   // iterations between two looks at the residuals
+        // iterations between two looks at the residuals; the first look comes after ONE: orthonormal MO matrices
+        // (A^T A = I) start at the answer, and four GEMMs on the way to the first synchronisation are 30-50 us
+        const int batch = (it == 0) ? 1 : 3;
         for (int b = 0; b < batch && it < NS_MAX_ITERS; b++, it++) {
             // T = A X; residual max|T - I| -> slots[2 + it], Xn = X; Xn = 2 Xn - X T
             WFO_TRY(gemm(ctx, false, false, n, n, n, 1.0, a, n, X, n, 0.0, T, n, 0, 0, st));
