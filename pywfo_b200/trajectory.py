@@ -26,6 +26,14 @@ def consecutive_pairs(n_cycles: int, stride: int = 1) -> np.ndarray:
     return np.stack([i, i + stride], axis=1).astype(np.int32)
 
 
+def referenced_cycles(pairs: np.ndarray):
+    """The cycles a set of pairs touches and the pairs renumbered into that subset: a rank that is dealt a few
+    pairs of a long trajectory uploads (and inverts) only those cycles."""
+    pairs = np.asarray(pairs, dtype=np.int32).reshape(-1, 2)
+    cycles, inverse = np.unique(pairs, return_inverse=True)
+    return cycles.astype(np.int64), inverse.reshape(-1, 2).astype(np.int32)
+
+
 def trajectory_overlaps(mo_coeffs, ci_coeffs, occ, ci_thresh=1e-4, ao_ovlps="ket", pairs=None, semantics="cache",
                         tier="auto", device=None):
     """``out[p] = overlaps_cache(mo[i], mo[j], ci[i], ci[j], occ, ci_thresh, ao_ovlps)`` for
@@ -51,7 +59,12 @@ def trajectory_overlaps(mo_coeffs, ci_coeffs, occ, ci_thresh=1e-4, ao_ovlps="ket
 
     def compute(idx, rank, world):
         try:
-            return ctx.trajectory_ci_host(mos, ci, occ, pr[idx], ci_thresh, sem, tier, side, rank=rank, world=world)[0]
+            cycles, local = referenced_cycles(pr[idx])
+            if cycles.size == mos.shape[0]:
+                sub_mos, sub_ci = mos, ci
+            else:   #  only what this rank's pairs need goes to the device
+                sub_mos, sub_ci = np.ascontiguousarray(mos[cycles]), np.ascontiguousarray(ci[cycles])
+            return ctx.trajectory_ci_host(sub_mos, sub_ci, occ, local, ci_thresh, sem, tier, side, rank=rank, world=world)[0]
         except _lib.WfoError as exc:
             if exc.code != _lib.ERR_NOCONV:
                 raise

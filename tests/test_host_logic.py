@@ -120,3 +120,17 @@ def test_excitation_tables_are_range_checked():
     for bad in ([5, 0], [0, 19], [-1, 3], [2, -1], [7, 40]):
         with pytest.raises(IndexError):
             _check_exc("ket", np.array([[1, 1], bad], dtype=np.int32), 5, 19)
+
+
+def test_trajectory_pairs_are_renumbered_into_the_cycles_they_touch():
+    """a rank uploads only the cycles its pairs reference."""
+    from pywfo_b200.trajectory import consecutive_pairs, referenced_cycles
+    pairs = np.array([[7, 2], [2, 3], [9, 7]], dtype=np.int32)
+    cycles, local = referenced_cycles(pairs)
+    assert cycles.tolist() == [2, 3, 7, 9]
+    assert np.array_equal(cycles[local], pairs)
+    allp = consecutive_pairs(9)
+    cyc, loc = referenced_cycles(allp[np.arange(1, 8, 3)])       # the pairs rank 1 of 3 is dealt
+    assert cyc.tolist() == [1, 2, 4, 5, 7, 8] and np.array_equal(cyc[loc], allp[[1, 4, 7]])
+    cyc, loc = referenced_cycles(allp)
+    assert cyc.size == 9 and np.array_equal(loc, allp)
