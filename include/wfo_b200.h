@@ -89,7 +89,9 @@ int wfo_smo_inv_dev(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos, 
  * stream while the rest of S_MO is still being multiplied; the next wfo_state_overlaps_dev call on THAT s_mo buffer
  * with that n_occ (same stream, s_mo untouched in between) picks the inverse up instead of computing it behind
  * S_MO.  Only n_occ <= 128 is started early; results agree with the unhinted path to rounding (the base block is
- * multiplied with another tile shape).  The raw-CI entry points do this on their own. */
+ * multiplied with another tile shape).  The raw-CI entry points do this on their own.  Not for streams under
+ * CUDA-graph capture: the early inverse kernel is launched ahead of its input and waits on the device for a flag
+ * (bounded), which relies on the two launches running concurrently. */
 int wfo_set_occ_hint(wfo_ctx *ctx, int n_occ);
 /* a_inv = a^-1 (n x n), replaces np.linalg.inv in pywfo/main.py:303 (98, 212).
  * n <= 128: one launch of the register-resident Gauss-Jordan inverse with partial pivoting (csrc/lu_base.cuh).
