@@ -1157,6 +1157,8 @@ int wfo_smo_inv_dev(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos, 
         ctx->pre_n = h;
         ctx->pre_Ai = Ai;
         ctx->pre_info = info;
+        ctx->pre_A = A;
+        ctx->pre_nslab = nslab;
     }
     if (bra_mos == ket_mos) {
         WFO_TRY(gemm(ctx, false, false, n, n, n, 1.0, bra_mos, n, c_inv, n, 0.0, P, n, 0, 0, st));
@@ -1464,6 +1466,22 @@ static int state_overlaps_block(wfo_ctx *ctx, size_t arena_off, const double *s_
         WFO_TRY(queue_t1());
         WFO_CUDA(cudaEventSynchronize(ctx->ev_info));
         const BaseInfo &hinfo = *ctx->h_info;
+        if (hinfo.singular == 2) {
+            // the early inverse kernel (wfo_smo_inv_dev with the occupation hint) gave up waiting for its input:
+            // kernels do not run concurrently here (a profiler, CUDA_LAUNCH_BLOCKING, ...).  Same input, same
+            // kernel, now behind the producer; then the rank-update stages again.
+            base_inverse_kernel<<<1, LUB_THREADS, lub_smem_bytes(n), st>>>(ctx->pre_A, n, n, p.Ai, n, p.info, ctx->pre_nslab,
+                                                                        (long long)n * n, nullptr, 0);
+            WFO_LAUNCH_CHECK(ctx);
+            WFO_CUDA(cudaMemcpyAsync(ctx->h_info, p.info, sizeof(BaseInfo), cudaMemcpyDeviceToHost, st));
+            WFO_CUDA(cudaStreamSynchronize(st));
+            if (v > 0) {   // W's D block again (the first pass subtracted garbage from it)
+                long long wtot = (long long)(v + 1) * (v + 1);
+                w_init_kernel<<<(unsigned)((wtot + 255) / 256), 256, 0, st>>>(s_mo, n_mo, n, v, p.Wb);
+                WFO_LAUNCH_CHECK(ctx);
+            }
+            WFO_TRY(queue_t1());
+        }
         bool bad_base = hinfo.singular || !(hinfo.min_piv > 1e-6 * hinfo.max_piv);
         if (bad_base && n > LUB_MAXN) {
             // the blockwise (Schur) inverse pivots inside its 128-blocks only: a well-conditioned base block with a

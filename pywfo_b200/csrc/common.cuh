@@ -91,6 +91,8 @@ struct wfo_ctx {
     const double *pre_smo;   // the S_MO buffer the stashed inverse belongs to (valid until consumed)
     int pre_n;
     double *pre_Ai;
+    const double *pre_A;     // the base block as the early chain multiplied it (K slabs), input of the early kernel AND its guard
+    int pre_nslab;
     wfo::BaseInfo *pre_info;
     cudaEvent_t ev_fork, ev_join;
     double *ns_slots;      // device: norms + per-iteration residuals of the Newton-Schulz inverse (128 doubles)

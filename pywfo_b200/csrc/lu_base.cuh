@@ -325,21 +325,32 @@ __global__ void __launch_bounds__(LUB_THREADS)
 base_inverse_kernel(const double *__restrict__ A_src, int ld_src, int n, double *__restrict__ Ai_out, int ld_out,
                     BaseInfo *__restrict__ info, int n_slabs, long long slab_stride, const int *wait_flag, int wait_value) {
     extern __shared__ __align__(16) double lub_tile[];    // n x LUB_LDS
+    __shared__ int go_on;
     const int tid = threadIdx.x;
     if (wait_flag) {
         // launched AHEAD of its input (wfo_smo_inv_dev's early base block): the CTA sits on an SM of its own
         // (its shared-memory request keeps the GEMM CTAs away, whose FP64 traffic would slow this latency-bound
-        // kernel by half) and waits until the producer stream raises the flag.  Bounded: ~2 s, then it runs
-        // on whatever is there and the consumer's verdict check (non-finite pivots) rejects the result.
+        // kernel by half) and waits until the producer stream raises the flag.  Bounded to a few ms: where kernels
+        // do not run concurrently (profilers, CUDA_LAUNCH_BLOCKING, a device saturated by somebody else) the
+        // flag cannot come; the kernel then leaves WITHOUT a result (info->singular = 2) and the consumer, which
+        // looks at the verdict anyway, runs the inverse again behind the producer.
         if (tid == 0) {
-            int seen = 0;
-            for (long long spin = 0; spin < (1ll << 24); spin++) {
+            int seen = 0, ok = 0;
+            for (int spin = 0; spin < 4096 && !ok; spin++) {
                 asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(seen) : "l"(wait_flag) : "memory");
-                if (seen == wait_value) break;
-                __nanosleep(100);
+                ok = (seen == wait_value);
+                if (!ok) __nanosleep(200);
+            }
+            go_on = ok;
+            if (!ok) {
+                info->det = 0.0;
+                info->min_piv = 0.0;
+                info->max_piv = 0.0;
+                info->singular = 2;
             }
         }
         __syncthreads();
+        if (!go_on) return;
     }
     // coalesced load through the staging tile; A may arrive as the K slabs of a split-K product (summed in fixed order)
     for (int idx = tid; idx < n * n; idx += LUB_THREADS) {
