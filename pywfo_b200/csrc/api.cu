@@ -1108,7 +1108,32 @@ int wfo_smo_inv_dev(wfo_ctx *ctx, const double *bra_mos, const double *ket_mos, 
     const ptrdiff_t dbytes = reinterpret_cast<const char *>(ket_mos) - reinterpret_cast<const char *>(bra_mos);
     ctx->pre_smo = nullptr;
     const int h = ctx->occ_hint;
-    if (h >= 1 && h <= LUB_MAXN && h <= n && n >= 96) {   // (tiny matrices: the five extra launches cost more than they hide)
+    if (h >= 1 && h <= LUB_MAXN && h <= n && n >= 96 && ctx->pre_probe == 0) {
+        // once per context: the early chain needs its waiting kernel and the producers behind it to run concurrently
+        int *d_res = nullptr, h_res = 0;
+        WFO_CUDA(cudaMalloc(&d_res, sizeof(int)));
+        for (int pass = 0; pass < 2; pass++) {
+            // pass 0 loads the two kernels (lazy module loading takes longer than the probe waits): flag first
+            const int epoch = ++ctx->pre_epoch;
+            if (pass == 0) {
+                set_flag_kernel<<<1, 32, 0, ctx->stream3>>>(ctx->pre_flag, epoch);
+                WFO_LAUNCH_CHECK(ctx);
+                WFO_CUDA(cudaStreamSynchronize(ctx->stream3));
+            }
+            concurrency_probe_kernel<<<1, 32, 0, ctx->stream4>>>(ctx->pre_flag, epoch, d_res);
+            WFO_LAUNCH_CHECK(ctx);
+            if (pass == 1) {
+                set_flag_kernel<<<1, 32, 0, ctx->stream3>>>(ctx->pre_flag, epoch);
+                WFO_LAUNCH_CHECK(ctx);
+            }
+            WFO_CUDA(cudaStreamSynchronize(ctx->stream3));
+            WFO_CUDA(cudaStreamSynchronize(ctx->stream4));
+        }
+        WFO_CUDA(cudaMemcpy(&h_res, d_res, sizeof(int), cudaMemcpyDeviceToHost));
+        WFO_CUDA(cudaFree(d_res));
+        ctx->pre_probe = h_res ? 1 : -1;
+    }
+    if (h >= 1 && h <= LUB_MAXN && h <= n && n >= 96 && ctx->pre_probe > 0) {   // (tiny matrices: the five extra launches cost more than they hide)
         // the base block first, on its own stream: A = (bra[:h] Cinv)(ket[:h] Cinv)^T, then its inverse (one CTA for
         // ~0.8 us per column) next to the full products below instead of behind them
         const size_t hn = (size_t)h * n, hh = (size_t)h * h;

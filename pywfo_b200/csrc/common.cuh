@@ -84,6 +84,7 @@ struct wfo_ctx {
     cudaStream_t stream3, stream4;
     int *pre_flag;           // device: raised (to pre_epoch) when the base block is ready for the waiting inverse kernel
     int pre_epoch;
+    int pre_probe;           // 0 not probed yet, 1 kernels on two streams run concurrently (early base block usable), -1 they do not
     cudaEvent_t ev_pre_in, ev_pre;
     int occ_hint;
     char *pre_buf;

@@ -431,6 +431,20 @@ cofactor_rows_kernel(const double *__restrict__ S, int ld_s, int n, const int32_
     }
 }
 
+// one-time probe (wfo_smo_inv_dev): is a kernel that waits on the device for a flag reached by a kernel launched
+// AFTER it on another stream?  (Not under profilers that serialise kernels, CUDA_LAUNCH_BLOCKING, ...)
+__global__ void concurrency_probe_kernel(const int *flag, int value, int *result) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int seen = 0, ok = 0;
+        for (int spin = 0; spin < 4096 && !ok; spin++) {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(seen) : "l"(flag) : "memory");
+            ok = (seen == value);
+            if (!ok) __nanosleep(200);
+        }
+        *result = ok;
+    }
+}
+
 __global__ void set_flag_kernel(int *flag, int value) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         __threadfence();
