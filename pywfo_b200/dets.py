@@ -17,12 +17,17 @@ from . import _lib, dist
 from .excitations import build_tables
 
 
-def precompute(bra_blocks, ket_blocks, mo_ovlps):
+def _blocks_of(blocked):
+    """Index lists from the reference's argument (a ``BlockResult`` with ``.blocks``, pywfo/dets.py:114-156) or from
+    a plain (n_blocks, n) array of index lists."""
+    return np.asarray(getattr(blocked, "blocks", blocked), dtype=np.int32)
+
+
+def precompute(bra_blocked, ket_blocked, mo_ovlps):
     """Determinants of ``mo_ovlps[bra_block][:, ket_block]`` for all block pairs
-    (pywfo/dets.py:191-198), one pivoted LU per pair on the GPU."""
-    rows = np.asarray(bra_blocks, dtype=np.int32)
-    cols = np.asarray(ket_blocks, dtype=np.int32)
-    return _lib.context().det_table_host(mo_ovlps, rows, cols)
+    (pywfo/dets.py:191-198), one pivoted LU per pair on the GPU.  Arguments as upstream (``BlockResult`` tuples
+    from ``block_dets``) or plain index-list arrays."""
+    return _lib.context().det_table_host(mo_ovlps, _blocks_of(bra_blocked), _blocks_of(ket_blocked))
 
 
 def wfoverlap(bra_mos, ket_mos, bra_ci, ket_ci, ci_thresh, S_AO, closed_shell=True, debug=True,

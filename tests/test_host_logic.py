@@ -134,3 +134,15 @@ def test_trajectory_pairs_are_renumbered_into_the_cycles_they_touch():
     assert cyc.tolist() == [1, 2, 4, 5, 7, 8] and np.array_equal(cyc[loc], allp[[1, 4, 7]])
     cyc, loc = referenced_cycles(allp)
     assert cyc.size == 9 and np.array_equal(loc, allp)
+
+
+def test_precompute_accepts_the_reference_block_tuples():
+    """pywfo.dets.precompute takes BlockResult tuples (dets.py:114-156, 191-198); plain index arrays work too."""
+    from collections import namedtuple
+    from pywfo_b200.dets import _blocks_of
+    BlockResult = namedtuple("BlockResult", "block_num super_block_num blocks block_map super_map ci_block_map sort_inds")
+    blocks = [[0, 1, 2], [0, 1, 5], [0, 2, 7]]
+    res = BlockResult(3, 2, blocks, [0, 1, 2], [0, 2], np.array([0, 1, 2]), [0, 1, 2])
+    assert np.array_equal(_blocks_of(res), np.array(blocks, dtype=np.int32))
+    assert np.array_equal(_blocks_of(np.array(blocks)), np.array(blocks, dtype=np.int32))
+    assert _blocks_of(res).dtype == np.int32
